@@ -1,0 +1,119 @@
+/* nudge_b200 — C ABI of the B200-native rigid-body simulation step (drop-in for rasmusbarr/nudge's hot path).
+ *
+ * Every entry point replaces one reference interface (file:line into /root/reference):
+ *
+ *   nb_collide                      <- nudge::collide                    nudge.h:134, nudge.cpp:3000-4009
+ *   nb_read_cached_impulses         <- nudge::read_cached_impulses       nudge.h:136, nudge.cpp:4021-4108
+ *   nb_write_cached_impulses        <- nudge::write_cached_impulses      nudge.h:138, nudge.cpp:4110-4158
+ *   nb_setup_contact_constraints    <- nudge::setup_contact_constraints  nudge.h:140, nudge.cpp:4170-4638
+ *   nb_apply_impulses               <- nudge::apply_impulses             nudge.h:142, nudge.cpp:4640-4855
+ *   nb_update_cached_impulses       <- nudge::update_cached_impulses     nudge.h:144, nudge.cpp:4857-4884
+ *   nb_advance                      <- nudge::advance                    nudge.h:146, nudge.cpp:4886-4926
+ *   nb_apply_gravity_damping        <- the user loop of example/main.cpp:291-305
+ *   nb_step                         <- simulate(), example/main.cpp:274-328 (one sub-step)
+ *
+ * Data layout: the reference's caller-owned SoA structs (nudge.h:29-129) with every index-carrying field
+ * widened to 32 bits (the reference caps at 8192 colliders / 65535 bodies, nudge.cpp:3010, nudge.h:68-71):
+ *
+ *   BodyPair{uint16 a,b}                             -> nb_body_pair{uint32 a,b}
+ *   collider tag uint16                              -> uint32
+ *   contact tag uint64 = feature | A<<32 | B<<48     -> tags[i] = A | (uint64)B<<32 ; features[i] = feature
+ *   sleeping pair uint32 = X | Y<<16                 -> uint64 = X | (uint64)Y<<32
+ *   ActiveBodies.indices uint16                      -> uint32
+ *
+ * The simulation state is DEVICE RESIDENT inside an nb_context (HBM); nb_upload_* / nb_download_* move the
+ * caller's host arrays across.  All calls are asynchronous on the given CUDA stream unless stated; no call
+ * falls back to the CPU — if the GPU or the CUDA extension is missing, nb_create fails.
+ * The uint16 drop-in with the exact nudge.h signatures lives in nudge_b200/csrc/nudge_compat.cpp.
+ *
+ * Return value: 0 on success, otherwise a negative nb_status; nb_last_error() gives the text.
+ */
+#ifndef NUDGE_B200_H
+#define NUDGE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float position[3]; uint32_t body; float rotation[4]; } nb_transform;          /* nudge.h:34-38 */
+typedef struct { float inertia_inverse[3]; float mass_inverse; } nb_body_properties;            /* nudge.h:40-43 */
+typedef struct { float velocity[3]; float unused0; float angular_velocity[3]; float unused1; } nb_body_momentum; /* nudge.h:45-50 */
+typedef struct { float radius; } nb_sphere_collider;                                            /* nudge.h:52-54 */
+typedef struct { float size[3]; float unused; } nb_box_collider;                                /* nudge.h:56-59 */
+typedef struct { float position[3]; float penetration; float normal[3]; float friction; } nb_contact; /* nudge.h:61-66 */
+typedef struct { uint32_t a, b; } nb_body_pair;                                                 /* nudge.h:68-71, widened */
+typedef struct { float impulse[3]; float unused; } nb_cached_impulse;                           /* nudge.h:109-112 */
+
+typedef struct {                                                                                /* nudge.h:73-82 */
+	nb_contact* data; nb_body_pair* bodies; uint64_t* tags; uint32_t* features;
+	uint32_t capacity, count;
+	uint64_t* sleeping_pairs; uint32_t sleeping_count;
+} nb_contact_data;
+
+typedef struct { uint32_t* tags; nb_box_collider* data; nb_transform* transforms; uint32_t count; } nb_box_colliders;
+typedef struct { uint32_t* tags; nb_sphere_collider* data; nb_transform* transforms; uint32_t count; } nb_sphere_colliders;
+typedef struct { nb_box_colliders boxes; nb_sphere_colliders spheres; } nb_collider_data;        /* nudge.h:84-98 */
+typedef struct { nb_transform* transforms; nb_body_properties* properties; nb_body_momentum* momentum; uint8_t* idle_counters; uint32_t count; } nb_body_data; /* nudge.h:100-106 */
+typedef struct { nb_body_pair* data; uint32_t count; } nb_body_connections;                      /* nudge.h:108-111 */
+typedef struct { uint64_t* tags; uint32_t* features; nb_cached_impulse* data; uint32_t capacity, count; } nb_contact_cache; /* nudge.h:114-119 */
+typedef struct { uint32_t* indices; uint32_t capacity, count; } nb_active_bodies;                /* nudge.h:121-125 */
+
+typedef struct nb_context nb_context;
+
+typedef struct {
+	uint32_t max_bodies, max_boxes, max_spheres, max_connections;
+	uint32_t max_pairs;     /* broadphase pairs (about 7 per collider in a pile); 0 = 16 per collider */
+	uint32_t max_contacts;  /* also the contact-cache capacity; 0 = 24 per body */
+	int device;             /* CUDA device ordinal */
+} nb_config;
+
+enum nb_status { NB_OK = 0, NB_ERR_CUDA = -1, NB_ERR_CAPACITY = -2, NB_ERR_ARGUMENT = -3, NB_ERR_OVERFLOW = -4 };
+
+/* Device counters of the last step (copied by nb_download_counts; synchronises the stream). */
+typedef struct {
+	uint32_t pairs, live_pairs, contacts, sleeping, active, cache, culled, batches, levels, overflow;
+} nb_counts;
+
+int nb_create(const nb_config* config, nb_context** out);
+void nb_destroy(nb_context* ctx);
+const char* nb_last_error(const nb_context* ctx);
+
+/* Host <-> HBM.  Counts in the structs say how many rows to move; pointers are HOST pointers. */
+int nb_upload_bodies(nb_context*, const nb_body_data* host, void* stream);
+int nb_upload_colliders(nb_context*, const nb_collider_data* host, void* stream);
+int nb_upload_connections(nb_context*, const nb_body_connections* host, void* stream);
+int nb_upload_cache(nb_context*, const nb_contact_cache* host, void* stream);
+int nb_download_bodies(nb_context*, nb_body_data* host, void* stream);
+int nb_download_contacts(nb_context*, nb_contact_data* host, nb_active_bodies* host_active, void* stream); /* synchronises */
+int nb_download_cache(nb_context*, nb_contact_cache* host, void* stream);                                  /* synchronises */
+int nb_download_counts(nb_context*, nb_counts* out, void* stream);                                         /* synchronises */
+int nb_upload_momentum(nb_context*, const nb_body_momentum* host, uint32_t count, void* stream);
+int nb_upload_transforms(nb_context*, const nb_transform* host, uint32_t count, void* stream);
+int nb_download_momentum(nb_context*, nb_body_momentum* host, uint32_t count, void* stream);
+int nb_download_transforms(nb_context*, nb_transform* host, uint32_t count, void* stream);
+
+/* The simulation step, device resident.  Same order of calls as example/main.cpp:274-328. */
+int nb_collide(nb_context*, void* stream);
+int nb_apply_gravity_damping(nb_context*, float time_step, float gravity, float damping, void* stream);
+int nb_read_cached_impulses(nb_context*, void* stream);
+int nb_setup_contact_constraints(nb_context*, void* stream);
+int nb_apply_impulses(nb_context*, uint32_t sweeps, void* stream);  /* `sweeps` back-to-back calls of nudge::apply_impulses */
+int nb_update_cached_impulses(nb_context*, void* stream);
+int nb_write_cached_impulses(nb_context*, void* stream);
+int nb_advance(nb_context*, float time_step, void* stream);
+int nb_step(nb_context*, float time_step, uint32_t iterations, float gravity, float damping, void* stream);
+
+/* Kernel-launch counter (every kernel this library launches increments it) and named device buffers for parity tests. */
+uint64_t nb_launch_count(const nb_context*);
+int nb_debug_read(nb_context*, const char* name, void* dst, size_t max_bytes, size_t* bytes, void* stream); /* synchronises */
+
+/* rcpps / rsqrtps model: tables are sampled from the host CPU in nb_create. */
+int nb_debug_rcp(nb_context*, const float* x, float* y, uint32_t n, int rsqrt);  /* runs the device LUT path; host pointers */
+int nb_lut_model_exact(const nb_context*);  /* 1 if the host CPU's rcpps/rsqrtps match the truncated-mantissa model on 2^20 probes */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,208 @@
+"""nudge_b200 — B200-native rigid-body simulation step, drop-in for rasmusbarr/nudge's hot path.
+
+This package is only the Python binding used by tests and bench.py: it loads the C-ABI shared library
+(include/nudge_b200.h, built by nudge_b200/csrc/build.sh) with ctypes and mirrors the reference's seven calls
+(nudge.h:134-146) on a device-resident simulation.  There is no CPU path: importing works without a GPU
+(so the symbol check can run), creating a `Sim` does not."""
+import ctypes as C
+import os
+import numpy as np
+from . import abi, scenes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libnudge_b200.so")
+
+EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_upload_colliders", "nb_upload_connections", "nb_upload_cache",
+           "nb_download_bodies", "nb_download_contacts", "nb_download_cache", "nb_download_counts", "nb_upload_momentum", "nb_upload_transforms",
+           "nb_download_momentum", "nb_download_transforms", "nb_collide", "nb_apply_gravity_damping", "nb_read_cached_impulses",
+           "nb_setup_contact_constraints", "nb_apply_impulses", "nb_update_cached_impulses", "nb_write_cached_impulses", "nb_advance", "nb_step",
+           "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact"]
+
+
+class Config(C.Structure):
+    _fields_ = [("max_bodies", C.c_uint32), ("max_boxes", C.c_uint32), ("max_spheres", C.c_uint32), ("max_connections", C.c_uint32),
+                ("max_pairs", C.c_uint32), ("max_contacts", C.c_uint32), ("device", C.c_int)]
+
+
+class Counts(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("pairs", "live_pairs", "contacts", "sleeping", "active", "cache", "culled", "batches", "levels", "overflow")]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads the CUDA extension; raises if it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("nudge_b200: %s is missing — run nudge_b200/csrc/build.sh (or __graft_entry__.build()); there is no CPU path" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        V = C.c_void_p
+        lib.nb_create.argtypes = [V, V]
+        lib.nb_destroy.argtypes = [V]
+        lib.nb_last_error.argtypes = [V]; lib.nb_last_error.restype = C.c_char_p
+        for f in ("nb_upload_bodies", "nb_upload_colliders", "nb_upload_connections", "nb_upload_cache", "nb_download_bodies", "nb_download_cache", "nb_download_counts"):
+            getattr(lib, f).argtypes = [V, V, V]
+        lib.nb_download_contacts.argtypes = [V, V, V, V]
+        for f in ("nb_upload_momentum", "nb_upload_transforms", "nb_download_momentum", "nb_download_transforms"):
+            getattr(lib, f).argtypes = [V, V, C.c_uint32, V]
+        for f in ("nb_collide", "nb_read_cached_impulses", "nb_setup_contact_constraints", "nb_update_cached_impulses", "nb_write_cached_impulses"):
+            getattr(lib, f).argtypes = [V, V]
+        lib.nb_apply_gravity_damping.argtypes = [V, C.c_float, C.c_float, C.c_float, V]
+        lib.nb_apply_impulses.argtypes = [V, C.c_uint32, V]
+        lib.nb_advance.argtypes = [V, C.c_float, V]
+        lib.nb_step.argtypes = [V, C.c_float, C.c_uint32, C.c_float, C.c_float, V]
+        lib.nb_launch_count.argtypes = [V]; lib.nb_launch_count.restype = C.c_uint64
+        lib.nb_debug_read.argtypes = [V, C.c_char_p, V, C.c_size_t, V, V]
+        lib.nb_debug_rcp.argtypes = [V, V, V, C.c_uint32, C.c_int]
+        lib.nb_lut_model_exact.argtypes = [V]
+        _lib = lib
+    return _lib
+
+
+class NudgeError(RuntimeError):
+    pass
+
+
+class Sim(abi.HostState):
+    """Device-resident simulation mirroring the reference's call sequence (example/main.cpp:274-328).
+
+    Host arrays (self.transforms, self.momentum, ...) are the caller-owned copies; `upload()` / `download_bodies()`
+    move them across.  `stream` is a raw cudaStream_t (0 = default stream)."""
+
+    def __init__(self, scene, contact_capacity=None, pair_capacity=None, device=0, stream=0):
+        super().__init__(scene, contact_capacity)
+        self.lib = load_library()
+        self.stream = C.c_void_p(stream)
+        cfg = Config(scene.n_bodies, scene.n_boxes, scene.n_spheres, max(1, len(scene.connections)),
+                     pair_capacity or max(4096, 16 * scene.n_colliders), self.cap, device)
+        self.ctx = C.c_void_p()
+        r = self.lib.nb_create(C.byref(cfg), C.byref(self.ctx))
+        if r != 0:
+            msg = self.lib.nb_last_error(self.ctx).decode() if self.ctx else "nb_create failed"
+            raise NudgeError("nb_create: %s (%d)" % (msg, r))
+        self.upload()
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.nb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, r, what):
+        if r != 0:
+            raise NudgeError("%s: %s (%d)" % (what, self.lib.nb_last_error(self.ctx).decode(), r))
+
+    # ---- host <-> HBM ----
+    def upload(self):
+        self._ck(self.lib.nb_upload_bodies(self.ctx, C.byref(self.bodies), self.stream), "nb_upload_bodies")
+        self._ck(self.lib.nb_upload_colliders(self.ctx, C.byref(self.colliders), self.stream), "nb_upload_colliders")
+        self._ck(self.lib.nb_upload_connections(self.ctx, C.byref(self.conn), self.stream), "nb_upload_connections")
+        self._ck(self.lib.nb_upload_cache(self.ctx, C.byref(self.cache), self.stream), "nb_upload_cache")
+
+    def upload_bodies(self):
+        self._ck(self.lib.nb_upload_bodies(self.ctx, C.byref(self.bodies), self.stream), "nb_upload_bodies")
+
+    def upload_cache(self):
+        self._ck(self.lib.nb_upload_cache(self.ctx, C.byref(self.cache), self.stream), "nb_upload_cache")
+
+    def download_bodies(self):
+        self._ck(self.lib.nb_download_bodies(self.ctx, C.byref(self.bodies), self.stream), "nb_download_bodies")
+
+    def download_contacts(self):
+        self.contacts.capacity = self.cap
+        self.active.capacity = self.scene.n_bodies
+        self._ck(self.lib.nb_download_contacts(self.ctx, C.byref(self.contacts), C.byref(self.active), self.stream), "nb_download_contacts")
+
+    def download_cache(self):
+        self.cache.capacity = self.cap
+        self._ck(self.lib.nb_download_cache(self.ctx, C.byref(self.cache), self.stream), "nb_download_cache")
+
+    def counts(self):
+        c = Counts()
+        self._ck(self.lib.nb_download_counts(self.ctx, C.byref(c), self.stream), "nb_download_counts")
+        return c
+
+    # ---- the seven calls + the user loop ----
+    def collide(self):
+        self._ck(self.lib.nb_collide(self.ctx, self.stream), "nb_collide")
+
+    def apply_gravity_damping(self):
+        s = self.scene
+        self._ck(self.lib.nb_apply_gravity_damping(self.ctx, float(s.time_step), float(s.gravity), float(s.damping), self.stream), "nb_apply_gravity_damping")
+
+    def read_cached_impulses(self):
+        self._ck(self.lib.nb_read_cached_impulses(self.ctx, self.stream), "nb_read_cached_impulses")
+
+    def setup_contact_constraints(self):
+        self._ck(self.lib.nb_setup_contact_constraints(self.ctx, self.stream), "nb_setup_contact_constraints")
+
+    def apply_impulses(self, sweeps=1):
+        self._ck(self.lib.nb_apply_impulses(self.ctx, int(sweeps), self.stream), "nb_apply_impulses")
+
+    def update_cached_impulses(self):
+        self._ck(self.lib.nb_update_cached_impulses(self.ctx, self.stream), "nb_update_cached_impulses")
+
+    def write_cached_impulses(self):
+        self._ck(self.lib.nb_write_cached_impulses(self.ctx, self.stream), "nb_write_cached_impulses")
+
+    def advance(self):
+        self._ck(self.lib.nb_advance(self.ctx, float(self.scene.time_step), self.stream), "nb_advance")
+
+    def step(self):
+        s = self.scene
+        self._ck(self.lib.nb_step(self.ctx, float(s.time_step), int(s.iterations), float(s.gravity), float(s.damping), self.stream), "nb_step")
+
+    def launch_count(self):
+        return int(self.lib.nb_launch_count(self.ctx))
+
+    def lut_model_exact(self):
+        return bool(self.lib.nb_lut_model_exact(self.ctx))
+
+    # ---- parity-test introspection ----
+    def debug(self, name, dtype):
+        n = C.c_size_t(0)
+        self._ck(self.lib.nb_debug_read(self.ctx, name.encode(), None, 0, C.byref(n), self.stream), "nb_debug_read")
+        buf = np.zeros(max(n.value, 1), np.uint8)
+        if n.value:
+            self._ck(self.lib.nb_debug_read(self.ctx, name.encode(), abi.ptr(buf), n.value, C.byref(n), self.stream), "nb_debug_read")
+        return buf[:n.value].view(dtype)
+
+    def debug_scalar(self, name):
+        v = np.zeros(1, np.uint32); n = C.c_size_t(0)
+        self._ck(self.lib.nb_debug_read(self.ctx, name.encode(), abi.ptr(v), 4, C.byref(n), self.stream), "nb_debug_read")
+        return int(v[0])
+
+    def device_rcp(self, x, rsqrt=False):
+        x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x)
+        self._ck(self.lib.nb_debug_rcp(self.ctx, abi.ptr(x), abi.ptr(y), len(x), 1 if rsqrt else 0), "nb_debug_rcp")
+        return y
+
+    def pairs_view(self):
+        kbits = self.debug_scalar("kbits")
+        keys = self.debug("pair_keys", np.uint64)
+        return dict(lo=(keys & np.uint64((1 << kbits) - 1)).astype(np.uint32), hi=(keys >> np.uint64(kbits)).astype(np.uint32), order=self.debug("order", np.uint32))
+
+    def impulses_view(self):
+        return dict(sorted=self.debug("sorted", np.uint32), data=self.debug("impulses", scenes.IMPULSE),
+                    culled_tags=self.debug("culled_tags", np.uint64), culled_features=self.debug("culled_features", np.uint32),
+                    culled_data=self.debug("culled_data", scenes.IMPULSE))
+
+    def constraints_view(self):
+        """Rows and states keyed by contact index (the reference keys them by batch lane; compare per contact)."""
+        stride = self.debug_scalar("row_stride")
+        contact = self.debug("row_contact", np.uint32)
+        n = len(contact)
+        planes = self.debug("row_planes", np.float32).reshape(39, stride)[:, :n]
+        states = self.debug("row_states", np.float32).reshape(3, stride)[:, :n]
+        sorted_c = self.debug("sorted", np.uint32)
+        batch_of_sorted = self.debug("batch_of", np.uint32)
+        batch = np.zeros(n, np.uint32); batch[sorted_c] = batch_of_sorted
+        return dict(contact=contact, a=self.debug("row_a", np.uint32), b=self.debug("row_b", np.uint32), rows=planes.T.copy(), states=states.T.copy(),
+                    batch_of_contact=batch, level=self.debug("level", np.uint32))

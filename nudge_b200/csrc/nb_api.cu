@@ -1,0 +1,526 @@
+// nudge_b200 — host side of the C ABI (include/nudge_b200.h): context, HBM arena, kernel sequencing.
+// The reference keeps all memory caller-owned and bump-allocates scratch from an Arena (nudge.cpp:990-1055);
+// here the context plays both roles for device memory: every buffer is carved once from cudaMalloc at
+// nb_create and reused every step, nothing is allocated or synchronised inside the step.
+#include "nb_solver.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+extern "C" void nb_host_sample_luts(u32* rcp_lut, u32* rsqrt_lut);   // nb_lut_host.cpp
+extern "C" int nb_host_check_lut_model(const u32* rcp_lut, const u32* rsqrt_lut);
+
+#define NB_MAX_LEVEL_COUNT 4096
+
+struct nb_context {
+	nb_config cfg;
+	int sms;
+	std::string error;
+	unsigned long long launches;
+	int lut_exact;
+	std::vector<void*> allocs;
+	u32 B, nboxes, nspheres, nconn;  // uploaded sizes
+	u32 tagbits, kbits, bodybits, batchbits;
+	u32 stride;    // scratch stride
+	u32 cstride;   // row plane stride
+	u32 slots_per_bucket;
+	int coop_blocks_solve, coop_blocks_levels;
+
+	// scene
+	nb_transform* xf; nb_body_properties* props; nb_body_momentum* mom; uint8_t* idle;
+	u32* box_tags; nb_box_collider* box_data; nb_transform* box_xf;
+	u32* sph_tags; nb_sphere_collider* sph_data; nb_transform* sph_xf;
+	nb_body_pair* conn;
+	u32* counts;
+	// collide
+	nb_transform* world_xf; float4* aabb_min; float4* aabb_max; u32* col_tag; u32* col_body; u32* order; u32* rank;
+	float4* tree_min; float4* tree_max;
+	SortBuffers sb; u32 sort_cap;
+	u64* pair_keys;  // alias into sb.keys[] after the pair sort
+	u32* flags; u32* offs; u32* block_sums;
+	uint2* live;
+	ContactOut staged, fin;
+	u64* sleeping;
+	u32* parent; u32* active; u32* active_idx;
+	// cache
+	u64* cache_tags; u32* cache_features; float4* cache_data;
+	u64* culled_tags; u32* culled_features; float4* culled_data;
+	u32* sorted; float4* impulses;
+	// setup / solve
+	float4* inertia;
+	u32* slot_of; u32* slot_done; u32* slot_left; u32* left_count; u32* batch_of; u32* pred; u32* level;
+	u32* level_count; u32* level_start; u32* level_fill; u32* slot_to_sorted;
+	Rows rows;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->error = std::string(#call) + ": " + cudaGetErrorString(e_); return NB_ERR_CUDA; } } while (0)
+
+template<class T>
+static int dev_alloc(nb_context* ctx, T** p, size_t n) {
+	void* q = nullptr;
+	size_t bytes = (n ? n : 1) * sizeof(T);
+	cudaError_t e = cudaMalloc(&q, bytes);
+	if (e != cudaSuccess) { ctx->error = std::string("cudaMalloc: ") + cudaGetErrorString(e); return NB_ERR_CUDA; }
+	cudaMemset(q, 0, bytes);
+	ctx->allocs.push_back(q);
+	*p = (T*)q;
+	return 0;
+}
+#define ALLOC(p, n) do { int r_ = dev_alloc(ctx, &(p), (size_t)(n)); if (r_) return r_; } while (0)
+
+static u32 bits_for(u64 n) { u32 b = 1; while (((u64)1 << b) < n) ++b; return b; }
+static Launch mk_launch(nb_context* ctx, void* stream) { Launch L = { (cudaStream_t)stream, &ctx->launches, ctx->sms }; return L; }
+#define GRID(n) nb_grid_for((unsigned)(n), ctx->sms)
+
+__global__ void k_reset_collide(u32* counts) {
+	if (threadIdx.x == 0) {
+		counts[CNT_PAIRS] = 0; counts[CNT_OVERFLOW] = 0;
+		for (int k = 0; k < 4; ++k) { counts[CNT_BMIN0 + k] = 0xffffffffu; counts[CNT_BMAX0 + k] = 0; }
+	}
+}
+__global__ void __launch_bounds__(NB_BLOCK) k_copy_u64(const u64* src, u64* dst, const u32* n_ptr) {
+	u32 n = *n_ptr;
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(NB_BLOCK) k_copy_u32(const u32* src, u32* dst, const u32* n_ptr) {
+	u32 n = *n_ptr;
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(NB_BLOCK) k_debug_rcp(const float* x, float* y, u32 n, int rsq) {
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = rsq ? nb_rsqrt(x[i]) : nb_rcp(x[i]);
+}
+
+extern "C" {
+
+int nb_create(const nb_config* config, nb_context** out) {
+	if (!config || !out) return NB_ERR_ARGUMENT;
+	nb_context* ctx = new nb_context();
+	*out = ctx;
+	ctx->cfg = *config;
+	ctx->launches = 0;
+	nb_config& c = ctx->cfg;
+	if (!c.max_bodies) c.max_bodies = 1;
+	u32 K = c.max_boxes + c.max_spheres;
+	if (!c.max_pairs) c.max_pairs = 16 * (K ? K : 1);
+	if (!c.max_contacts) c.max_contacts = 24 * c.max_bodies;
+	int ndev = 0;
+	CK(cudaGetDeviceCount(&ndev));
+	if (ndev <= 0) { ctx->error = "no CUDA device: nudge_b200 has no CPU path"; return NB_ERR_CUDA; }
+	CK(cudaSetDevice(c.device));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, c.device));
+	ctx->sms = prop.multiProcessorCount;
+	if (!prop.cooperativeLaunch) { ctx->error = "device lacks cooperative launch"; return NB_ERR_CUDA; }
+
+	const u32 B = c.max_bodies, P = c.max_pairs, C = c.max_contacts;
+	ctx->B = 0; ctx->nboxes = 0; ctx->nspheres = 0; ctx->nconn = 0;
+	ctx->tagbits = 1; ctx->kbits = bits_for(K ? K : 1); ctx->bodybits = bits_for(B); ctx->batchbits = bits_for((u64)C + 2);
+	ctx->stride = ((std::max(std::max(P, C), std::max(B, K)) + 63) / 64) * 64;
+	ctx->cstride = ((C + 31) / 32) * 32;
+	ctx->slots_per_bucket = (C + 15) / 16 + 1;
+
+	ALLOC(ctx->xf, B); ALLOC(ctx->props, B); ALLOC(ctx->mom, B); ALLOC(ctx->idle, B);
+	ALLOC(ctx->box_tags, c.max_boxes); ALLOC(ctx->box_data, c.max_boxes); ALLOC(ctx->box_xf, c.max_boxes);
+	ALLOC(ctx->sph_tags, c.max_spheres); ALLOC(ctx->sph_data, c.max_spheres); ALLOC(ctx->sph_xf, c.max_spheres);
+	ALLOC(ctx->conn, c.max_connections);
+	ALLOC(ctx->counts, CNT__COUNT);
+	ALLOC(ctx->world_xf, K); ALLOC(ctx->aabb_min, K); ALLOC(ctx->aabb_max, K); ALLOC(ctx->col_tag, K); ALLOC(ctx->col_body, K);
+	ALLOC(ctx->order, K); ALLOC(ctx->rank, K);
+	size_t tree_nodes = 0; { u32 n = K ? K : 1; tree_nodes = n; while (n > 8) { n = (n + 7) / 8; tree_nodes += n; } }
+	ALLOC(ctx->tree_min, tree_nodes + 8); ALLOC(ctx->tree_max, tree_nodes + 8);
+	ctx->sort_cap = std::max(std::max(K, P), 2 * C);
+	for (int i = 0; i < 2; ++i) { ALLOC(ctx->sb.keys[i], ctx->sort_cap); ALLOC(ctx->sb.vals[i], ctx->sort_cap); }
+	ALLOC(ctx->sb.hist, 256 * NB_SORT_GRID); ALLOC(ctx->sb.block_sums, 8 * NB_SCAN_GRID);
+	ALLOC(ctx->flags, 5 * (size_t)ctx->stride); ALLOC(ctx->offs, 5 * (size_t)ctx->stride); ALLOC(ctx->block_sums, 8 * NB_SCAN_GRID);
+	ALLOC(ctx->live, P);
+	ALLOC(ctx->staged.data, 2 * (size_t)C); ALLOC(ctx->staged.bodies, C); ALLOC(ctx->staged.tags, C); ALLOC(ctx->staged.features, C);
+	ALLOC(ctx->fin.data, 2 * (size_t)C); ALLOC(ctx->fin.bodies, C); ALLOC(ctx->fin.tags, C); ALLOC(ctx->fin.features, C);
+	ALLOC(ctx->sleeping, (size_t)P + C);
+	ALLOC(ctx->parent, B); ALLOC(ctx->active, B); ALLOC(ctx->active_idx, B);
+	ALLOC(ctx->cache_tags, C); ALLOC(ctx->cache_features, C); ALLOC(ctx->cache_data, C);
+	ALLOC(ctx->culled_tags, C); ALLOC(ctx->culled_features, C); ALLOC(ctx->culled_data, C);
+	ALLOC(ctx->sorted, C); ALLOC(ctx->impulses, C);
+	ALLOC(ctx->inertia, 2 * (size_t)B);
+	ALLOC(ctx->slot_of, C); ALLOC(ctx->slot_done, 16 * (size_t)ctx->slots_per_bucket); ALLOC(ctx->slot_left, 16 * (size_t)ctx->slots_per_bucket);
+	ALLOC(ctx->left_count, 16); ALLOC(ctx->batch_of, C); ALLOC(ctx->pred, 2 * (size_t)C); ALLOC(ctx->level, C);
+	ALLOC(ctx->level_count, NB_MAX_LEVEL_COUNT); ALLOC(ctx->level_start, NB_MAX_LEVEL_COUNT + 1); ALLOC(ctx->level_fill, NB_MAX_LEVEL_COUNT);
+	ALLOC(ctx->slot_to_sorted, C);
+	ALLOC(ctx->rows.plane, (size_t)ROW_PLANES * ctx->cstride); ALLOC(ctx->rows.state, 3 * (size_t)ctx->cstride);
+	ALLOC(ctx->rows.a, C); ALLOC(ctx->rows.b, C); ALLOC(ctx->rows.contact, C);
+	ctx->rows.stride = ctx->cstride;
+	ctx->pair_keys = ctx->sb.keys[0];
+
+	// rcpps / rsqrtps tables from this host's CPU
+	u32 rcp_lut[2048], rsqrt_lut[2048];
+	nb_host_sample_luts(rcp_lut, rsqrt_lut);
+	ctx->lut_exact = nb_host_check_lut_model(rcp_lut, rsqrt_lut);
+	CK(cudaMemcpyToSymbol(c_rcp_lut, rcp_lut, sizeof(rcp_lut)));
+	CK(cudaMemcpyToSymbol(c_rsqrt_lut, rsqrt_lut, sizeof(rsqrt_lut)));
+	CK(cudaMemcpyToSymbol(g_rcp_lut, rcp_lut, sizeof(rcp_lut)));
+	CK(cudaMemcpyToSymbol(g_rsqrt_lut, rsqrt_lut, sizeof(rsqrt_lut)));
+
+	CK(cudaFuncSetAttribute(k_schedule, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SchedSmem)));
+	int per_sm = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, NB_BLOCK, 0));
+	if (per_sm < 1) { ctx->error = "k_solve does not fit on an SM"; return NB_ERR_CUDA; }
+	ctx->coop_blocks_solve = ctx->sms * std::min(per_sm, 2);
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_levels, NB_BLOCK, 0));
+	if (per_sm < 1) { ctx->error = "k_levels does not fit on an SM"; return NB_ERR_CUDA; }
+	ctx->coop_blocks_levels = ctx->sms * std::min(per_sm, 4);
+	CK(cudaDeviceSynchronize());
+	return NB_OK;
+}
+
+void nb_destroy(nb_context* ctx) {
+	if (!ctx) return;
+	cudaDeviceSynchronize();
+	for (size_t i = 0; i < ctx->allocs.size(); ++i) cudaFree(ctx->allocs[i]);
+	delete ctx;
+}
+
+const char* nb_last_error(const nb_context* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+uint64_t nb_launch_count(const nb_context* ctx) { return ctx->launches; }
+int nb_lut_model_exact(const nb_context* ctx) { return ctx->lut_exact; }
+
+#define H2D(dst, src, n, T) CK(cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, (cudaStream_t)stream))
+#define D2H(dst, src, n, T) CK(cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyDeviceToHost, (cudaStream_t)stream))
+
+int nb_upload_bodies(nb_context* ctx, const nb_body_data* h, void* stream) {
+	if (h->count > ctx->cfg.max_bodies) { ctx->error = "too many bodies"; return NB_ERR_CAPACITY; }
+	ctx->B = h->count;
+	H2D(ctx->xf, h->transforms, h->count, nb_transform); H2D(ctx->props, h->properties, h->count, nb_body_properties);
+	H2D(ctx->mom, h->momentum, h->count, nb_body_momentum); H2D(ctx->idle, h->idle_counters, h->count, uint8_t);
+	return NB_OK;
+}
+int nb_upload_momentum(nb_context* ctx, const nb_body_momentum* h, uint32_t count, void* stream) { H2D(ctx->mom, h, count, nb_body_momentum); return NB_OK; }
+int nb_upload_transforms(nb_context* ctx, const nb_transform* h, uint32_t count, void* stream) { H2D(ctx->xf, h, count, nb_transform); return NB_OK; }
+int nb_download_momentum(nb_context* ctx, nb_body_momentum* h, uint32_t count, void* stream) { D2H(h, ctx->mom, count, nb_body_momentum); return NB_OK; }
+int nb_download_transforms(nb_context* ctx, nb_transform* h, uint32_t count, void* stream) { D2H(h, ctx->xf, count, nb_transform); return NB_OK; }
+
+int nb_upload_colliders(nb_context* ctx, const nb_collider_data* h, void* stream) {
+	if (h->boxes.count > ctx->cfg.max_boxes || h->spheres.count > ctx->cfg.max_spheres) { ctx->error = "too many colliders"; return NB_ERR_CAPACITY; }
+	ctx->nboxes = h->boxes.count; ctx->nspheres = h->spheres.count;
+	u32 maxtag = 1;
+	for (u32 i = 0; i < h->boxes.count; ++i) maxtag = std::max(maxtag, h->boxes.tags[i]);
+	for (u32 i = 0; i < h->spheres.count; ++i) maxtag = std::max(maxtag, h->spheres.tags[i]);
+	ctx->tagbits = bits_for((u64)maxtag + 1);
+	ctx->kbits = bits_for(std::max(1u, ctx->nboxes + ctx->nspheres));
+	H2D(ctx->box_tags, h->boxes.tags, h->boxes.count, u32); H2D(ctx->box_data, h->boxes.data, h->boxes.count, nb_box_collider);
+	H2D(ctx->box_xf, h->boxes.transforms, h->boxes.count, nb_transform);
+	H2D(ctx->sph_tags, h->spheres.tags, h->spheres.count, u32); H2D(ctx->sph_data, h->spheres.data, h->spheres.count, nb_sphere_collider);
+	H2D(ctx->sph_xf, h->spheres.transforms, h->spheres.count, nb_transform);
+	return NB_OK;
+}
+int nb_upload_connections(nb_context* ctx, const nb_body_connections* h, void* stream) {
+	if (h->count > ctx->cfg.max_connections) { ctx->error = "too many connections"; return NB_ERR_CAPACITY; }
+	ctx->nconn = h->count;
+	H2D(ctx->conn, h->data, h->count, nb_body_pair);
+	return NB_OK;
+}
+int nb_upload_cache(nb_context* ctx, const nb_contact_cache* h, void* stream) {
+	if (h->count > ctx->cfg.max_contacts) { ctx->error = "cache too large"; return NB_ERR_CAPACITY; }
+	H2D(ctx->cache_tags, h->tags, h->count, u64); H2D(ctx->cache_features, h->features, h->count, u32); H2D(ctx->cache_data, h->data, h->count, nb_cached_impulse);
+	u32 n = h->count;
+	CK(cudaMemcpyAsync(ctx->counts + CNT_CACHE, &n, 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+	CK(cudaStreamSynchronize((cudaStream_t)stream));
+	return NB_OK;
+}
+int nb_download_bodies(nb_context* ctx, nb_body_data* h, void* stream) {
+	u32 n = std::min(h->count, ctx->B);
+	D2H(h->transforms, ctx->xf, n, nb_transform); D2H(h->momentum, ctx->mom, n, nb_body_momentum); D2H(h->idle_counters, ctx->idle, n, uint8_t);
+	CK(cudaStreamSynchronize((cudaStream_t)stream));
+	return NB_OK;
+}
+static int get_counts(nb_context* ctx, u32* host, void* stream) {
+	D2H(host, ctx->counts, CNT__COUNT, u32);
+	CK(cudaStreamSynchronize((cudaStream_t)stream));
+	return NB_OK;
+}
+int nb_download_counts(nb_context* ctx, nb_counts* out, void* stream) {
+	u32 h[CNT__COUNT];
+	int r = get_counts(ctx, h, stream); if (r) return r;
+	out->pairs = h[CNT_PAIRS]; out->live_pairs = h[CNT_LIVE_TOTAL]; out->contacts = h[CNT_CONTACTS]; out->sleeping = h[CNT_SLEEPING];
+	out->active = h[CNT_ACTIVE]; out->cache = h[CNT_CACHE]; out->culled = h[CNT_CULLED]; out->batches = h[CNT_BATCHES]; out->levels = h[CNT_LEVELS];
+	out->overflow = h[CNT_OVERFLOW];
+	return NB_OK;
+}
+int nb_download_contacts(nb_context* ctx, nb_contact_data* h, nb_active_bodies* ha, void* stream) {
+	u32 c[CNT__COUNT];
+	int r = get_counts(ctx, c, stream); if (r) return r;
+	if (h) {
+		u32 n = c[CNT_CONTACTS], s = c[CNT_SLEEPING];
+		if (n > h->capacity) { ctx->error = "host contact buffer too small"; return NB_ERR_CAPACITY; }
+		h->count = n; h->sleeping_count = s;
+		D2H(h->data, ctx->fin.data, n, nb_contact); D2H(h->bodies, ctx->fin.bodies, n, nb_body_pair);
+		D2H(h->tags, ctx->fin.tags, n, u64); D2H(h->features, ctx->fin.features, n, u32);
+		if (h->sleeping_pairs) D2H(h->sleeping_pairs, ctx->sleeping, s, u64);
+	}
+	if (ha) {
+		u32 n = c[CNT_ACTIVE];
+		if (n > ha->capacity) { ctx->error = "host active-body buffer too small"; return NB_ERR_CAPACITY; }
+		ha->count = n;
+		D2H(ha->indices, ctx->active_idx, n, u32);
+	}
+	CK(cudaStreamSynchronize((cudaStream_t)stream));
+	return c[CNT_OVERFLOW] ? NB_ERR_OVERFLOW : NB_OK;
+}
+int nb_download_cache(nb_context* ctx, nb_contact_cache* h, void* stream) {
+	u32 c[CNT__COUNT];
+	int r = get_counts(ctx, c, stream); if (r) return r;
+	u32 n = c[CNT_CACHE];
+	if (n > h->capacity) { ctx->error = "host cache buffer too small"; return NB_ERR_CAPACITY; }
+	h->count = n;
+	D2H(h->tags, ctx->cache_tags, n, u64); D2H(h->features, ctx->cache_features, n, u32); D2H(h->data, ctx->cache_data, n, nb_cached_impulse);
+	CK(cudaStreamSynchronize((cudaStream_t)stream));
+	return NB_OK;
+}
+
+// ---------------- collide ----------------
+int nb_collide(nb_context* ctx, void* stream) {
+	Launch L = mk_launch(ctx, stream);
+	cudaStream_t st = L.stream;
+	const u32 K = ctx->nboxes + ctx->nspheres, B = ctx->B, nboxes = ctx->nboxes;
+	u32* counts = ctx->counts;
+	k_reset_collide<<<1, 32, 0, st>>>(counts); ++ctx->launches;
+	if (K == 0 || B == 0) return NB_OK;
+	k_collider_world<<<GRID(K), NB_BLOCK, 0, st>>>(ctx->nboxes, ctx->nspheres, ctx->xf, ctx->box_xf, ctx->box_data, ctx->box_tags,
+		ctx->sph_xf, ctx->sph_data, ctx->sph_tags, ctx->world_xf, ctx->aabb_min, ctx->aabb_max, ctx->col_tag, ctx->col_body, counts);
+	k_morton<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->aabb_min, counts, ctx->sb.keys[0], ctx->sb.vals[0]);
+	ctx->launches += 2;
+	// radix sort on the 48-bit code; ties keep index order like the stable sort of nudge.cpp:3165
+	CK(cudaMemcpyAsync(counts + CNT_SCRATCH1, &K, 4, cudaMemcpyHostToDevice, st));
+	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_SCRATCH1, 0, 48, true, 0);
+	Tree T;
+	{
+		size_t off = 0; u32 n = K; int l = 0;
+		while (true) { T.mn[l] = ctx->tree_min + off; T.mx[l] = ctx->tree_max + off; T.n[l] = n; off += n; ++l; if (n <= 8) break; n = (n + 7) / 8; }
+		T.levels = l;
+	}
+	k_leaves<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->sb.vals[cur], ctx->aabb_min, ctx->aabb_max, ctx->order, ctx->rank, (float4*)T.mn[0], (float4*)T.mx[0]);
+	++ctx->launches;
+	for (int l = 1; l < T.levels; ++l) {
+		k_build_level<<<GRID(T.n[l]), NB_BLOCK, 0, st>>>(T.mn[l - 1], T.mx[l - 1], T.n[l - 1], (float4*)T.mn[l], (float4*)T.mx[l], T.n[l]);
+		++ctx->launches;
+	}
+	k_find_pairs<<<GRID(K), NB_BLOCK, 0, st>>>(T, K, ctx->order, ctx->kbits, ctx->sb.keys[0], ctx->cfg.max_pairs, counts);
+	k_clamp_count<<<1, 1, 0, st>>>(counts, CNT_PAIRS, ctx->cfg.max_pairs);
+	ctx->launches += 2;
+	cur = nb_radix_sort(L, ctx->sb, counts + CNT_PAIRS, 0, (int)(2 * ctx->kbits), false, 0);  // nudge.cpp:3498
+	ctx->pair_keys = ctx->sb.keys[cur];
+
+	// coarse islands (nudge.cpp:3500-3703)
+	const u32 P = ctx->cfg.max_pairs, S = ctx->stride;
+	k_uf_init<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, B); ++ctx->launches;
+	if (ctx->nconn) { k_uf_union_conn<<<GRID(ctx->nconn), NB_BLOCK, 0, st>>>(ctx->parent, ctx->conn, ctx->nconn); ++ctx->launches; }
+	k_uf_union_pairs<<<GRID(P), NB_BLOCK, 0, st>>>(ctx->parent, ctx->pair_keys, ctx->kbits, ctx->col_body, counts);
+	k_uf_flatten_active<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, ctx->idle, B);
+	k_pair_flags<<<GRID(P), NB_BLOCK, 0, st>>>(ctx->pair_keys, ctx->kbits, nboxes, ctx->col_body, ctx->parent, ctx->active, ctx->flags, S, counts);
+	ctx->launches += 3;
+	nb_scan<5>(L, ctx->flags, ctx->offs, S, counts + CNT_PAIRS, 0, ctx->block_sums, counts + CNT_LIVE0);  // -> LIVE0..3, SLEEP_COARSE
+	k_partition<<<GRID(P), NB_BLOCK, 0, st>>>(ctx->pair_keys, ctx->kbits, ctx->flags, ctx->offs, S, ctx->col_tag, ctx->live, ctx->sleeping, counts);
+	++ctx->launches;
+
+	// narrowphase: count, scan, emit (nudge.cpp:3753-3786)
+	k_narrowphase<false><<<GRID(P), NB_BLOCK, 0, st>>>(ctx->live, nboxes, ctx->world_xf, ctx->box_data, ctx->sph_data, ctx->col_tag, ctx->flags, ctx->offs, S, ctx->staged, ctx->cfg.max_contacts, counts);
+	++ctx->launches;
+	nb_scan<3>(L, ctx->flags, ctx->offs, S, counts + CNT_LIVE_TOTAL, 0, ctx->block_sums, counts + CNT_FACE);  // -> FACE, EDGE, OTHER
+	k_narrowphase<true><<<GRID(P), NB_BLOCK, 0, st>>>(ctx->live, nboxes, ctx->world_xf, ctx->box_data, ctx->sph_data, ctx->col_tag, ctx->flags, ctx->offs, S, ctx->staged, ctx->cfg.max_contacts, counts);
+	++ctx->launches;
+
+	// fine islands, active bodies, contact compaction (nudge.cpp:3788-4006)
+	const u32 C = ctx->cfg.max_contacts;
+	k_uf_init<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, B); ++ctx->launches;
+	if (ctx->nconn) { k_uf_union_conn<<<GRID(ctx->nconn), NB_BLOCK, 0, st>>>(ctx->parent, ctx->conn, ctx->nconn); ++ctx->launches; }
+	k_uf_union_contacts<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->parent, ctx->staged.bodies, counts);
+	k_uf_flatten_active<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, ctx->idle, B);
+	k_body_flags<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, ctx->flags, B);
+	ctx->launches += 3;
+	nb_scan<1>(L, ctx->flags, ctx->offs, S, nullptr, B, ctx->block_sums, counts + CNT_ACTIVE);
+	k_active_scatter<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->flags, ctx->offs, ctx->active_idx, B);
+	k_contact_flags<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->staged.bodies, ctx->staged.tags, ctx->parent, ctx->active, ctx->flags, S, counts);
+	ctx->launches += 2;
+	nb_scan<2>(L, ctx->flags, ctx->offs, S, counts + CNT_STAGED, 0, ctx->block_sums, counts + CNT_CONTACTS);  // -> CONTACTS, SLEEP_FINE
+	k_contact_compact<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->staged, ctx->fin, ctx->flags, ctx->offs, S, ctx->sleeping, counts);
+	++ctx->launches;
+
+	// sort sleeping pairs (nudge.cpp:4008): key X | Y<<32, both below 2^tagbits
+	k_copy_u64<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sleeping, ctx->sb.keys[0], counts + CNT_SLEEPING); ++ctx->launches;
+	cur = nb_radix_sort(L, ctx->sb, counts + CNT_SLEEPING, 0, (int)ctx->tagbits, false, 0);
+	cur = nb_radix_sort(L, ctx->sb, counts + CNT_SLEEPING, 32, (int)(32 + ctx->tagbits), false, cur);
+	k_copy_u64<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sleeping, counts + CNT_SLEEPING); ++ctx->launches;
+	CK(cudaGetLastError());
+	return NB_OK;
+}
+
+int nb_apply_gravity_damping(nb_context* ctx, float time_step, float gravity, float damping, void* stream) {
+	k_gravity_damping<<<GRID(ctx->B), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->active_idx, ctx->mom, time_step, gravity, damping, ctx->counts);
+	++ctx->launches;
+	CK(cudaGetLastError());
+	return NB_OK;
+}
+
+// ---------------- contact cache ----------------
+int nb_read_cached_impulses(nb_context* ctx, void* stream) {
+	Launch L = mk_launch(ctx, stream);
+	cudaStream_t st = L.stream;
+	u32* counts = ctx->counts;
+	const u32 C = ctx->cfg.max_contacts, S = ctx->stride;
+	// order contacts by tag: stable sort on the feature word, then on the pair word (nudge.cpp:4024-4044)
+	k_tag_keys_feature<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.features, ctx->sb.keys[0], ctx->sb.vals[0], counts); ++ctx->launches;
+	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_CONTACTS, 0, 32, true, 0);
+	k_tag_keys_pair<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.tags, ctx->sb.vals[cur], ctx->sb.keys[cur], ctx->tagbits, counts); ++ctx->launches;
+	cur = nb_radix_sort(L, ctx->sb, counts + CNT_CONTACTS, 0, (int)(2 * ctx->tagbits), true, cur);
+	k_copy_u32<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sb.vals[cur], ctx->sorted, counts + CNT_CONTACTS);
+	k_cache_lookup<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.tags, ctx->fin.features, ctx->cache_tags, ctx->cache_features, ctx->cache_data, ctx->impulses, counts);
+	k_culled_flags<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->cache_tags, ctx->sleeping, ctx->flags, counts);
+	ctx->launches += 3;
+	nb_scan<1>(L, ctx->flags, ctx->offs, S, counts + CNT_CACHE, 0, ctx->block_sums, counts + CNT_CULLED);
+	k_culled_scatter<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->flags, ctx->offs, ctx->cache_tags, ctx->cache_features, ctx->cache_data,
+		ctx->culled_tags, ctx->culled_features, ctx->culled_data, counts);
+	++ctx->launches;
+	CK(cudaGetLastError());
+	return NB_OK;
+}
+
+int nb_write_cached_impulses(nb_context* ctx, void* stream) {
+	const u32 C = ctx->cfg.max_contacts;
+	k_cache_merge<<<GRID(C), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->sorted, ctx->fin.tags, ctx->fin.features, ctx->impulses,
+		ctx->culled_tags, ctx->culled_features, ctx->culled_data, ctx->cache_tags, ctx->cache_features, ctx->cache_data, ctx->counts);
+	++ctx->launches;
+	CK(cudaGetLastError());
+	return NB_OK;
+}
+
+// ---------------- setup + solve ----------------
+static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) {
+	Rows R = ctx->rows;
+	const float4* impulses = ctx->impulses;
+	nb_body_momentum* mom = ctx->mom;
+	const u32* level_start = ctx->level_start;
+	u32* counts = ctx->counts;
+	void* args[] = { &R, &impulses, &mom, &level_start, &mode, &sweeps, &counts };
+	CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
+	++ctx->launches;
+	return NB_OK;
+}
+
+int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
+	Launch L = mk_launch(ctx, stream);
+	cudaStream_t st = L.stream;
+	u32* counts = ctx->counts;
+	const u32 C = ctx->cfg.max_contacts, S = ctx->stride, B = ctx->B;
+	k_inertia<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->xf, ctx->props, ctx->inertia, ctx->mom);
+	k_schedule<<<16, 32, sizeof(SchedSmem), st>>>(ctx->sorted, ctx->fin.bodies, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,
+		ctx->flags, ctx->left_count, counts);
+	ctx->launches += 2;
+	nb_scan<1>(L, ctx->flags, ctx->offs, S, counts + CNT_CONTACTS, 0, ctx->block_sums, counts + CNT_FULL_BATCHES);
+	k_batch_index<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,
+		ctx->offs, ctx->left_count, ctx->batch_of, ctx->sb.keys[0], ctx->sb.vals[0], ctx->batchbits, counts);
+	++ctx->launches;
+	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_ENTRIES, 0, (int)(ctx->bodybits + ctx->batchbits), true, 0);
+	k_preds<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, ctx->pred, counts);
+	++ctx->launches;
+	{
+		const u32* pred = ctx->pred; u32* level = ctx->level; u32* level_count = ctx->level_count; u32 max_levels = NB_MAX_LEVEL_COUNT;
+		void* args[] = { &pred, &level, &level_count, &max_levels, &counts };
+		CK(cudaLaunchCooperativeKernel((void*)k_levels, dim3(ctx->coop_blocks_levels), dim3(NB_BLOCK), args, 0, st));
+		++ctx->launches;
+	}
+	k_level_starts<<<1, 1024, 0, st>>>(ctx->level_count, ctx->level_start, ctx->level_fill, NB_MAX_LEVEL_COUNT, counts);
+	k_level_scatter<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->level, ctx->level_start, ctx->level_fill, ctx->slot_to_sorted, NB_MAX_LEVEL_COUNT, counts);
+	k_build_rows<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->slot_to_sorted, ctx->sorted, ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts);
+	ctx->launches += 3;
+	int r = launch_solve(ctx, 0, 1, st); if (r) return r;  // warm start (nudge.cpp:4563-4632)
+	CK(cudaGetLastError());
+	return NB_OK;
+}
+
+int nb_apply_impulses(nb_context* ctx, uint32_t sweeps, void* stream) {
+	if (!sweeps) return NB_OK;
+	int r = launch_solve(ctx, 1, sweeps, (cudaStream_t)stream); if (r) return r;
+	CK(cudaGetLastError());
+	return NB_OK;
+}
+
+int nb_update_cached_impulses(nb_context* ctx, void* stream) {
+	k_update_impulses<<<GRID(ctx->cfg.max_contacts), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->rows, ctx->impulses, ctx->counts);
+	++ctx->launches;
+	CK(cudaGetLastError());
+	return NB_OK;
+}
+
+int nb_advance(nb_context* ctx, float time_step, void* stream) {
+	k_advance<<<GRID(ctx->B), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->active_idx, ctx->xf, ctx->mom, ctx->idle, time_step, ctx->counts);
+	++ctx->launches;
+	CK(cudaGetLastError());
+	return NB_OK;
+}
+
+int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity, float damping, void* stream) {
+	int r;
+	if ((r = nb_collide(ctx, stream))) return r;
+	if ((r = nb_apply_gravity_damping(ctx, time_step, gravity, damping, stream))) return r;
+	if ((r = nb_read_cached_impulses(ctx, stream))) return r;
+	if ((r = nb_setup_contact_constraints(ctx, stream))) return r;
+	if ((r = nb_apply_impulses(ctx, iterations, stream))) return r;
+	if ((r = nb_update_cached_impulses(ctx, stream))) return r;
+	if ((r = nb_write_cached_impulses(ctx, stream))) return r;
+	return nb_advance(ctx, time_step, stream);
+}
+
+// ---------------- parity-test introspection ----------------
+int nb_debug_read(nb_context* ctx, const char* name, void* dst, size_t max_bytes, size_t* bytes, void* stream) {
+	u32 c[CNT__COUNT];
+	int r = get_counts(ctx, c, stream); if (r) return r;
+	const u32 K = ctx->nboxes + ctx->nspheres;
+	struct Entry { const char* name; const void* ptr; size_t bytes; };
+	const Entry table[] = {
+		{ "counts", ctx->counts, sizeof(u32) * CNT__COUNT },
+		{ "order", ctx->order, sizeof(u32) * K },
+		{ "aabb_min", ctx->aabb_min, sizeof(float4) * K },
+		{ "aabb_max", ctx->aabb_max, sizeof(float4) * K },
+		{ "world_xf", ctx->world_xf, sizeof(nb_transform) * K },
+		{ "pair_keys", ctx->pair_keys, sizeof(u64) * c[CNT_PAIRS] },
+		{ "live", ctx->live, sizeof(uint2) * c[CNT_LIVE_TOTAL] },
+		{ "sorted", ctx->sorted, sizeof(u32) * c[CNT_CONTACTS] },
+		{ "impulses", ctx->impulses, sizeof(float4) * c[CNT_CONTACTS] },
+		{ "culled_tags", ctx->culled_tags, sizeof(u64) * c[CNT_CULLED] },
+		{ "culled_features", ctx->culled_features, sizeof(u32) * c[CNT_CULLED] },
+		{ "culled_data", ctx->culled_data, sizeof(float4) * c[CNT_CULLED] },
+		{ "batch_of", ctx->batch_of, sizeof(u32) * c[CNT_CONTACTS] },
+		{ "level", ctx->level, sizeof(u32) * c[CNT_CONTACTS] },
+		{ "level_start", ctx->level_start, sizeof(u32) * (c[CNT_LEVELS] + 1) },
+		{ "row_contact", ctx->rows.contact, sizeof(u32) * c[CNT_CONTACTS] },
+		{ "row_a", ctx->rows.a, sizeof(u32) * c[CNT_CONTACTS] },
+		{ "row_b", ctx->rows.b, sizeof(u32) * c[CNT_CONTACTS] },
+		{ "row_planes", ctx->rows.plane, sizeof(float) * (size_t)ROW_PLANES * ctx->cstride },
+		{ "row_states", ctx->rows.state, sizeof(float) * 3 * (size_t)ctx->cstride },
+		{ "inertia", ctx->inertia, sizeof(float4) * 2 * ctx->B },
+	};
+	if (!strcmp(name, "row_stride")) { if (max_bytes < 4) return NB_ERR_ARGUMENT; *(u32*)dst = ctx->cstride; if (bytes) *bytes = 4; return NB_OK; }
+	if (!strcmp(name, "kbits")) { if (max_bytes < 4) return NB_ERR_ARGUMENT; *(u32*)dst = ctx->kbits; if (bytes) *bytes = 4; return NB_OK; }
+	for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); ++i)
+		if (!strcmp(name, table[i].name)) {
+			if (bytes) *bytes = table[i].bytes;
+			if (!dst) return NB_OK;
+			if (table[i].bytes > max_bytes) { ctx->error = "debug buffer too small"; return NB_ERR_CAPACITY; }
+			CK(cudaMemcpyAsync(dst, table[i].ptr, table[i].bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+			CK(cudaStreamSynchronize((cudaStream_t)stream));
+			return NB_OK;
+		}
+	ctx->error = std::string("unknown debug buffer ") + name;
+	return NB_ERR_ARGUMENT;
+}
+
+int nb_debug_rcp(nb_context* ctx, const float* x, float* y, uint32_t n, int rsq) {
+	float* dx = (float*)ctx->sb.keys[0]; float* dy = (float*)ctx->sb.keys[1];
+	if ((size_t)n * 4 > (size_t)ctx->sort_cap * 8) { ctx->error = "too many probes"; return NB_ERR_CAPACITY; }
+	CK(cudaMemcpy(dx, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+	k_debug_rcp<<<GRID(n), NB_BLOCK>>>(dx, dy, n, rsq); ++ctx->launches;
+	CK(cudaMemcpy(y, dy, (size_t)n * 4, cudaMemcpyDeviceToHost));
+	return NB_OK;
+}
+
+}

@@ -1,0 +1,597 @@
+// nudge_b200 — contact cache, constraint setup, the sequential-impulse sweeps and the integrator.
+// Replaces nudge::read_cached_impulses / write_cached_impulses (nudge.cpp:4021-4158),
+// setup_contact_constraints (4170-4638), apply_impulses (4640-4855), update_cached_impulses (4857-4884)
+// and advance (4886-4926).
+//
+// Exact-order Gauss-Seidel on a GPU: the reference walks 8-lane batches in the order its
+// sequential 16-bucket first-fit scheduler emits them (nudge.cpp:4206-4340), each batch reading the body
+// velocities the previous one wrote.  We (1) replay that scheduler bit for bit with one warp per bucket to
+// get every contact's batch index, (2) chain the contacts of each body by batch index, (3) assign every
+// contact its dependency level (longest chain below it) and (4) run the sweep level by level inside one
+// co-resident kernel with a grid barrier between levels.  Contacts of one level touch disjoint bodies, so
+// the result is bit-identical to the sequential walk while ~60 levels replace ~30k sequential batches.
+// Rows are stored SoA (one float per contact per plane) so that a warp reads 128 contiguous bytes per plane.
+#pragma once
+#include "nb_collide.cuh"
+
+#define NB_NONE 0xffffffffu
+
+enum {  // constraint row planes, member order of ContactConstraintV (nudge.cpp:907-957)
+	PA_Z, PA_X, PA_Y, PB_Z, PB_X, PB_Y, N_X, U_X, V_X, N_Y, U_Y, V_Y, N_Z, U_Z, V_Z, BIAS, FRICTION, NVTNI, FC_X, FC_Y, FC_Z,
+	NA_X, NA_Y, NA_Z, NB_X, NB_Y, NB_Z, UA_X, UA_Y, UA_Z, VA_X, VA_Y, VA_Z, UB_X, UB_Y, UB_Z, VB_X, VB_Y, VB_Z, ROW_PLANES
+};
+
+NB_DEV bool key_less(u64 ta, u32 fa, u64 tb, u32 fb) { return ta < tb || (ta == tb && fa < fb); }
+
+// ---------------- contact cache read (nudge.cpp:4021-4108) ----------------
+__global__ void __launch_bounds__(NB_BLOCK) k_tag_keys_feature(const u32* features, u64* keys, u32* vals, const u32* counts) {
+	u32 n = counts[CNT_CONTACTS];
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { keys[i] = features[i]; vals[i] = i; }
+}
+__global__ void __launch_bounds__(NB_BLOCK) k_tag_keys_pair(const u64* tags, const u32* vals, u64* keys, u32 tagbits, const u32* counts) {
+	u32 n = counts[CNT_CONTACTS];
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		u64 t = tags[vals[i]];
+		keys[i] = ((t >> 32) << tagbits) | (t & 0xffffffffu);  // major = B (bits 48-63 of the reference tag), then A
+	}
+}
+
+// impulses[c] = cache entry with the same tag, else zero; the lower bound is the entry the reference's merge stops at
+__global__ void __launch_bounds__(NB_BLOCK) k_cache_lookup(const u64* tags, const u32* features, const u64* cache_tags, const u32* cache_features,
+														   const float4* cache_data, float4* impulses, const u32* counts) {
+	u32 n = counts[CNT_CONTACTS], m = counts[CNT_CACHE];
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		u64 t = tags[i]; u32 f = features[i];
+		u32 lo = 0, hi = m;
+		while (lo < hi) { u32 mid = (lo + hi) >> 1; if (key_less(cache_tags[mid], cache_features[mid], t, f)) lo = mid + 1; else hi = mid; }
+		float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		if (lo < m && cache_tags[lo] == t && cache_features[lo] == f) v = cache_data[lo];
+		impulses[i] = v;
+	}
+}
+
+// cache entries of sleeping pairs survive the frame ("culled", nudge.cpp:4064-4101)
+__global__ void __launch_bounds__(NB_BLOCK) k_culled_flags(const u64* cache_tags, const u64* sleeping, u32* flags, const u32* counts) {
+	u32 m = counts[CNT_CACHE], s = counts[CNT_SLEEPING];
+	for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x) {
+		u64 t = cache_tags[e];
+		u32 lo = 0, hi = s;
+		while (lo < hi) { u32 mid = (lo + hi) >> 1; if (sleeping[mid] < t) lo = mid + 1; else hi = mid; }
+		flags[e] = (lo < s && sleeping[lo] == t) ? 1u : 0u;
+	}
+}
+__global__ void __launch_bounds__(NB_BLOCK) k_culled_scatter(const u32* flags, const u32* offs, const u64* cache_tags, const u32* cache_features, const float4* cache_data,
+															 u64* culled_tags, u32* culled_features, float4* culled_data, const u32* counts) {
+	u32 m = counts[CNT_CACHE];
+	for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x)
+		if (flags[e]) { u32 d = offs[e]; culled_tags[d] = cache_tags[e]; culled_features[d] = cache_features[e]; culled_data[d] = cache_data[e]; }
+}
+
+// ---------------- contact cache write: 2-way merge by rank (nudge.cpp:4110-4158) ----------------
+__global__ void __launch_bounds__(NB_BLOCK) k_cache_merge(const u32* sorted, const u64* tags, const u32* features, const float4* impulses,
+		const u64* culled_tags, const u32* culled_features, const float4* culled_data, u64* cache_tags, u32* cache_features, float4* cache_data, u32* counts) {
+	u32 n = counts[CNT_CONTACTS], m = counts[CNT_CULLED];
+	if (blockIdx.x == 0 && threadIdx.x == 0) counts[CNT_CACHE] = n + m;
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n + m; i += gridDim.x * blockDim.x) {
+		if (i < n) {  // contact i of the tag order goes after every culled entry with key <= its key (ties: culled first)
+			u32 c = sorted[i]; u64 t = tags[c]; u32 f = features[c];
+			u32 lo = 0, hi = m;
+			while (lo < hi) { u32 mid = (lo + hi) >> 1; if (!key_less(t, f, culled_tags[mid], culled_features[mid])) lo = mid + 1; else hi = mid; }
+			u32 d = i + lo;
+			cache_tags[d] = t; cache_features[d] = f; cache_data[d] = impulses[c];
+		}
+		else {  // culled entry j goes after every contact with key < its key
+			u32 j = i - n; u64 t = culled_tags[j]; u32 f = culled_features[j];
+			u32 lo = 0, hi = n;
+			while (lo < hi) { u32 mid = (lo + hi) >> 1; u32 c = sorted[mid]; if (key_less(tags[c], features[c], t, f)) lo = mid + 1; else hi = mid; }
+			u32 d = j + lo;
+			cache_tags[d] = t; cache_features[d] = f; cache_data[d] = culled_data[j];
+		}
+	}
+}
+
+// ---------------- per-body world inverse inertia (nudge.cpp:4182-4199) ----------------
+__global__ void __launch_bounds__(NB_BLOCK) k_inertia(u32 B, const nb_transform* xf, const nb_body_properties* props, float4* inertia, nb_body_momentum* momentum) {
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+		float4 q = reinterpret_cast<const float4*>(xf + i)[1];
+		float4 pr = reinterpret_cast<const float4*>(props)[i];
+		mat3 m = qmatrix(mkq(q));
+		float ix = pr.x, iy = pr.y, iz = pr.z;
+		float xx = ix*m.c0.x*m.c0.x + iy*m.c1.x*m.c1.x + iz*m.c2.x*m.c2.x;
+		float yy = ix*m.c0.y*m.c0.y + iy*m.c1.y*m.c1.y + iz*m.c2.y*m.c2.y;
+		float zz = ix*m.c0.z*m.c0.z + iy*m.c1.z*m.c1.z + iz*m.c2.z*m.c2.z;
+		float xy = ix*m.c0.x*m.c0.y + iy*m.c1.x*m.c1.y + iz*m.c2.x*m.c2.y;
+		float xz = ix*m.c0.x*m.c0.z + iy*m.c1.x*m.c1.z + iz*m.c2.x*m.c2.z;
+		float yz = ix*m.c0.y*m.c0.z + iy*m.c1.y*m.c1.z + iz*m.c2.y*m.c2.z;
+		inertia[2*i] = make_float4(xx, yy, zz, 0.0f);
+		inertia[2*i + 1] = make_float4(xy, xz, yz, 0.0f);
+		momentum[i].unused0 = pr.w;  // nudge.cpp:4198
+	}
+}
+
+// ---------------- scheduler replay: one warp per bucket (nudge.cpp:4206-4340) ----------------
+// The reference's state per bucket is a list of partially filled 8-lane slots; a contact goes to the first slot
+// holding neither of its bodies, a slot that receives its 8th contact is emitted and replaced by the last slot of
+// the list.  Buckets only interact through the global emission order, which equals the order of the contact
+// index at which each slot filled up, so 16 warps can replay them independently.
+#define NB_SCHED_MAXV 1024  // vacant slots kept in shared memory per bucket
+struct SchedSmem {
+	u32 a[8][NB_SCHED_MAXV];  // body ids, lane-major so that 32 threads read 32 consecutive slots
+	u32 b[8][NB_SCHED_MAXV];
+	u32 uid[NB_SCHED_MAXV];
+	uint8_t filled[NB_SCHED_MAXV];
+};
+
+__global__ void __launch_bounds__(32) k_schedule(const u32* sorted, const uint2* bodies, u32* slot_of, u32* slot_done, u32* slot_left, u32 slots_per_bucket,
+												 u32* complete_flag, u32* left_count /*[16]*/, u32* counts) {
+	extern __shared__ unsigned char smem_raw[];
+	SchedSmem& S = *reinterpret_cast<SchedSmem*>(smem_raw);
+	const u32 bucket = blockIdx.x, lane = threadIdx.x;
+	const u32 n = counts[CNT_CONTACTS];
+	u32 vcount = 0, next_uid = 0;
+	u32* done = slot_done + (size_t)bucket * slots_per_bucket;
+	u32* left = slot_left + (size_t)bucket * slots_per_bucket;
+	for (u32 base = bucket; base < n; base += 16 * 32) {
+		u32 my_i = base + 16 * lane;
+		u32 my_ca = 0, my_cb = 0;
+		if (my_i < n) {
+			uint2 ab = bodies[sorted[my_i]];
+			my_ca = ab.x ? ab.x : ab.y;  // ignore dependencies on body 0 (nudge.cpp:4238-4240)
+			my_cb = ab.y ? ab.y : ab.x;
+			complete_flag[my_i] = 0;
+		}
+		u32 steps = min(32u, (n - base + 15) / 16);
+		for (u32 s = 0; s < steps; ++s) {
+			u32 i = base + 16 * s;
+			u32 ca = __shfl_sync(0xffffffffu, my_ca, s), cb = __shfl_sync(0xffffffffu, my_cb, s);
+			// first slot with no conflict; index vcount is the always-free sentinel
+			u32 j = vcount;
+			for (u32 jb = 0; jb < vcount; jb += 32) {
+				u32 jj = jb + lane;
+				bool free_slot = false;
+				if (jj < vcount) {
+					u32 f = S.filled[jj];
+					bool conflict = false;
+					#pragma unroll
+					for (u32 l = 0; l < 8; ++l)
+						if (l < f) { u32 sa = S.a[l][jj], sb = S.b[l][jj]; conflict |= (sa == ca) | (sb == ca) | (sa == cb) | (sb == cb); }
+					free_slot = !conflict;
+				}
+				u32 ballot = __ballot_sync(0xffffffffu, free_slot);
+				if (ballot) { j = jb + __ffs(ballot) - 1; break; }
+			}
+			if (j == vcount) {  // open a new slot
+				if (vcount >= NB_SCHED_MAXV) { if (lane == 0) atomicOr(&counts[CNT_OVERFLOW], OVF_SCHED); return; }
+				if (lane == 0) { S.a[0][j] = ca; S.b[0][j] = cb; S.filled[j] = 1; S.uid[j] = next_uid; slot_of[i] = next_uid; done[next_uid] = NB_NONE; }
+				++next_uid; ++vcount;
+				__syncwarp();
+			}
+			else {
+				u32 f = S.filled[j];
+				u32 uid = S.uid[j];
+				__syncwarp();
+				if (lane == 0) { S.a[f][j] = ca; S.b[f][j] = cb; S.filled[j] = (uint8_t)(f + 1); slot_of[i] = uid; }
+				__syncwarp();
+				if (f == 7) {  // slot complete: emitted now, the last slot of the list takes its place (nudge.cpp:4294-4306)
+					if (lane == 0) { done[uid] = i; complete_flag[i] = 1; }
+					u32 last = vcount - 1;
+					if (j != last) {
+						if (lane < 8) { S.a[lane][j] = S.a[lane][last]; S.b[lane][j] = S.b[lane][last]; }
+						if (lane == 8) { S.filled[j] = S.filled[last]; S.uid[j] = S.uid[last]; }
+					}
+					--vcount;
+					__syncwarp();
+				}
+			}
+		}
+	}
+	// leftovers are flushed bucket-major in list order (nudge.cpp:4316-4338)
+	for (u32 jj = lane; jj < vcount; jj += 32) left[S.uid[jj]] = jj;
+	if (lane == 0) left_count[bucket] = vcount;
+}
+
+// batch index of every contact + the (body, batch) chain entries
+__global__ void __launch_bounds__(NB_BLOCK) k_batch_index(const u32* sorted, const uint2* bodies, const u32* slot_of, const u32* slot_done, const u32* slot_left,
+		u32 slots_per_bucket, const u32* complete_off, const u32* left_count, u32* batch_of, u64* chain_keys, u32* chain_vals, u32 batchbits, u32* counts) {
+	u32 n = counts[CNT_CONTACTS];
+	u32 nfull = counts[CNT_FULL_BATCHES];
+	u32 left_base[17]; left_base[0] = 0;
+	#pragma unroll
+	for (int k = 0; k < 16; ++k) left_base[k + 1] = left_base[k] + left_count[k];
+	if (blockIdx.x == 0 && threadIdx.x == 0) { counts[CNT_BATCHES] = nfull + left_base[16]; counts[CNT_ENTRIES] = 2 * n; }
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		u32 bucket = i & 15, uid = slot_of[i];
+		u32 t = slot_done[(size_t)bucket * slots_per_bucket + uid];
+		u32 batch = (t != NB_NONE) ? complete_off[t] : nfull + left_base[bucket] + slot_left[(size_t)bucket * slots_per_bucket + uid];
+		batch_of[i] = batch;
+		uint2 ab = bodies[sorted[i]];
+		chain_keys[2*i] = ab.x ? (((u64)ab.x << batchbits) | batch) : ~(u64)0;
+		chain_keys[2*i + 1] = ab.y ? (((u64)ab.y << batchbits) | batch) : ~(u64)0;
+		chain_vals[2*i] = 2*i; chain_vals[2*i + 1] = 2*i + 1;
+	}
+}
+
+// predecessor of each contact on body a and body b = previous entry of the same body in (body, batch) order
+__global__ void __launch_bounds__(NB_BLOCK) k_preds(const u64* chain_keys, const u32* chain_vals, u32 batchbits, u32* pred /*[2n]*/, const u32* counts) {
+	u32 n2 = counts[CNT_ENTRIES];
+	for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += gridDim.x * blockDim.x) {
+		u64 k = chain_keys[e];
+		u32 v = chain_vals[e];
+		u32 p = NB_NONE;
+		if (k != ~(u64)0 && e > 0) {
+			u64 kp = chain_keys[e - 1];
+			if ((kp >> batchbits) == (k >> batchbits)) p = chain_vals[e - 1] >> 1;
+		}
+		pred[v] = p;
+	}
+}
+
+// dependency levels by relaxation, all inside one co-resident kernel (one grid barrier per round)
+__global__ void __launch_bounds__(NB_BLOCK) k_levels(const u32* pred, u32* level, u32* level_count, u32 max_levels, u32* counts) {
+	u32 n = counts[CNT_CONTACTS];
+	u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+	for (u32 i = tid; i < n; i += nth) level[i] = 0;
+	for (u32 l = tid; l < max_levels; l += nth) level_count[l] = 0;
+	if (tid == 0) { counts[CNT_LVCH0] = 0; counts[CNT_LVCH0 + 1] = 0; counts[CNT_LVCH0 + 2] = 0; counts[CNT_SCRATCH0] = 0; }
+	grid_barrier(&counts[CNT_BAR0], gridDim.x);
+	// Round r raises flag r%3, everybody reads it after the barrier of round r, and it is cleared during round r+2
+	// (after the barrier of round r+1, which every reader of round r has passed) for its next use in round r+3.
+	for (u32 iter = 0; iter <= max_levels; ++iter) {
+		if (tid == 0) counts[CNT_LVCH0 + (iter + 1) % 3] = 0;
+		bool changed = false;
+		for (u32 i = tid; i < n; i += nth) {
+			u32 pa = pred[2*i], pb = pred[2*i + 1];
+			u32 l = 0;
+			if (pa != NB_NONE) l = max(l, __ldcg(&level[pa]) + 1);
+			if (pb != NB_NONE) l = max(l, __ldcg(&level[pb]) + 1);
+			if (l != __ldcg(&level[i])) { __stcg(&level[i], l); changed = true; }
+		}
+		if (changed) atomicOr(&counts[CNT_LVCH0 + iter % 3], 1u);
+		grid_barrier(&counts[CNT_BAR0], gridDim.x);
+		if (!ld_acquire_u32(&counts[CNT_LVCH0 + iter % 3])) break;
+	}
+	// histogram of levels
+	for (u32 i = tid; i < n; i += nth) {
+		u32 l = __ldcg(&level[i]);
+		if (l >= max_levels) { atomicOr(&counts[CNT_OVERFLOW], OVF_LEVELS); l = max_levels - 1; }
+		atomicAdd(&level_count[l], 1u);
+		atomicMax(&counts[CNT_SCRATCH0], l + 1);
+	}
+}
+
+__global__ void __launch_bounds__(1024) k_level_starts(const u32* level_count, u32* level_start, u32* level_fill, u32 max_levels, u32* counts) {
+	// one block: exclusive scan of level_count (max_levels <= 4096)
+	__shared__ u32 sm[33];
+	__shared__ u32 carry;
+	if (threadIdx.x == 0) { carry = 0; counts[CNT_LEVELS] = counts[CNT_SCRATCH0]; }
+	__syncthreads();
+	for (u32 base = 0; base < max_levels; base += 1024) {
+		u32 i = base + threadIdx.x;
+		u32 v = i < max_levels ? level_count[i] : 0;
+		u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+		u32 incl = warp_incl_scan(v);
+		if (lane == 31) sm[wid] = incl;
+		__syncthreads();
+		if (wid == 0) { u32 w = sm[lane]; u32 wi = warp_incl_scan(w); sm[lane] = wi - w; if (lane == 31) sm[32] = wi; }
+		__syncthreads();
+		u32 ex = incl - v + sm[wid] + carry;
+		if (i < max_levels) { level_start[i] = ex; level_fill[i] = 0; }
+		__syncthreads();
+		if (threadIdx.x == 0) carry += sm[32];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) level_start[max_levels] = carry;
+}
+
+__global__ void __launch_bounds__(NB_BLOCK) k_level_scatter(const u32* level, const u32* level_start, u32* level_fill, u32* slot_to_sorted, u32 max_levels, const u32* counts) {
+	u32 n = counts[CNT_CONTACTS];
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		u32 l = min(level[i], max_levels - 1);
+		u32 pos = level_start[l] + atomicAdd(&level_fill[l], 1u);  // order inside a level is free: its contacts touch disjoint bodies
+		slot_to_sorted[pos] = i;
+	}
+}
+
+// ---------------- constraint rows (nudge.cpp:4350-4561), one thread per contact, SoA planes ----------------
+struct Rows { float* plane; u32 stride; u32* a; u32* b; u32* contact; float* state; };  // plane[k*stride + j], state[k*stride + j]
+
+__global__ void __launch_bounds__(NB_BLOCK) k_build_rows(const u32* slot_to_sorted, const u32* sorted, const float4* contacts, const uint2* bodies,
+		const nb_transform* xf, const float4* inertia, const nb_body_momentum* momentum, Rows R, const u32* counts) {
+	__shared__ u32 s_rsqrt[2048];
+	for (u32 i = threadIdx.x; i < 2048; i += blockDim.x) s_rsqrt[i] = g_rsqrt_lut[i];
+	__syncthreads();
+	u32 n = counts[CNT_CONTACTS];
+	for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+		u32 c = sorted[slot_to_sorted[j]];
+		float4 cp = contacts[2*c], cn = contacts[2*c + 1];
+		uint2 ab = bodies[c];
+		u32 a = ab.x, b = ab.y;
+		float position_x = cp.x, position_y = cp.y, position_z = cp.z, penetration = cp.w;
+		float normal_x = cn.x, normal_y = cn.y, normal_z = cn.z, friction = cn.w;
+		float a_mass_inverse = momentum[a].unused0, b_mass_inverse = momentum[b].unused0;
+		float4 apos = reinterpret_cast<const float4*>(xf + a)[0], bpos = reinterpret_cast<const float4*>(xf + b)[0];
+		f3 pa = mk3(position_x - apos.x, position_y - apos.y, position_z - apos.z);
+		f3 pb = mk3(position_x - bpos.x, position_y - bpos.y, position_z - bpos.z);
+		float4 Ad = inertia[2*a], Ao = inertia[2*a + 1], Bd = inertia[2*b], Bo = inertia[2*b + 1];  // (xx,yy,zz,-) (xy,xz,yz,-)
+		f3 nrm = mk3(normal_x, normal_y, normal_z);
+		f3 nat = cross3(pa, nrm);
+		float na_x = Ad.x*nat.x + Ao.x*nat.y + Ao.y*nat.z;
+		float na_y = Ao.x*nat.x + Ad.y*nat.y + Ao.z*nat.z;
+		float na_z = Ao.y*nat.x + Ao.z*nat.y + Ad.z*nat.z;
+		f3 nbt = cross3(pb, nrm);
+		float nb_x = Bd.x*nbt.x + Bo.x*nbt.y + Bo.y*nbt.z;
+		float nb_y = Bo.x*nbt.x + Bd.y*nbt.y + Bo.z*nbt.z;
+		float nb_z = Bo.y*nbt.x + Bo.z*nbt.y + Bd.z*nbt.z;
+		nat = cross3(mk3(na_x, na_y, na_z), pa);
+		nbt = cross3(mk3(nb_x, nb_y, nb_z), pb);
+		float rx = nat.x + nbt.x, ry = nat.y + nbt.y, rz = nat.z + nbt.z;
+		float r_dot_n = rx*normal_x + ry*normal_y + rz*normal_z;
+		float mass_inverse = a_mass_inverse + b_mass_inverse;
+		float nvtni = mass_inverse + r_dot_n;
+		bool nonzero = nvtni < 0.0f || nvtni > 0.0f;  // _CMP_NEQ_OQ is ordered (nudge.cpp:636-638, 4439)
+		nvtni = nonzero ? (-1.0f / nvtni) : 0.0f;
+		float bias = -2.0f * nb_max(penetration - 1e-3f, 0.0f) * nvtni;  // nudge.cpp:4442 with the constants of 49-50
+		float s = nb_abs(normal_x);
+		float u_x = normal_z*s;
+		float u_y = u_x - normal_z;
+		float u_z = nb_madd(normal_x - normal_y, s, normal_y);
+		u_x = nb_neg(u_x);
+		{ float f = nb_rsqrt_t(u_x*u_x + u_y*u_y + u_z*u_z, s_rsqrt); u_x *= f; u_y *= f; u_z *= f; }
+		f3 u = mk3(u_x, u_y, u_z);
+		f3 v = cross3(u, nrm);
+		f3 ua = cross3(pa, u), va = cross3(pa, v), ub = cross3(pb, u), vb = cross3(pb, v);
+		float a_duu = Ad.x*ua.x*ua.x + Ad.y*ua.y*ua.y + Ad.z*ua.z*ua.z;
+		float a_dvv = Ad.x*va.x*va.x + Ad.y*va.y*va.y + Ad.z*va.z*va.z;
+		float a_duv = Ad.x*ua.x*va.x + Ad.y*ua.y*va.y + Ad.z*ua.z*va.z;
+		float a_suu = Ao.x*ua.x*ua.y + Ao.y*ua.x*ua.z + Ao.z*ua.y*ua.z;
+		float a_svv = Ao.x*va.x*va.y + Ao.y*va.x*va.z + Ao.z*va.y*va.z;
+		float a_suv = Ao.x*(ua.x*va.y + ua.y*va.x) + Ao.y*(ua.x*va.z + ua.z*va.x) + Ao.z*(ua.y*va.z + ua.z*va.y);
+		float b_duu = Bd.x*ub.x*ub.x + Bd.y*ub.y*ub.y + Bd.z*ub.z*ub.z;
+		float b_dvv = Bd.x*vb.x*vb.x + Bd.y*vb.y*vb.y + Bd.z*vb.z*vb.z;
+		float b_duv = Bd.x*ub.x*vb.x + Bd.y*ub.y*vb.y + Bd.z*ub.z*vb.z;
+		float b_suu = Bo.x*ub.x*ub.y + Bo.y*ub.x*ub.z + Bo.z*ub.y*ub.z;
+		float b_svv = Bo.x*vb.x*vb.y + Bo.y*vb.x*vb.z + Bo.z*vb.y*vb.z;
+		float b_suv = Bo.x*(ub.x*vb.y + ub.y*vb.x) + Bo.y*(ub.x*vb.z + ub.z*vb.x) + Bo.z*(ub.y*vb.z + ub.z*vb.y);
+		float friction_x = mass_inverse + a_duu + a_suu + a_suu + b_duu + b_suu + b_suu;
+		float friction_y = mass_inverse + a_dvv + a_svv + a_svv + b_dvv + b_svv + b_svv;
+		float friction_z = a_duv + a_duv + a_suv + a_suv + b_duv + b_duv + b_suv + b_suv;
+		float ua_xt = Ad.x*ua.x + Ao.x*ua.y + Ao.y*ua.z, ua_yt = Ao.x*ua.x + Ad.y*ua.y + Ao.z*ua.z, ua_zt = Ao.y*ua.x + Ao.z*ua.y + Ad.z*ua.z;
+		float va_xt = Ad.x*va.x + Ao.x*va.y + Ao.y*va.z, va_yt = Ao.x*va.x + Ad.y*va.y + Ao.z*va.z, va_zt = Ao.y*va.x + Ao.z*va.y + Ad.z*va.z;
+		float ub_xt = Bd.x*ub.x + Bo.x*ub.y + Bo.y*ub.z, ub_yt = Bo.x*ub.x + Bd.y*ub.y + Bo.z*ub.z, ub_zt = Bo.y*ub.x + Bo.z*ub.y + Bd.z*ub.z;
+		float vb_xt = Bd.x*vb.x + Bo.x*vb.y + Bo.y*vb.z, vb_yt = Bo.x*vb.x + Bd.y*vb.y + Bo.z*vb.z, vb_zt = Bo.y*vb.x + Bo.z*vb.y + Bd.z*vb.z;
+		float* P = R.plane + j; const u32 S = R.stride;
+		P[N_X*S] = normal_x; P[N_Y*S] = normal_y; P[N_Z*S] = normal_z;
+		P[PA_X*S] = pa.x; P[PA_Y*S] = pa.y; P[PA_Z*S] = pa.z; P[PB_X*S] = pb.x; P[PB_Y*S] = pb.y; P[PB_Z*S] = pb.z;
+		P[NVTNI*S] = nvtni; P[BIAS*S] = bias; P[FRICTION*S] = friction;
+		P[U_X*S] = u.x; P[U_Y*S] = u.y; P[U_Z*S] = u.z; P[V_X*S] = v.x; P[V_Y*S] = v.y; P[V_Z*S] = v.z;
+		P[FC_X*S] = friction_x; P[FC_Y*S] = friction_y; P[FC_Z*S] = friction_z;
+		P[UA_X*S] = nb_neg(ua_xt); P[UA_Y*S] = nb_neg(ua_yt); P[UA_Z*S] = nb_neg(ua_zt);
+		P[VA_X*S] = nb_neg(va_xt); P[VA_Y*S] = nb_neg(va_yt); P[VA_Z*S] = nb_neg(va_zt);
+		P[NA_X*S] = nb_neg(na_x); P[NA_Y*S] = nb_neg(na_y); P[NA_Z*S] = nb_neg(na_z);
+		P[UB_X*S] = ub_xt; P[UB_Y*S] = ub_yt; P[UB_Z*S] = ub_zt; P[VB_X*S] = vb_xt; P[VB_Y*S] = vb_yt; P[VB_Z*S] = vb_zt;
+		P[NB_X*S] = nb_x; P[NB_Y*S] = nb_y; P[NB_Z*S] = nb_z;
+		R.a[j] = a; R.b[j] = b; R.contact[j] = c;
+	}
+}
+
+// body momentum rows are shared between SMs inside the level loop: always go through L2
+NB_DEV void ld_momentum(const nb_body_momentum* m, u32 i, float4& lin, float4& ang) {
+	const float4* p = reinterpret_cast<const float4*>(m + i);
+	lin = __ldcg(p); ang = __ldcg(p + 1);
+}
+NB_DEV void st_momentum(nb_body_momentum* m, u32 i, float4 lin, float4 ang) {
+	float4* p = reinterpret_cast<float4*>(m + i);
+	__stcg(p, lin); __stcg(p + 1, ang);
+}
+
+// One contact of the warm start (nudge.cpp:4563-4632).
+NB_DEV void warm_start_contact(const Rows& R, u32 j, const float4* impulses, nb_body_momentum* momentum, const u32* s_rsqrt) {
+	const float* P = R.plane + j; const u32 S = R.stride;
+	u32 a = R.a[j], b = R.b[j];
+	float4 ci = impulses[R.contact[j]];
+	float4 al, aw, bl, bw;
+	ld_momentum(momentum, a, al, aw); ld_momentum(momentum, b, bl, bw);
+	float n_x = P[N_X*S], n_y = P[N_Y*S], n_z = P[N_Z*S];
+	float u_x = P[U_X*S], u_y = P[U_Y*S], u_z = P[U_Z*S], v_x = P[V_X*S], v_y = P[V_Y*S], v_z = P[V_Z*S];
+	float normal_impulse = nb_max(n_x*ci.x + n_y*ci.y + n_z*ci.z, 0.0f);
+	float max_friction_impulse = normal_impulse * P[FRICTION*S];
+	float fix = u_x*ci.x + u_y*ci.y + u_z*ci.z;
+	float fiy = v_x*ci.x + v_y*ci.y + v_z*ci.z;
+	float fcs = fix*fix + fiy*fiy;
+	fcs = nb_rsqrt_t(fcs, s_rsqrt);
+	fcs = fcs * max_friction_impulse;
+	fcs = nb_min(1.0f, fcs);  // first operand on NaN
+	fix = fix * fcs; fiy = fiy * fcs;
+	float lx = fix*u_x + fiy*v_x + n_x * normal_impulse;
+	float ly = fix*u_y + fiy*v_y + n_y * normal_impulse;
+	float lz = fix*u_z + fiy*v_z + n_z * normal_impulse;
+	float aax = fix*P[UA_X*S] + fiy*P[VA_X*S] + normal_impulse*P[NA_X*S];
+	float aay = fix*P[UA_Y*S] + fiy*P[VA_Y*S] + normal_impulse*P[NA_Y*S];
+	float aaz = fix*P[UA_Z*S] + fiy*P[VA_Z*S] + normal_impulse*P[NA_Z*S];
+	float bax = fix*P[UB_X*S] + fiy*P[VB_X*S] + normal_impulse*P[NB_X*S];
+	float bay = fix*P[UB_Y*S] + fiy*P[VB_Y*S] + normal_impulse*P[NB_Y*S];
+	float baz = fix*P[UB_Z*S] + fiy*P[VB_Z*S] + normal_impulse*P[NB_Z*S];
+	al.x -= lx * al.w; al.y -= ly * al.w; al.z -= lz * al.w;
+	aw.x += aax; aw.y += aay; aw.z += aaz;
+	bl.x += lx * bl.w; bl.y += ly * bl.w; bl.z += lz * bl.w;
+	bw.x += bax; bw.y += bay; bw.z += baz;
+	R.state[0*S + j] = normal_impulse; R.state[1*S + j] = fix; R.state[2*S + j] = fiy;
+	if (a) st_momentum(momentum, a, al, aw);  // body 0 is static: its row only ever changes by +-0
+	if (b) st_momentum(momentum, b, bl, bw);
+}
+
+// One contact of one projected Gauss-Seidel sweep (nudge.cpp:4646-4853), same operation order, FMAs where the source has madd.
+NB_DEV void solve_contact(const Rows& R, u32 j, nb_body_momentum* momentum, const u32* s_rcp, const u32* s_rsqrt) {
+	const float* c = R.plane + j; const u32 S = R.stride;
+	u32 a = R.a[j], b = R.b[j];
+	float4 al, aw, bl, bw;
+	ld_momentum(momentum, a, al, aw); ld_momentum(momentum, b, bl, bw);
+	float a_velocity_x = al.x, a_velocity_y = al.y, a_velocity_z = al.z, a_mass_inverse = al.w;
+	float a_angular_velocity_x = aw.x, a_angular_velocity_y = aw.y, a_angular_velocity_z = aw.z;
+	float b_velocity_x = bl.x, b_velocity_y = bl.y, b_velocity_z = bl.z, b_mass_inverse = bl.w;
+	float b_angular_velocity_x = bw.x, b_angular_velocity_y = bw.y, b_angular_velocity_z = bw.z;
+	float pa_z = c[PA_Z*S], pa_x = c[PA_X*S], pa_y = c[PA_Y*S];
+	float v_xa = nb_madd(a_angular_velocity_y, pa_z, a_velocity_x);
+	float v_ya = nb_madd(a_angular_velocity_z, pa_x, a_velocity_y);
+	float v_za = nb_madd(a_angular_velocity_x, pa_y, a_velocity_z);
+	float pb_z = c[PB_Z*S], pb_x = c[PB_X*S], pb_y = c[PB_Y*S];
+	float v_xb = nb_madd(b_angular_velocity_y, pb_z, b_velocity_x);
+	float v_yb = nb_madd(b_angular_velocity_z, pb_x, b_velocity_y);
+	float v_zb = nb_madd(b_angular_velocity_x, pb_y, b_velocity_z);
+	v_xa = nb_madd(b_angular_velocity_z, pb_y, v_xa);
+	v_ya = nb_madd(b_angular_velocity_x, pb_z, v_ya);
+	v_za = nb_madd(b_angular_velocity_y, pb_x, v_za);
+	float n_x = c[N_X*S], fu_x = c[U_X*S], fv_x = c[V_X*S];
+	v_xb = nb_madd(a_angular_velocity_z, pa_y, v_xb);
+	v_yb = nb_madd(a_angular_velocity_x, pa_z, v_yb);
+	v_zb = nb_madd(a_angular_velocity_y, pa_x, v_zb);
+	float n_y = c[N_Y*S], fu_y = c[U_Y*S], fv_y = c[V_Y*S];
+	float v_x = v_xb - v_xa, v_y = v_yb - v_ya, v_z = v_zb - v_za;
+	float t_z = n_x * v_x, t_x = v_x * fu_x, t_y = v_x * fv_x;
+	float n_z = c[N_Z*S], fu_z = c[U_Z*S], fv_z = c[V_Z*S];
+	float normal_bias = c[BIAS*S];
+	float old_normal_impulse = __ldcg(&R.state[0*S + j]);
+	float normal_factor = c[NVTNI*S];
+	t_z = nb_madd(n_y, v_y, t_z); t_x = nb_madd(v_y, fu_y, t_x); t_y = nb_madd(v_y, fv_y, t_y);
+	normal_bias = normal_bias + old_normal_impulse;
+	t_z = nb_madd(n_z, v_z, t_z); t_x = nb_madd(v_z, fu_z, t_x); t_y = nb_madd(v_z, fv_z, t_y);
+	float normal_impulse = nb_madd(normal_factor, t_z, normal_bias);
+	float t_xx = t_x*t_x, t_yy = t_y*t_y, t_xy = t_x*t_y;
+	float tl2 = t_xx + t_yy;
+	normal_impulse = nb_max(normal_impulse, 0.0f);
+	t_x *= tl2; t_y *= tl2;
+	__stcg(&R.state[0*S + j], normal_impulse);
+	float max_friction_impulse = normal_impulse * c[FRICTION*S];
+	normal_impulse = normal_impulse - old_normal_impulse;
+	float friction_factor = t_xx * c[FC_X*S];
+	float linear_impulse_x = n_x * normal_impulse;
+	friction_factor = nb_madd(t_yy, c[FC_Y*S], friction_factor);
+	float linear_impulse_y = n_y * normal_impulse;
+	friction_factor = nb_madd(t_xy, c[FC_Z*S], friction_factor);
+	float linear_impulse_z = n_z * normal_impulse;
+	friction_factor = nb_rcp_t(friction_factor, s_rcp);
+	a_angular_velocity_x = nb_madd(c[NA_X*S], normal_impulse, a_angular_velocity_x);
+	a_angular_velocity_y = nb_madd(c[NA_Y*S], normal_impulse, a_angular_velocity_y);
+	a_angular_velocity_z = nb_madd(c[NA_Z*S], normal_impulse, a_angular_velocity_z);
+	float old_friction_impulse_x = __ldcg(&R.state[1*S + j]), old_friction_impulse_y = __ldcg(&R.state[2*S + j]);
+	friction_factor = nb_min(1e+6f, friction_factor);  // first operand on NaN
+	float friction_impulse_x = t_x*friction_factor, friction_impulse_y = t_y*friction_factor;
+	friction_impulse_x = old_friction_impulse_x - friction_impulse_x;
+	friction_impulse_y = old_friction_impulse_y - friction_impulse_y;
+	float friction_clamp_scale = friction_impulse_x*friction_impulse_x + friction_impulse_y*friction_impulse_y;
+	friction_clamp_scale = nb_rsqrt_t(friction_clamp_scale, s_rsqrt);
+	b_angular_velocity_x = nb_madd(c[NB_X*S], normal_impulse, b_angular_velocity_x);
+	b_angular_velocity_y = nb_madd(c[NB_Y*S], normal_impulse, b_angular_velocity_y);
+	b_angular_velocity_z = nb_madd(c[NB_Z*S], normal_impulse, b_angular_velocity_z);
+	friction_clamp_scale = friction_clamp_scale * max_friction_impulse;
+	friction_clamp_scale = nb_min(1.0f, friction_clamp_scale);
+	friction_impulse_x = friction_impulse_x * friction_clamp_scale;
+	friction_impulse_y = friction_impulse_y * friction_clamp_scale;
+	__stcg(&R.state[1*S + j], friction_impulse_x); __stcg(&R.state[2*S + j], friction_impulse_y);
+	friction_impulse_x -= old_friction_impulse_x;
+	friction_impulse_y -= old_friction_impulse_y;
+	linear_impulse_x = nb_madd(fu_x, friction_impulse_x, linear_impulse_x);
+	linear_impulse_y = nb_madd(fu_y, friction_impulse_x, linear_impulse_y);
+	linear_impulse_z = nb_madd(fu_z, friction_impulse_x, linear_impulse_z);
+	linear_impulse_x = nb_madd(fv_x, friction_impulse_y, linear_impulse_x);
+	linear_impulse_y = nb_madd(fv_y, friction_impulse_y, linear_impulse_y);
+	linear_impulse_z = nb_madd(fv_z, friction_impulse_y, linear_impulse_z);
+	float a_mass_inverse_neg = nb_neg(a_mass_inverse);
+	a_velocity_x = nb_madd(linear_impulse_x, a_mass_inverse_neg, a_velocity_x);
+	a_velocity_y = nb_madd(linear_impulse_y, a_mass_inverse_neg, a_velocity_y);
+	a_velocity_z = nb_madd(linear_impulse_z, a_mass_inverse_neg, a_velocity_z);
+	a_angular_velocity_x = nb_madd(c[UA_X*S], friction_impulse_x, a_angular_velocity_x);
+	a_angular_velocity_y = nb_madd(c[UA_Y*S], friction_impulse_x, a_angular_velocity_y);
+	a_angular_velocity_z = nb_madd(c[UA_Z*S], friction_impulse_x, a_angular_velocity_z);
+	a_angular_velocity_x = nb_madd(c[VA_X*S], friction_impulse_y, a_angular_velocity_x);
+	a_angular_velocity_y = nb_madd(c[VA_Y*S], friction_impulse_y, a_angular_velocity_y);
+	a_angular_velocity_z = nb_madd(c[VA_Z*S], friction_impulse_y, a_angular_velocity_z);
+	b_velocity_x = nb_madd(linear_impulse_x, b_mass_inverse, b_velocity_x);
+	b_velocity_y = nb_madd(linear_impulse_y, b_mass_inverse, b_velocity_y);
+	b_velocity_z = nb_madd(linear_impulse_z, b_mass_inverse, b_velocity_z);
+	b_angular_velocity_x = nb_madd(c[UB_X*S], friction_impulse_x, b_angular_velocity_x);
+	b_angular_velocity_y = nb_madd(c[UB_Y*S], friction_impulse_x, b_angular_velocity_y);
+	b_angular_velocity_z = nb_madd(c[UB_Z*S], friction_impulse_x, b_angular_velocity_z);
+	b_angular_velocity_x = nb_madd(c[VB_X*S], friction_impulse_y, b_angular_velocity_x);
+	b_angular_velocity_y = nb_madd(c[VB_Y*S], friction_impulse_y, b_angular_velocity_y);
+	b_angular_velocity_z = nb_madd(c[VB_Z*S], friction_impulse_y, b_angular_velocity_z);
+	// unused1 is zeroed on touched bodies (nudge.cpp:4823, 4849)
+	if (a) st_momentum(momentum, a, make_float4(a_velocity_x, a_velocity_y, a_velocity_z, a_mass_inverse), make_float4(a_angular_velocity_x, a_angular_velocity_y, a_angular_velocity_z, 0.0f));
+	if (b) st_momentum(momentum, b, make_float4(b_velocity_x, b_velocity_y, b_velocity_z, b_mass_inverse), make_float4(b_angular_velocity_x, b_angular_velocity_y, b_angular_velocity_z, 0.0f));
+}
+
+// mode 0: warm start (one pass); mode 1: `sweeps` PGS sweeps.  Co-resident grid, barrier between levels.
+__global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impulses, nb_body_momentum* momentum, const u32* level_start, int mode, u32 sweeps, u32* counts) {
+	__shared__ u32 s_rcp[2048];
+	__shared__ u32 s_rsqrt[2048];
+	for (u32 i = threadIdx.x; i < 2048; i += blockDim.x) { s_rcp[i] = g_rcp_lut[i]; s_rsqrt[i] = g_rsqrt_lut[i]; }
+	__syncthreads();
+	u32 levels = counts[CNT_LEVELS];
+	u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+	u32 passes = mode ? sweeps : 1;
+	for (u32 s = 0; s < passes; ++s)
+		for (u32 l = 0; l < levels; ++l) {
+			u32 begin = level_start[l], end = level_start[l + 1];
+			for (u32 j = begin + tid; j < end; j += nth) {
+				if (mode) solve_contact(R, j, momentum, s_rcp, s_rsqrt);
+				else warm_start_contact(R, j, impulses, momentum, s_rsqrt);
+			}
+			grid_barrier(&counts[CNT_BAR0], gridDim.x);
+		}
+}
+
+// ---------------- update_cached_impulses (nudge.cpp:4857-4884) ----------------
+__global__ void __launch_bounds__(NB_BLOCK) k_update_impulses(Rows R, float4* impulses, const u32* counts) {
+	u32 n = counts[CNT_CONTACTS];
+	for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+		const float* c = R.plane + j; const u32 S = R.stride;
+		float s0 = R.state[0*S + j], s1 = R.state[1*S + j], s2 = R.state[2*S + j];
+		float4* dst = impulses + R.contact[j];
+		float4 v = *dst;
+		v.x = s0*c[N_X*S] + s1*c[U_X*S] + s2*c[V_X*S];
+		v.y = s0*c[N_Y*S] + s1*c[U_Y*S] + s2*c[V_Y*S];
+		v.z = s0*c[N_Z*S] + s1*c[U_Z*S] + s2*c[V_Z*S];
+		*dst = v;
+	}
+}
+
+// ---------------- user gravity/damping loop (example/main.cpp:291-305) and advance (nudge.cpp:4886-4926) ----------------
+__global__ void __launch_bounds__(NB_BLOCK) k_gravity_damping(const u32* active_idx, nb_body_momentum* momentum, float time_step, float gravity, float damping_base, const u32* counts) {
+	u32 n = counts[CNT_ACTIVE];
+	float damping = 1.0f - time_step*damping_base;
+	float dv = gravity * time_step;
+	for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		u32 i = active_idx[k];
+		float4* p = reinterpret_cast<float4*>(momentum + i);
+		float4 l = p[0], w = p[1];
+		l.y -= dv;
+		l.x *= damping; l.y *= damping; l.z *= damping;
+		w.x *= damping; w.y *= damping; w.z *= damping;
+		p[0] = l; p[1] = w;
+	}
+}
+
+__global__ void __launch_bounds__(NB_BLOCK) k_advance(const u32* active_idx, nb_transform* xf, const nb_body_momentum* momentum, uint8_t* idle, float time_step, const u32* counts) {
+	u32 n = counts[CNT_ACTIVE];
+	float half_time_step = 0.5f * time_step;
+	for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		u32 i = active_idx[k];
+		const float4* mp = reinterpret_cast<const float4*>(momentum + i);
+		float4 l = mp[0], w = mp[1];
+		f3 velocity = mk3(l.x, l.y, l.z), angular_velocity = mk3(w.x, w.y, w.z);
+		if (dot3(velocity, velocity) < 1e-2f && dot3(angular_velocity, angular_velocity) < 1e-1f) {
+			uint8_t c = idle[i];
+			if (c < 0xff) idle[i] = c + 1;
+		}
+		else idle[i] = 0;
+		xform t = ld_xform(xf, i);
+		quat dr; dr.v = angular_velocity; dr.s = 0.0f;
+		dr = qmul(dr, mkq(t.q));
+		dr.v = mul3(dr.v, half_time_step); dr.s *= half_time_step;
+		t.p.x += velocity.x * time_step; t.p.y += velocity.y * time_step; t.p.z += velocity.z * time_step;
+		t.q.x += dr.v.x; t.q.y += dr.v.y; t.q.z += dr.v.z; t.q.w += dr.s;
+		float f = 1.0f / sqrtf(t.q.w*t.q.w + t.q.x*t.q.x + t.q.y*t.q.y + t.q.z*t.q.z);  // nudge.cpp:1128-1133
+		t.q.x *= f; t.q.y *= f; t.q.z *= f; t.q.w *= f;
+		st_xform(xf, i, t);
+	}
+}
