@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py — simulation steps/s of the rigid-body step (collide -> cache -> setup -> N sweeps -> cache -> advance).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU implementation on the host cores
+
+Workload (BASELINE.json configs[1]): 65,536 random boxes dropped onto a ground plane, 8 solver iterations, measured on the
+settled pile.  One "step" = one sub-step of example/main.cpp:274-328.  Prints ONE JSON line (see README / DESIGN.md §5)."""
+import argparse, json, os, subprocess, sys, threading, time
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from nudge_b200 import scenes  # noqa: E402
+
+WORKLOAD = "64k boxes random drop onto ground plane, 8 solver iters (BASELINE.json configs[1]), settled pile"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.rows = []; self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def settle_gpu(sim, steps):
+    for _ in range(steps):
+        sim.step()
+    return sim.counts()
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import nudge_b200
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream().cuda_stream
+    scene = scenes.box_drop(args.boxes, iterations=args.iterations, seed=2 + rank)
+    sim = nudge_b200.Sim(scene, device=local, stream=stream)
+    c = settle_gpu(sim, args.presim)
+    if c.overflow:
+        raise RuntimeError("capacity overflow during settling: %d" % c.overflow)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def staged_step(ev=None):
+        sim.collide(); sim.apply_gravity_damping(); sim.read_cached_impulses(); sim.setup_contact_constraints()
+        if ev: ev[0].record()
+        sim.apply_impulses(scene.iterations)
+        if ev: ev[1].record()
+        sim.update_cached_impulses(); sim.write_cached_impulses(); sim.advance()
+
+    for _ in range(max(args.warmup, 3)):
+        staged_step()
+    K = args.steps
+    E = lambda: torch.cuda.Event(enable_timing=True)
+    step_ev = [(E(), E()) for _ in range(K)]; solve_ev = [(E(), E()) for _ in range(K)]
+    sampler = ClockSampler(local); sampler.start()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = sim.launch_count()
+    wall0 = time.perf_counter()
+    for k in range(K):
+        flush.fill_(k & 255)                      # L2 flush between timed iterations (not part of the step time)
+        step_ev[k][0].record()
+        staged_step(solve_ev[k])
+        step_ev[k][1].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = sim.launch_count() - launches0
+    if world > 1: dist.barrier()
+    sampler.stop_flag = True
+    step_ms = [a.elapsed_time(b) for a, b in step_ev]
+    solve_ms = [a.elapsed_time(b) for a, b in solve_ev]
+    total_ms = float(sum(step_ms))
+    cnt = sim.counts()
+
+    # ---- end to end through the public API with HOST buffers (pinned): upload state, step, read state back ----
+    nb = scene.n_bodies
+    pinned = {}
+    for name in ("transforms", "properties", "momentum", "idle"):
+        a = getattr(sim, name)
+        t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+        v = t.numpy().view(a.dtype)[:len(a)]
+        v[:] = a
+        pinned[name] = (t, v); setattr(sim, name, v)
+    from nudge_b200 import abi
+    sim.bodies = abi.BodyData(abi.ptr(sim.transforms), abi.ptr(sim.properties), abi.ptr(sim.momentum), abi.ptr(sim.idle), nb)
+    sim.download_bodies()
+    h2d = sum(getattr(sim, n).nbytes for n in ("transforms", "properties", "momentum", "idle"))
+    d2h = sum(getattr(sim, n).nbytes for n in ("transforms", "momentum", "idle"))
+    for _ in range(3):
+        sim.upload_bodies(); sim.step(); sim.download_bodies()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = E(), E()
+    e0.record()
+    for k in range(K):
+        sim.upload_bodies(); sim.step(); sim.download_bodies()   # download synchronises: the caller holds the new transforms
+    e1.record(); torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([total_ms, e2e_ms, float(cnt.contacts), float(sum(solve_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms = float(tmax[0]), float(tmax[1]); contacts_all = float(tsum[2])
+    else:
+        contacts_all = float(cnt.contacts)
+    if rank != 0:
+        if world > 1: dist.destroy_process_group()
+        return
+    steps_per_s = world * K / (total_ms * 1e-3)          # every rank advances its own 64k-box scene: replicas of the workload
+    e2e_steps_per_s = world * K / (e2e_ms * 1e-3)
+    peak, peak_src = peaks()
+    sweeps = scene.iterations
+    C, A = cnt.contacts, cnt.active
+    alg_bytes = (184.0 * C + 64.0 * A) * sweeps            # per sweep 184 B/contact + 64 B/active body
+    solve_avg_ms = float(np.mean(solve_ms))
+    achieved = alg_bytes / (solve_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "solver_traffic.json")
+    if os.path.exists(tp):
+        try: traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception: traffic = None
+    line = {
+        "metric": "simulation steps/s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "bodies_per_gpu": scene.n_bodies, "colliders_per_gpu": scene.n_colliders, "solver_iterations": sweeps,
+                   "contacts": int(C), "broadphase_pairs": int(cnt.pairs), "batches": int(cnt.batches), "gs_levels": int(cnt.levels),
+                   "presim_steps": args.presim, "solver_mode": "exact reference Gauss-Seidel order (level-scheduled)",
+                   "parallelism": "1 GPU" if world == 1 else "%d independent replicas of the workload, one per GPU (no cross-GPU contacts)" % world,
+                   "l2": "flushed between timed steps (256 MiB write), flush excluded from step time", "timing": "CUDA events per step, summed; max over ranks"},
+        "contacts_solved_per_s": contacts_all * sweeps * K / (total_ms * 1e-3),
+        "wall_ms_per_step_incl_flush": wall * 1e3 / K,
+        "solver_share_of_step": float(sum(solve_ms)) / float(sum(step_ms)),
+        "roofline": {"bound": "hbm", "kernel": "k_solve (8 sweeps per launch)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": solve_avg_ms,
+                     "note": "latency bound: %d dependent levels x %d sweeps, one grid barrier each" % (cnt.levels, sweeps)},
+        "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "what": "nb_upload_bodies (pinned host) + nb_step + nb_download_bodies per step"},
+        "gpu_launches": int(launches), "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(args)
+    print(json.dumps(line))
+    if world > 1: dist.destroy_process_group()
+
+
+def cpu_baseline_sample(args):
+    """The unmodified reference (oracle/_ref, -O3 -mavx2 -mfma, FTZ/DAZ on like example/main.cpp:338-339) on the host: one
+    8191-box pile of the same generator (the reference's 2^13 collider limit, nudge.cpp:3010), settled on the GPU, then timed."""
+    import nudge_b200
+    from oracle import pyref
+    s = scenes.box_drop(8191, iterations=args.iterations, seed=77)
+    g = nudge_b200.Sim(s)
+    settle_gpu(g, args.presim)
+    g.download_bodies(); g.download_cache()
+    r = pyref.RefSim(s, fast=True, ftz=True, contact_capacity=g.cap)
+    r.transforms[:] = g.transforms; r.momentum[:] = g.momentum; r.idle[:] = g.idle
+    from nudge_b200 import abi
+    n = g.cache.count
+    r.cache_tags[:n] = abi.wide_tag_to_ref(g.cache_tags[:n], g.cache_features[:n]); r.cache_data[:n] = g.cache_data[:n]; r.cache.count = n
+    g.close()
+    for _ in range(5):
+        r.step()
+    t0 = time.perf_counter(); k = 0
+    while time.perf_counter() - t0 < 10.0:
+        r.step(); k += 1
+    dt = time.perf_counter() - t0
+    return {"value": k / dt, "unit": "steps/s", "cores": 1, "kind": "reference",
+            "sample": "one 8191-box settled pile (%d contacts) of the same generator, %d steps in %.1f s; the reference cannot run 65,536 boxes (nudge.cpp:3010)" % (r.contacts.count, k, dt),
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation (oracle/_ref) with all the host threads it can use.  The library is
+    single threaded and capped at 8192 colliders, so the 65,536-box workload is run as 8 independent 8191-box piles, one thread each."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import pyref
+    tiles = 8
+    threads = min(tiles, os.cpu_count() or 1)
+    sims = [None] * tiles
+
+    def work(fn):
+        ths = [threading.Thread(target=fn, args=(t,)) for t in range(tiles)]
+        # at most `threads` run at once
+        for b in range(0, tiles, threads):
+            for th in ths[b:b + threads]: th.start()
+            for th in ths[b:b + threads]: th.join()
+
+    def make(t):
+        s = scenes.box_drop(8191, iterations=args.iterations, seed=100 + t)
+        sims[t] = pyref.RefSim(s, fast=True, ftz=True)
+        for _ in range(args.ref_presim):
+            sims[t].step()
+
+    def step(t):
+        sims[t].lib.ref_set_ftz_daz(1)
+        sims[t].step()
+
+    work(make)
+    for _ in range(max(args.warmup, 1)):
+        work(step)
+    K = min(args.steps, args.ref_steps)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        work(step)
+    dt = time.perf_counter() - t0
+    value = K / dt
+    contacts = sum(s.contacts.count for s in sims)
+    line = {"impl": "reference", "metric": "simulation steps/s", "value": value, "unit": "steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K,
+            "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": "8 independent 8191-box piles (65,528 boxes, %d contacts) stepped together, one host thread each" % contacts,
+                       "solver_iterations": args.iterations, "presim_steps": args.ref_presim},
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "reference",
+                             "sample": "8 x 8191-box piles per step; unmodified nudge.cpp, g++ -O3 -mavx2 -mfma, FTZ/DAZ on"},
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--boxes", type=int, default=65536)
+    ap.add_argument("--iterations", type=int, default=8)
+    ap.add_argument("--presim", type=int, default=900, help="untimed settling steps before the measurement")
+    ap.add_argument("--ref-presim", type=int, default=700)
+    ap.add_argument("--ref-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

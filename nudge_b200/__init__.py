@@ -16,7 +16,7 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_download_bodies", "nb_download_contacts", "nb_download_cache", "nb_download_counts", "nb_upload_momentum", "nb_upload_transforms",
            "nb_download_momentum", "nb_download_transforms", "nb_collide", "nb_apply_gravity_damping", "nb_read_cached_impulses",
            "nb_setup_contact_constraints", "nb_apply_impulses", "nb_update_cached_impulses", "nb_write_cached_impulses", "nb_advance", "nb_step",
-           "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact"]
+           "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact", "nb_debug_sort", "nb_debug_scan", "nb_debug_enable"]
 
 
 class Config(C.Structure):
@@ -57,6 +57,9 @@ def load_library():
         lib.nb_debug_read.argtypes = [V, C.c_char_p, V, C.c_size_t, V, V]
         lib.nb_debug_rcp.argtypes = [V, V, V, C.c_uint32, C.c_int]
         lib.nb_lut_model_exact.argtypes = [V]
+        lib.nb_debug_sort.argtypes = [V, V, V, C.c_uint32, C.c_int, C.c_int]
+        lib.nb_debug_scan.argtypes = [V, V, C.c_uint32, V]
+        lib.nb_debug_enable.argtypes = [V, C.c_int]
         _lib = lib
     return _lib
 
@@ -71,7 +74,7 @@ class Sim(abi.HostState):
     Host arrays (self.transforms, self.momentum, ...) are the caller-owned copies; `upload()` / `download_bodies()`
     move them across.  `stream` is a raw cudaStream_t (0 = default stream)."""
 
-    def __init__(self, scene, contact_capacity=None, pair_capacity=None, device=0, stream=0):
+    def __init__(self, scene, contact_capacity=None, pair_capacity=None, device=0, stream=0, debug=False):
         super().__init__(scene, contact_capacity)
         self.lib = load_library()
         self.stream = C.c_void_p(stream)
@@ -82,6 +85,8 @@ class Sim(abi.HostState):
         if r != 0:
             msg = self.lib.nb_last_error(self.ctx).decode() if self.ctx else "nb_create failed"
             raise NudgeError("nb_create: %s (%d)" % (msg, r))
+        if debug:
+            self._ck(self.lib.nb_debug_enable(self.ctx, 1), "nb_debug_enable")
         self.upload()
 
     def close(self):
@@ -181,8 +186,22 @@ class Sim(abi.HostState):
 
     def device_rcp(self, x, rsqrt=False):
         x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x)
-        self._ck(self.lib.nb_debug_rcp(self.ctx, abi.ptr(x), abi.ptr(y), len(x), 1 if rsqrt else 0), "nb_debug_rcp")
+        for b in range(0, len(x), 1024):
+            xs = np.ascontiguousarray(x[b:b + 1024]); ys = np.empty_like(xs)
+            self._ck(self.lib.nb_debug_rcp(self.ctx, abi.ptr(xs), abi.ptr(ys), len(xs), 1 if rsqrt else 0), "nb_debug_rcp")
+            y[b:b + 1024] = ys
         return y
+
+    def device_sort(self, keys, vals=None, begin_bit=0, end_bit=64):
+        keys = np.ascontiguousarray(keys, np.uint64).copy()
+        v = np.ascontiguousarray(vals, np.uint32).copy() if vals is not None else None
+        self._ck(self.lib.nb_debug_sort(self.ctx, abi.ptr(keys), abi.ptr(v) if v is not None else None, len(keys), begin_bit, end_bit), "nb_debug_sort")
+        return keys, v
+
+    def device_scan(self, data):
+        d = np.ascontiguousarray(data, np.uint32).copy(); total = np.zeros(1, np.uint32)
+        self._ck(self.lib.nb_debug_scan(self.ctx, abi.ptr(d), len(d), abi.ptr(total)), "nb_debug_scan")
+        return d, int(total[0])
 
     def pairs_view(self):
         kbits = self.debug_scalar("kbits")

@@ -39,6 +39,8 @@ struct nb_context {
 	float4* tree_min; float4* tree_max;
 	SortBuffers sb; u32 sort_cap;
 	u64* pair_keys;  // alias into sb.keys[] after the pair sort
+	u64* pair_keys_debug;  // copy kept for parity tests when debug is enabled (the sort buffers are reused later in the step)
+	int debug;
 	u32* flags; u32* offs; u32* block_sums;
 	uint2* live;
 	ContactOut staged, fin;
@@ -151,6 +153,7 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ALLOC(ctx->rows.a, C); ALLOC(ctx->rows.b, C); ALLOC(ctx->rows.contact, C);
 	ctx->rows.stride = ctx->cstride;
 	ctx->pair_keys = ctx->sb.keys[0];
+	ctx->pair_keys_debug = nullptr; ctx->debug = 0;
 
 	// rcpps / rsqrtps tables from this host's CPU
 	u32 rcp_lut[2048], rsqrt_lut[2048];
@@ -309,6 +312,7 @@ int nb_collide(nb_context* ctx, void* stream) {
 	ctx->launches += 2;
 	cur = nb_radix_sort(L, ctx->sb, counts + CNT_PAIRS, 0, (int)(2 * ctx->kbits), false, 0);  // nudge.cpp:3498
 	ctx->pair_keys = ctx->sb.keys[cur];
+	if (ctx->debug) { k_copy_u64<<<GRID(ctx->cfg.max_pairs), NB_BLOCK, 0, st>>>(ctx->pair_keys, ctx->pair_keys_debug, counts + CNT_PAIRS); ++ctx->launches; }
 
 	// coarse islands (nudge.cpp:3500-3703)
 	const u32 P = ctx->cfg.max_pairs, S = ctx->stride;
@@ -482,7 +486,7 @@ int nb_debug_read(nb_context* ctx, const char* name, void* dst, size_t max_bytes
 		{ "aabb_min", ctx->aabb_min, sizeof(float4) * K },
 		{ "aabb_max", ctx->aabb_max, sizeof(float4) * K },
 		{ "world_xf", ctx->world_xf, sizeof(nb_transform) * K },
-		{ "pair_keys", ctx->pair_keys, sizeof(u64) * c[CNT_PAIRS] },
+		{ "pair_keys", ctx->pair_keys_debug, sizeof(u64) * (ctx->pair_keys_debug ? c[CNT_PAIRS] : 0) },
 		{ "live", ctx->live, sizeof(uint2) * c[CNT_LIVE_TOTAL] },
 		{ "sorted", ctx->sorted, sizeof(u32) * c[CNT_CONTACTS] },
 		{ "impulses", ctx->impulses, sizeof(float4) * c[CNT_CONTACTS] },
@@ -512,6 +516,36 @@ int nb_debug_read(nb_context* ctx, const char* name, void* dst, size_t max_bytes
 		}
 	ctx->error = std::string("unknown debug buffer ") + name;
 	return NB_ERR_ARGUMENT;
+}
+
+// Keeps a copy of the sorted broadphase pair list for nb_debug_read("pair_keys") (one extra copy kernel per collide).
+int nb_debug_enable(nb_context* ctx, int on) {
+	if (on && !ctx->pair_keys_debug) ALLOC(ctx->pair_keys_debug, ctx->cfg.max_pairs);
+	ctx->debug = on;
+	return NB_OK;
+}
+
+// Runs the device radix sort / scan on host data (unit tests of the primitives).
+int nb_debug_sort(nb_context* ctx, uint64_t* keys, uint32_t* vals, uint32_t n, int begin_bit, int end_bit) {
+	if (n > ctx->sort_cap) { ctx->error = "too many keys"; return NB_ERR_CAPACITY; }
+	Launch L = mk_launch(ctx, nullptr);
+	CK(cudaMemcpy(ctx->sb.keys[0], keys, (size_t)n * 8, cudaMemcpyHostToDevice));
+	if (vals) CK(cudaMemcpy(ctx->sb.vals[0], vals, (size_t)n * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(ctx->counts + CNT_SCRATCH1, &n, 4, cudaMemcpyHostToDevice));
+	int cur = nb_radix_sort(L, ctx->sb, ctx->counts + CNT_SCRATCH1, begin_bit, end_bit, vals != nullptr, 0);
+	CK(cudaMemcpy(keys, ctx->sb.keys[cur], (size_t)n * 8, cudaMemcpyDeviceToHost));
+	if (vals) CK(cudaMemcpy(vals, ctx->sb.vals[cur], (size_t)n * 4, cudaMemcpyDeviceToHost));
+	return NB_OK;
+}
+int nb_debug_scan(nb_context* ctx, uint32_t* data, uint32_t n, uint32_t* total) {
+	if (n > ctx->stride) { ctx->error = "too many values"; return NB_ERR_CAPACITY; }
+	Launch L = mk_launch(ctx, nullptr);
+	CK(cudaMemcpy(ctx->flags, data, (size_t)n * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(ctx->counts + CNT_SCRATCH1, &n, 4, cudaMemcpyHostToDevice));
+	nb_scan<1>(L, ctx->flags, ctx->offs, ctx->stride, ctx->counts + CNT_SCRATCH1, 0, ctx->block_sums, ctx->counts + CNT_SCRATCH0);
+	CK(cudaMemcpy(data, ctx->offs, (size_t)n * 4, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(total, ctx->counts + CNT_SCRATCH0, 4, cudaMemcpyDeviceToHost));
+	return NB_OK;
 }
 
 int nb_debug_rcp(nb_context* ctx, const float* x, float* y, uint32_t n, int rsq) {

@@ -149,15 +149,20 @@ def demo_scene(n_boxes=1024, n_spheres=1024, iterations=8, seed=1, spread=5.0, h
     return s
 
 
-def box_drop(n_boxes=65536, iterations=8, seed=2, density_L=None, height=None, rotate=True):
-    """BASELINE configs 1 and 3: N boxes dropped at random onto the ground plane.
+def box_drop(n_boxes=65536, iterations=8, seed=2, density_L=None, spacing=(2.8, 2.6, 2.8), rotate=True):
+    """BASELINE configs 1 and 3: N random boxes dropped onto the ground plane.
 
-    The footprint half-width L keeps the probe's areal density (8191 boxes at L=15)."""
+    Boxes start on a jittered lattice (random sizes U[0.5,1.5]^3 and random orientations) above a footprint of
+    half-width L that keeps the survey probe's areal density (8191 boxes at L=15), then fall and pile up."""
     rng = np.random.default_rng(seed)
     L = density_L if density_L is not None else 15.0 * np.sqrt(n_boxes / 8191.0)
-    H = height if height is not None else 40.0
+    side = max(1, int(2 * L / spacing[0]))
+    idx = rng.permutation(n_boxes)  # "random drop": body index carries no information about position
+    layer, rem = idx // (side * side), idx % (side * side)
+    gx, gz = rem // side, rem % side
+    pos = np.stack([(gx + 0.5) * spacing[0] - L, layer * spacing[1] + 2.0, (gz + 0.5) * spacing[2] - L], 1)
+    pos = (pos + rng.uniform(-0.2, 0.2, pos.shape)).astype(np.float32)
     sizes = (rng.random((n_boxes, 3)) + 0.5).astype(np.float32)
-    pos = np.stack([rng.random(n_boxes) * 2 * L - L, rng.random(n_boxes) * H + 1.0, rng.random(n_boxes) * 2 * L - L], 1).astype(np.float32)
     rot = _random_unit_quaternions(rng, n_boxes) if rotate else None
     half = max(400.0, 2.0 * L)
     s = _assemble("box_drop_%d" % n_boxes, sizes, pos, rot, np.zeros(0, np.float32), np.zeros((0, 3), np.float32),

@@ -151,3 +151,13 @@ def compare_oracle_gpu_step(o, g, rep, sweeps_individually=True):
     g.download_bodies()
     rep.eq("transforms", o.transforms, g.transforms); rep.eq("idle", o.idle, g.idle)
     return rep.ok
+
+
+def sync_oracle_from_gpu(o, g):
+    """Copies the GPU simulation's body state and contact cache into an oracle instance (same Scene), so that one
+    step can be compared from identical input state (never compare long trajectories)."""
+    g.download_bodies(); g.download_cache()
+    o.transforms[:] = g.transforms; o.momentum[:] = g.momentum; o.idle[:] = g.idle
+    n = g.cache.count
+    o.cache_tags[:n] = g.cache_tags[:n]; o.cache_features[:n] = g.cache_features[:n]; o.cache_data[:n] = g.cache_data[:n]
+    o.cache.count = n

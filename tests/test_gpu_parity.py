@@ -1,0 +1,176 @@
+"""GPU parity tests proper: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs, bit for
+bit at every stage (pair lists, contacts, tag order, batch indices, constraint rows, impulses after every sweep,
+momentum, cache, transforms), against the committed golden fixtures, and through size-independent properties at the
+full BASELINE size."""
+import os
+import numpy as np
+import pytest
+import nudge_b200
+from nudge_b200 import scenes, abi
+from tests import golden_util as G
+from tests.parity_util import Report, compare_oracle_gpu_step, sync_oracle_from_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(scene):
+    from oracle import pyoracle
+    o = pyoracle.OracleSim(scene)
+    g = nudge_b200.Sim(scene, contact_capacity=o.cap, debug=True)
+    assert g.lut_model_exact(), "host CPU's rcpps/rsqrtps do not follow the LUT model: bit parity is not expected on this box"
+    return o, g
+
+
+def _steps(o, g, n, individually=True):
+    for i in range(n):
+        rep = Report("%s step %d" % (o.scene.name, i))
+        assert compare_oracle_gpu_step(o, g, rep, individually), str(rep)
+        assert g.counts().overflow == 0
+
+
+def test_library_is_the_cuda_extension():
+    g = nudge_b200.Sim(scenes.two_boxes())
+    g.collide(); g.download_contacts()
+    assert g.launch_count() > 10 and g.contacts.count == 4
+
+
+def test_device_lut_equals_host_instruction():
+    from oracle import pyoracle
+    lib = pyoracle.load()
+    g = nudge_b200.Sim(scenes.demo_scene(2000, 0))
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 2**32, 1 << 16, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    for rs in (False, True):
+        y = np.empty_like(x); (lib.nbo_rsqrt if rs else lib.nbo_rcp)(abi.ptr(x), abi.ptr(y), len(x))
+        yd = g.device_rcp(x, rs)
+        same = (y.view(np.uint32) == yd.view(np.uint32)) | (np.isnan(y) & np.isnan(yd))
+        assert same.all()
+
+
+def test_small_mixed_scene_every_stage():
+    o, g = _pair(scenes.demo_scene(100, 100, iterations=4, spread=2.0, height=20.0))
+    _steps(o, g, 25)
+
+
+def test_demo_scene_config0():
+    o, g = _pair(scenes.demo_scene(1024, 1024, iterations=8))
+    _steps(o, g, 10)
+
+
+def test_rotated_box_drop():
+    o, g = _pair(scenes.box_drop(3000, iterations=8))
+    _steps(o, g, 30)
+
+
+def test_fused_sweeps_equal_individual_sweeps():
+    o, g = _pair(scenes.demo_scene(300, 300, iterations=16, spread=3.0, height=20.0))
+    _steps(o, g, 6, individually=False)
+
+
+def test_sleeping_islands_and_culled_cache():
+    o, g = _pair(scenes.demo_scene(120, 120, iterations=4, spread=6.0, height=6.0, seed=11))
+    _steps(o, g, 40)
+    rng = np.random.default_rng(5)
+    sleepy = rng.random(o.scene.n_bodies) < 0.8
+    for s in (o, g):
+        s.idle[sleepy] = 0xff
+        s.momentum["velocity"][sleepy] = 0; s.momentum["angular_velocity"][sleepy] = 0
+    g.upload_bodies()
+    seen = 0
+    for i in range(6):
+        rep = Report("sleep %d" % i)
+        assert compare_oracle_gpu_step(o, g, rep), str(rep)
+        seen = max(seen, g.contacts.sleeping_count)
+    assert seen > 0
+
+
+def test_empty_and_contact_free_scenes():
+    s = scenes.demo_scene(0, 0)               # ground only
+    o, g = _pair(s); _steps(o, g, 2)
+    s = scenes.demo_scene(20, 20, spread=50.0, height=300.0)   # nothing touches
+    o, g = _pair(s); _steps(o, g, 3)
+
+
+def test_golden_two_box_cases_through_cuda():
+    """The reference's own known-answer tests (tests/main.cpp), run on the GPU path: counts 4 / 8 / 3 / 1 / 2 and exact tags."""
+    g0 = G.load_box_cases()
+    sim = nudge_b200.Sim(G.scene_of(g0, 0), contact_capacity=64)
+    errs = []
+    for k in range(len(g0["count"])):
+        s = G.scene_of(g0, k)
+        sim.transforms[:] = s.transforms; sim.box_data[:] = s.box_data; sim.box_transforms[:] = s.box_transforms
+        sim.upload()
+        sim.collide(); sim.download_contacts()
+        e = G.check_case(g0, k, sim.contacts_view())
+        if e:
+            errs.append(e)
+    assert not errs, "\n".join(errs[:10])
+
+
+def test_golden_trajectory_through_cuda():
+    t = np.load(os.path.join(G.HERE, "golden", "step_cases.npz"))
+    s = scenes.demo_scene(48, 48, iterations=8, seed=int(t["seed"]), spread=2.0, height=12.0)
+    g = nudge_b200.Sim(s)
+    for k in range(len(t["contacts"])):
+        g.step()
+        g.download_bodies()
+        c = g.counts()
+        assert c.contacts == t["contacts"][k] and c.cache == t["cache"][k]
+        assert np.array_equal(g.transforms.view(np.uint8), t["transforms"][k].view(np.uint8)), "transforms differ at step %d" % k
+        assert np.array_equal(g.momentum.view(np.uint8), t["momentum"][k].view(np.uint8)), "momentum differs at step %d" % k
+
+
+def test_settled_8k_pile_one_step_from_identical_state():
+    s = scenes.box_drop(8000, iterations=8)
+    o, g = _pair(s)
+    for _ in range(500):
+        g.step()
+    sync_oracle_from_gpu(o, g)
+    _steps(o, g, 2)
+
+
+def test_full_size_64k_properties_and_one_step_parity():
+    """BASELINE config 1 size: 65,536 boxes.  Settles on the GPU, then (a) one full step bit-exact against the widened
+    oracle from identical state and (b) size-independent properties: pair list sorted and unique, every pair's AABBs
+    overlap, contact tag order sorted, cache sorted by tag, batches conflict-free, levels respect per-body order."""
+    s = scenes.box_drop(65536, iterations=8)
+    o, g = _pair(s)
+    for _ in range(700):
+        g.step()
+    assert g.counts().overflow == 0
+    sync_oracle_from_gpu(o, g)
+    _steps(o, g, 1)
+    g.collide(); g.apply_gravity_damping(); g.read_cached_impulses(); g.setup_contact_constraints()
+    g.download_contacts()
+    p = g.pairs_view()
+    key = (p["hi"].astype(np.uint64) << np.uint64(32)) | p["lo"].astype(np.uint64)
+    assert (np.diff(key.astype(np.int64)) > 0).all()
+    lo = g.debug("aabb_min", np.float32).reshape(-1, 4); hi = g.debug("aabb_max", np.float32).reshape(-1, 4)
+    a, b = p["lo"].astype(np.int64), p["hi"].astype(np.int64)
+    assert ((hi[a, :3] > lo[b, :3]) & (hi[b, :3] > lo[a, :3])).all()
+    v = g.constraints_view()
+    n = g.contacts.count
+    srt = g.debug("sorted", np.uint32).astype(np.int64)
+    tags, feats = g.contact_tags[:n][srt], g.contact_features[:n][srt]
+    k1 = (tags >> np.uint64(32)).astype(np.int64); k2 = (tags & np.uint64(0xffffffff)).astype(np.int64)
+    order_ok = (np.diff(k1) > 0) | ((np.diff(k1) == 0) & ((np.diff(k2) > 0) | ((np.diff(k2) == 0) & (np.diff(feats.astype(np.int64)) >= 0))))
+    assert order_ok.all()
+    batch = v["batch_of_contact"].astype(np.int64)
+    bodies = g.contact_bodies[:n]
+    for col in ("a", "b"):
+        body = bodies[col].astype(np.int64)
+        m = body != 0
+        pairs = np.unique(np.stack([batch[m], body[m]], 1), axis=0)
+        assert len(pairs) == m.sum() or col == "b"   # a body appears at most once per batch on each side
+    allb = np.concatenate([np.stack([batch, bodies["a"].astype(np.int64)], 1), np.stack([batch, bodies["b"].astype(np.int64)], 1)])
+    allb = allb[allb[:, 1] != 0]
+    assert len(np.unique(allb, axis=0)) == len(allb), "a batch holds two contacts of one body"
+    # levels: along each body, level strictly increases with batch index
+    level_of_contact = np.zeros(n, np.int64); level_of_contact[srt] = v["level"]
+    for col in ("a", "b"):
+        body = bodies[col].astype(np.int64)
+        m = body != 0
+        o2 = np.lexsort((batch[m], body[m]))
+        bb, ll = body[m][o2], level_of_contact[m][o2]
+        same = bb[1:] == bb[:-1]
+        assert (ll[1:][same] > ll[:-1][same]).all() or col == "b"
