@@ -214,14 +214,15 @@ class Sim(abi.HostState):
                     culled_data=self.debug("culled_data", scenes.IMPULSE))
 
     def constraints_view(self):
-        """Rows and states keyed by contact index (the reference keys them by batch lane; compare per contact)."""
+        """Rows and states per occupied slot (slot = batch*8 + lane, the reference's ContactConstraintV lane), keyed by contact index."""
         stride = self.debug_scalar("row_stride")
-        contact = self.debug("row_contact", np.uint32)
-        n = len(contact)
-        planes = self.debug("row_planes", np.float32).reshape(39, stride)[:, :n]
-        states = self.debug("row_states", np.float32).reshape(3, stride)[:, :n]
+        slot_contact = self.debug("row_contact", np.uint32)
+        used = np.nonzero(slot_contact != 0xffffffff)[0]
+        planes = self.debug("row_planes", np.float32).reshape(39, stride)[:, used]
+        states = self.debug("row_states", np.float32).reshape(3, stride)[:, used]
         sorted_c = self.debug("sorted", np.uint32)
-        batch_of_sorted = self.debug("batch_of", np.uint32)
-        batch = np.zeros(n, np.uint32); batch[sorted_c] = batch_of_sorted
-        return dict(contact=contact, a=self.debug("row_a", np.uint32), b=self.debug("row_b", np.uint32), rows=planes.T.copy(), states=states.T.copy(),
-                    batch_of_contact=batch, level=self.debug("level", np.uint32))
+        n = len(sorted_c)
+        batch = np.zeros(n, np.uint32); batch[sorted_c] = self.debug("batch_of", np.uint32)
+        slot = np.zeros(n, np.uint32); slot[sorted_c] = self.debug("slot_idx", np.uint32)
+        return dict(contact=slot_contact[used], a=self.debug("row_a", np.uint32)[used], b=self.debug("row_b", np.uint32)[used], rows=planes.T.copy(), states=states.T.copy(),
+                    batch_of_contact=batch, slot_of_contact=slot, slots=used.astype(np.uint32))

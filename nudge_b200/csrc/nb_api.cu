@@ -12,7 +12,6 @@
 extern "C" void nb_host_sample_luts(u32* rcp_lut, u32* rsqrt_lut);   // nb_lut_host.cpp
 extern "C" int nb_host_check_lut_model(const u32* rcp_lut, const u32* rsqrt_lut);
 
-#define NB_MAX_LEVEL_COUNT 4096
 
 struct nb_context {
 	nb_config cfg;
@@ -26,7 +25,7 @@ struct nb_context {
 	u32 stride;    // scratch stride
 	u32 cstride;   // row plane stride
 	u32 slots_per_bucket;
-	int coop_blocks_solve, coop_blocks_levels;
+	int coop_blocks_solve;
 
 	// scene
 	nb_transform* xf; nb_body_properties* props; nb_body_momentum* mom; uint8_t* idle;
@@ -52,8 +51,7 @@ struct nb_context {
 	u32* sorted; float4* impulses;
 	// setup / solve
 	float4* inertia;
-	u32* slot_of; u32* slot_done; u32* slot_left; u32* left_count; u32* batch_of; u32* pred; u32* level;
-	u32* level_count; u32* level_start; u32* level_fill; u32* slot_to_sorted;
+	u32* slot_of; u32* slot_done; u32* slot_left; u32* left_count; u32* batch_of; u32* slot_idx; u32* version;
 	Rows rows;
 };
 
@@ -120,7 +118,7 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ctx->B = 0; ctx->nboxes = 0; ctx->nspheres = 0; ctx->nconn = 0;
 	ctx->tagbits = 1; ctx->kbits = bits_for(K ? K : 1); ctx->bodybits = bits_for(B); ctx->batchbits = bits_for((u64)C + 2);
 	ctx->stride = ((std::max(std::max(P, C), std::max(B, K)) + 63) / 64) * 64;
-	ctx->cstride = ((C + 31) / 32) * 32;
+	ctx->cstride = ((C + 8 * 16 * NB_SCHED_MAXV + 31) / 32) * 32;  // slots = batch*8 + lane; leftover batches of the 16 buckets may be partly empty
 	ctx->slots_per_bucket = (C + 15) / 16 + 1;
 
 	ALLOC(ctx->xf, B); ALLOC(ctx->props, B); ALLOC(ctx->mom, B); ALLOC(ctx->idle, B);
@@ -146,11 +144,9 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ALLOC(ctx->sorted, C); ALLOC(ctx->impulses, C);
 	ALLOC(ctx->inertia, 2 * (size_t)B);
 	ALLOC(ctx->slot_of, C); ALLOC(ctx->slot_done, 16 * (size_t)ctx->slots_per_bucket); ALLOC(ctx->slot_left, 16 * (size_t)ctx->slots_per_bucket);
-	ALLOC(ctx->left_count, 16); ALLOC(ctx->batch_of, C); ALLOC(ctx->pred, 2 * (size_t)C); ALLOC(ctx->level, C);
-	ALLOC(ctx->level_count, NB_MAX_LEVEL_COUNT); ALLOC(ctx->level_start, NB_MAX_LEVEL_COUNT + 1); ALLOC(ctx->level_fill, NB_MAX_LEVEL_COUNT);
-	ALLOC(ctx->slot_to_sorted, C);
+	ALLOC(ctx->left_count, 16); ALLOC(ctx->batch_of, C); ALLOC(ctx->slot_idx, C); ALLOC(ctx->version, B);
 	ALLOC(ctx->rows.plane, (size_t)ROW_PLANES * ctx->cstride); ALLOC(ctx->rows.state, 3 * (size_t)ctx->cstride);
-	ALLOC(ctx->rows.a, C); ALLOC(ctx->rows.b, C); ALLOC(ctx->rows.contact, C);
+	ALLOC(ctx->rows.a, ctx->cstride); ALLOC(ctx->rows.b, ctx->cstride); ALLOC(ctx->rows.contact, ctx->cstride); ALLOC(ctx->rows.wait, 2 * (size_t)ctx->cstride);
 	ctx->rows.stride = ctx->cstride;
 	ctx->pair_keys = ctx->sb.keys[0];
 	ctx->pair_keys_debug = nullptr; ctx->debug = 0;
@@ -164,14 +160,10 @@ int nb_create(const nb_config* config, nb_context** out) {
 	CK(cudaMemcpyToSymbol(g_rcp_lut, rcp_lut, sizeof(rcp_lut)));
 	CK(cudaMemcpyToSymbol(g_rsqrt_lut, rsqrt_lut, sizeof(rsqrt_lut)));
 
-	CK(cudaFuncSetAttribute(k_schedule, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SchedSmem)));
 	int per_sm = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, NB_BLOCK, 0));
 	if (per_sm < 1) { ctx->error = "k_solve does not fit on an SM"; return NB_ERR_CUDA; }
-	ctx->coop_blocks_solve = ctx->sms * std::min(per_sm, 2);
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_levels, NB_BLOCK, 0));
-	if (per_sm < 1) { ctx->error = "k_levels does not fit on an SM"; return NB_ERR_CUDA; }
-	ctx->coop_blocks_levels = ctx->sms * std::min(per_sm, 4);
+	ctx->coop_blocks_solve = ctx->sms * per_sm;  // all co-resident: the dataflow solver relies on it
 	CK(cudaDeviceSynchronize());
 	return NB_OK;
 }
@@ -402,9 +394,10 @@ static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) 
 	Rows R = ctx->rows;
 	const float4* impulses = ctx->impulses;
 	nb_body_momentum* mom = ctx->mom;
-	const u32* level_start = ctx->level_start;
+	u32* version = ctx->version;
 	u32* counts = ctx->counts;
-	void* args[] = { &R, &impulses, &mom, &level_start, &mode, &sweeps, &counts };
+	CK(cudaMemsetAsync(version, 0, sizeof(u32) * (ctx->B ? ctx->B : 1), st));
+	void* args[] = { &R, &impulses, &mom, &version, &mode, &sweeps, &counts };
 	CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
 	++ctx->launches;
 	return NB_OK;
@@ -416,26 +409,18 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 	u32* counts = ctx->counts;
 	const u32 C = ctx->cfg.max_contacts, S = ctx->stride, B = ctx->B;
 	k_inertia<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->xf, ctx->props, ctx->inertia, ctx->mom);
-	k_schedule<<<16, 32, sizeof(SchedSmem), st>>>(ctx->sorted, ctx->fin.bodies, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,
+	k_schedule<<<16, 32, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,
 		ctx->flags, ctx->left_count, counts);
 	ctx->launches += 2;
 	nb_scan<1>(L, ctx->flags, ctx->offs, S, counts + CNT_CONTACTS, 0, ctx->block_sums, counts + CNT_FULL_BATCHES);
+	CK(cudaMemsetAsync(ctx->rows.contact, 0xff, sizeof(u32) * ctx->cstride, st));
 	k_batch_index<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,
-		ctx->offs, ctx->left_count, ctx->batch_of, ctx->sb.keys[0], ctx->sb.vals[0], ctx->batchbits, counts);
+		ctx->offs, ctx->left_count, ctx->batch_of, ctx->slot_idx, ctx->rows.contact, ctx->cstride, ctx->sb.keys[0], ctx->sb.vals[0], ctx->batchbits, counts);
 	++ctx->launches;
 	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_ENTRIES, 0, (int)(ctx->bodybits + ctx->batchbits), true, 0);
-	k_preds<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, ctx->pred, counts);
-	++ctx->launches;
-	{
-		const u32* pred = ctx->pred; u32* level = ctx->level; u32* level_count = ctx->level_count; u32 max_levels = NB_MAX_LEVEL_COUNT;
-		void* args[] = { &pred, &level, &level_count, &max_levels, &counts };
-		CK(cudaLaunchCooperativeKernel((void*)k_levels, dim3(ctx->coop_blocks_levels), dim3(NB_BLOCK), args, 0, st));
-		++ctx->launches;
-	}
-	k_level_starts<<<1, 1024, 0, st>>>(ctx->level_count, ctx->level_start, ctx->level_fill, NB_MAX_LEVEL_COUNT, counts);
-	k_level_scatter<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->level, ctx->level_start, ctx->level_fill, ctx->slot_to_sorted, NB_MAX_LEVEL_COUNT, counts);
-	k_build_rows<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->slot_to_sorted, ctx->sorted, ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts);
-	ctx->launches += 3;
+	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, ctx->slot_idx, ctx->rows.wait, ctx->cstride, counts);
+	k_build_rows<<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts);
+	ctx->launches += 2;
 	int r = launch_solve(ctx, 0, 1, st); if (r) return r;  // warm start (nudge.cpp:4563-4632)
 	CK(cudaGetLastError());
 	return NB_OK;
@@ -449,7 +434,7 @@ int nb_apply_impulses(nb_context* ctx, uint32_t sweeps, void* stream) {
 }
 
 int nb_update_cached_impulses(nb_context* ctx, void* stream) {
-	k_update_impulses<<<GRID(ctx->cfg.max_contacts), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->rows, ctx->impulses, ctx->counts);
+	k_update_impulses<<<GRID(ctx->cstride), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->rows, ctx->impulses, ctx->counts);
 	++ctx->launches;
 	CK(cudaGetLastError());
 	return NB_OK;
@@ -494,11 +479,11 @@ int nb_debug_read(nb_context* ctx, const char* name, void* dst, size_t max_bytes
 		{ "culled_features", ctx->culled_features, sizeof(u32) * c[CNT_CULLED] },
 		{ "culled_data", ctx->culled_data, sizeof(float4) * c[CNT_CULLED] },
 		{ "batch_of", ctx->batch_of, sizeof(u32) * c[CNT_CONTACTS] },
-		{ "level", ctx->level, sizeof(u32) * c[CNT_CONTACTS] },
-		{ "level_start", ctx->level_start, sizeof(u32) * (c[CNT_LEVELS] + 1) },
-		{ "row_contact", ctx->rows.contact, sizeof(u32) * c[CNT_CONTACTS] },
-		{ "row_a", ctx->rows.a, sizeof(u32) * c[CNT_CONTACTS] },
-		{ "row_b", ctx->rows.b, sizeof(u32) * c[CNT_CONTACTS] },
+		{ "slot_idx", ctx->slot_idx, sizeof(u32) * c[CNT_CONTACTS] },
+		{ "row_contact", ctx->rows.contact, sizeof(u32) * 8 * c[CNT_BATCHES] },
+		{ "row_a", ctx->rows.a, sizeof(u32) * 8 * c[CNT_BATCHES] },
+		{ "row_b", ctx->rows.b, sizeof(u32) * 8 * c[CNT_BATCHES] },
+		{ "row_wait", ctx->rows.wait, sizeof(u32) * 2 * (size_t)ctx->cstride },
 		{ "row_planes", ctx->rows.plane, sizeof(float) * (size_t)ROW_PLANES * ctx->cstride },
 		{ "row_states", ctx->rows.state, sizeof(float) * 3 * (size_t)ctx->cstride },
 		{ "inertia", ctx->inertia, sizeof(float4) * 2 * ctx->B },

@@ -176,10 +176,16 @@ __global__ void k_clamp_count(u32* counts, int which, u32 cap) {
 }
 
 // ---------------- islands: lock-free union-find, smaller index becomes the root (nudge.cpp:3500-3703, 3788-3971) ----------------
-NB_DEV u32 uf_find(u32* parent, u32 x) {
-	u32 p = ((volatile u32*)parent)[x];
-	while (p != x) { x = p; p = ((volatile u32*)parent)[x]; }
-	return x;
+NB_DEV u32 uf_find(u32* parent, u32 x) {  // with path halving: every write points a node at one of its ancestors, so races are benign
+	volatile u32* vp = parent;
+	while (true) {
+		u32 p = vp[x];
+		if (p == x) return x;
+		u32 gp = vp[p];
+		if (gp == p) return p;
+		vp[x] = gp;
+		x = gp;
+	}
 }
 NB_DEV void uf_unite(u32* parent, u32 a, u32 b) {
 	if (!a || !b) return;  // body 0 is the static world and is ignored (nudge.cpp:3517-3519, 3583-3585)

@@ -6,11 +6,13 @@
 // Exact-order Gauss-Seidel on a GPU: the reference walks 8-lane batches in the order its
 // sequential 16-bucket first-fit scheduler emits them (nudge.cpp:4206-4340), each batch reading the body
 // velocities the previous one wrote.  We (1) replay that scheduler bit for bit with one warp per bucket to
-// get every contact's batch index, (2) chain the contacts of each body by batch index, (3) assign every
-// contact its dependency level (longest chain below it) and (4) run the sweep level by level inside one
-// co-resident kernel with a grid barrier between levels.  Contacts of one level touch disjoint bodies, so
-// the result is bit-identical to the sequential walk while ~60 levels replace ~30k sequential batches.
-// Rows are stored SoA (one float per contact per plane) so that a warp reads 128 contiguous bytes per plane.
+// get every contact's batch index and lane, (2) chain the contacts of each body by batch index, and (3) run all
+// sweeps as ONE co-resident dataflow kernel: every body carries a version counter, a contact waits until both
+// of its bodies carry the token of its predecessor in the reference order, applies its impulse, and publishes
+// its own token.  No grid barrier, sweeps pipeline into each other, and the result is bit-identical to the
+// sequential walk because every body sees exactly the reference's sequence of updates.
+// Rows are stored SoA (one float per contact per plane) so that a warp reads 128 contiguous bytes per plane;
+// the slot of a contact is batch*8 + lane, i.e. the reference's own ContactConstraintV layout flattened.
 #pragma once
 #include "nb_collide.cuh"
 
@@ -114,71 +116,118 @@ __global__ void __launch_bounds__(NB_BLOCK) k_inertia(u32 B, const nb_transform*
 // holding neither of its bodies, a slot that receives its 8th contact is emitted and replaced by the last slot of
 // the list.  Buckets only interact through the global emission order, which equals the order of the contact
 // index at which each slot filled up, so 16 warps can replay them independently.
-#define NB_SCHED_MAXV 1024  // vacant slots kept in shared memory per bucket
+#define NB_SCHED_SHARED 480  // list positions 32.. live in shared memory, positions 0..31 in registers (one per lane)
+#define NB_SCHED_MAXV (32 + NB_SCHED_SHARED)
 struct SchedSmem {
-	u32 a[8][NB_SCHED_MAXV];  // body ids, lane-major so that 32 threads read 32 consecutive slots
-	u32 b[8][NB_SCHED_MAXV];
-	u32 uid[NB_SCHED_MAXV];
-	uint8_t filled[NB_SCHED_MAXV];
+	u32 a[8][NB_SCHED_SHARED];  // body ids, lane-major so that 32 threads read 32 consecutive slots
+	u32 b[8][NB_SCHED_SHARED];
+	u32 uid[NB_SCHED_SHARED];
+	u32 filled[NB_SCHED_SHARED];
 };
 
+// slot_of[i] = uid << 3 | lane, where lane is the SIMD lane the contact lands in (= number of contacts already in its slot)
 __global__ void __launch_bounds__(32) k_schedule(const u32* sorted, const uint2* bodies, u32* slot_of, u32* slot_done, u32* slot_left, u32 slots_per_bucket,
 												 u32* complete_flag, u32* left_count /*[16]*/, u32* counts) {
-	extern __shared__ unsigned char smem_raw[];
-	SchedSmem& S = *reinterpret_cast<SchedSmem*>(smem_raw);
+	__shared__ SchedSmem S;
 	const u32 bucket = blockIdx.x, lane = threadIdx.x;
 	const u32 n = counts[CNT_CONTACTS];
 	u32 vcount = 0, next_uid = 0;
+	u32 ra[8], rb[8], rf = 0, ruid = 0;  // the slot at list position `lane`
+	#pragma unroll
+	for (int l = 0; l < 8; ++l) { ra[l] = 0; rb[l] = 0; }
 	u32* done = slot_done + (size_t)bucket * slots_per_bucket;
 	u32* left = slot_left + (size_t)bucket * slots_per_bucket;
+	// software pipeline: the (ca, cb) of the next 32 contacts of this bucket are fetched while the current 32 are placed
+	u32 nx_ca = 0, nx_cb = 0;
+	{
+		u32 i0 = bucket + 16 * lane;
+		if (i0 < n) { uint2 ab = bodies[sorted[i0]]; nx_ca = ab.x ? ab.x : ab.y; nx_cb = ab.y ? ab.y : ab.x; complete_flag[i0] = 0; }  // body 0 is ignored (nudge.cpp:4238-4240)
+	}
 	for (u32 base = bucket; base < n; base += 16 * 32) {
-		u32 my_i = base + 16 * lane;
-		u32 my_ca = 0, my_cb = 0;
-		if (my_i < n) {
-			uint2 ab = bodies[sorted[my_i]];
-			my_ca = ab.x ? ab.x : ab.y;  // ignore dependencies on body 0 (nudge.cpp:4238-4240)
-			my_cb = ab.y ? ab.y : ab.x;
-			complete_flag[my_i] = 0;
+		u32 my_ca = nx_ca, my_cb = nx_cb;
+		{
+			u32 i1 = base + 16 * 32 + 16 * lane;
+			if (i1 < n) { uint2 ab = bodies[sorted[i1]]; nx_ca = ab.x ? ab.x : ab.y; nx_cb = ab.y ? ab.y : ab.x; complete_flag[i1] = 0; }
 		}
 		u32 steps = min(32u, (n - base + 15) / 16);
 		for (u32 s = 0; s < steps; ++s) {
 			u32 i = base + 16 * s;
 			u32 ca = __shfl_sync(0xffffffffu, my_ca, s), cb = __shfl_sync(0xffffffffu, my_cb, s);
-			// first slot with no conflict; index vcount is the always-free sentinel
+			// first list position with no conflict; position vcount is the always-free sentinel (nudge.cpp:4250-4257)
 			u32 j = vcount;
-			for (u32 jb = 0; jb < vcount; jb += 32) {
-				u32 jj = jb + lane;
-				bool free_slot = false;
-				if (jj < vcount) {
-					u32 f = S.filled[jj];
-					bool conflict = false;
-					#pragma unroll
-					for (u32 l = 0; l < 8; ++l)
-						if (l < f) { u32 sa = S.a[l][jj], sb = S.b[l][jj]; conflict |= (sa == ca) | (sb == ca) | (sa == cb) | (sb == cb); }
-					free_slot = !conflict;
+			{
+				bool conflict = false;
+				#pragma unroll
+				for (u32 l = 0; l < 8; ++l)
+					if (l < rf) conflict |= (ra[l] == ca) | (rb[l] == ca) | (ra[l] == cb) | (rb[l] == cb);
+				u32 ballot = __ballot_sync(0xffffffffu, lane < vcount && !conflict);
+				if (ballot) j = __ffs(ballot) - 1;
+				else if (vcount > 32) {
+					for (u32 jb = 0; jb < vcount - 32; jb += 32) {
+						u32 jj = jb + lane;
+						bool free_slot = false;
+						if (jj < vcount - 32) {
+							u32 f = S.filled[jj];
+							bool c2 = false;
+							#pragma unroll
+							for (u32 l = 0; l < 8; ++l)
+								if (l < f) { u32 sa = S.a[l][jj], sb = S.b[l][jj]; c2 |= (sa == ca) | (sb == ca) | (sa == cb) | (sb == cb); }
+							free_slot = !c2;
+						}
+						u32 bl = __ballot_sync(0xffffffffu, free_slot);
+						if (bl) { j = 32 + jb + __ffs(bl) - 1; break; }
+					}
 				}
-				u32 ballot = __ballot_sync(0xffffffffu, free_slot);
-				if (ballot) { j = jb + __ffs(ballot) - 1; break; }
 			}
-			if (j == vcount) {  // open a new slot
+			if (j == vcount) {  // open a new slot at the end of the list
 				if (vcount >= NB_SCHED_MAXV) { if (lane == 0) atomicOr(&counts[CNT_OVERFLOW], OVF_SCHED); return; }
-				if (lane == 0) { S.a[0][j] = ca; S.b[0][j] = cb; S.filled[j] = 1; S.uid[j] = next_uid; slot_of[i] = next_uid; done[next_uid] = NB_NONE; }
+				if (j < 32) { if (lane == j) { ra[0] = ca; rb[0] = cb; rf = 1; ruid = next_uid; } }
+				else if (lane == 0) { S.a[0][j - 32] = ca; S.b[0][j - 32] = cb; S.filled[j - 32] = 1; S.uid[j - 32] = next_uid; }
+				if (lane == 0) { slot_of[i] = next_uid << 3; done[next_uid] = NB_NONE; }
 				++next_uid; ++vcount;
 				__syncwarp();
 			}
 			else {
-				u32 f = S.filled[j];
-				u32 uid = S.uid[j];
+				u32 f, uid;
+				if (j < 32) { f = __shfl_sync(0xffffffffu, rf, j); uid = __shfl_sync(0xffffffffu, ruid, j); }
+				else { f = S.filled[j - 32]; uid = S.uid[j - 32]; }
 				__syncwarp();
-				if (lane == 0) { S.a[f][j] = ca; S.b[f][j] = cb; S.filled[j] = (uint8_t)(f + 1); slot_of[i] = uid; }
+				if (j < 32) {
+					if (lane == j) {
+						#pragma unroll
+						for (u32 l = 0; l < 8; ++l) if (l == f) { ra[l] = ca; rb[l] = cb; }
+						rf = f + 1;
+					}
+				}
+				else if (lane == 0) { S.a[f][j - 32] = ca; S.b[f][j - 32] = cb; S.filled[j - 32] = f + 1; }
+				if (lane == 0) slot_of[i] = (uid << 3) | f;
 				__syncwarp();
 				if (f == 7) {  // slot complete: emitted now, the last slot of the list takes its place (nudge.cpp:4294-4306)
 					if (lane == 0) { done[uid] = i; complete_flag[i] = 1; }
 					u32 last = vcount - 1;
 					if (j != last) {
-						if (lane < 8) { S.a[lane][j] = S.a[lane][last]; S.b[lane][j] = S.b[lane][last]; }
-						if (lane == 8) { S.filled[j] = S.filled[last]; S.uid[j] = S.uid[last]; }
+						if (last < 32) {  // register -> register
+							u32 tf = __shfl_sync(0xffffffffu, rf, last), tu = __shfl_sync(0xffffffffu, ruid, last);
+							#pragma unroll
+							for (u32 l = 0; l < 8; ++l) {
+								u32 ta = __shfl_sync(0xffffffffu, ra[l], last), tb = __shfl_sync(0xffffffffu, rb[l], last);
+								if (lane == j) { ra[l] = ta; rb[l] = tb; }
+							}
+							if (lane == j) { rf = tf; ruid = tu; }
+						}
+						else if (j < 32) {  // shared -> register
+							if (lane == j) {
+								#pragma unroll
+								for (u32 l = 0; l < 8; ++l) { ra[l] = S.a[l][last - 32]; rb[l] = S.b[l][last - 32]; }
+								rf = S.filled[last - 32]; ruid = S.uid[last - 32];
+							}
+						}
+						else {  // shared -> shared
+							if (lane < 8) { S.a[lane][j - 32] = S.a[lane][last - 32]; S.b[lane][j - 32] = S.b[lane][last - 32]; }
+							if (lane == 8) { S.filled[j - 32] = S.filled[last - 32]; S.uid[j - 32] = S.uid[last - 32]; }
+						}
 					}
+					if (last < 32 && lane == last) rf = 0;
 					--vcount;
 					__syncwarp();
 				}
@@ -186,24 +235,33 @@ __global__ void __launch_bounds__(32) k_schedule(const u32* sorted, const uint2*
 		}
 	}
 	// leftovers are flushed bucket-major in list order (nudge.cpp:4316-4338)
-	for (u32 jj = lane; jj < vcount; jj += 32) left[S.uid[jj]] = jj;
+	if (lane < min(vcount, 32u)) left[ruid] = lane;
+	if (vcount > 32) for (u32 jj = lane; jj < vcount - 32; jj += 32) left[S.uid[jj]] = 32 + jj;
 	if (lane == 0) left_count[bucket] = vcount;
 }
 
-// batch index of every contact + the (body, batch) chain entries
+// batch index and slot (batch*8 + lane) of every contact + the (body, batch) chain entries
 __global__ void __launch_bounds__(NB_BLOCK) k_batch_index(const u32* sorted, const uint2* bodies, const u32* slot_of, const u32* slot_done, const u32* slot_left,
-		u32 slots_per_bucket, const u32* complete_off, const u32* left_count, u32* batch_of, u64* chain_keys, u32* chain_vals, u32 batchbits, u32* counts) {
+		u32 slots_per_bucket, const u32* complete_off, const u32* left_count, u32* batch_of, u32* slot_idx, u32* slot_contact, u32 max_slots,
+		u64* chain_keys, u32* chain_vals, u32 batchbits, u32* counts) {
 	u32 n = counts[CNT_CONTACTS];
 	u32 nfull = counts[CNT_FULL_BATCHES];
 	u32 left_base[17]; left_base[0] = 0;
 	#pragma unroll
 	for (int k = 0; k < 16; ++k) left_base[k + 1] = left_base[k] + left_count[k];
-	if (blockIdx.x == 0 && threadIdx.x == 0) { counts[CNT_BATCHES] = nfull + left_base[16]; counts[CNT_ENTRIES] = 2 * n; }
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		u32 nb = nfull + left_base[16];
+		if (8 * nb > max_slots) { atomicOr(&counts[CNT_OVERFLOW], OVF_SCHED); nb = max_slots / 8; }
+		counts[CNT_BATCHES] = nb; counts[CNT_ENTRIES] = 2 * n;
+	}
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		u32 bucket = i & 15, uid = slot_of[i];
+		u32 bucket = i & 15, packed = slot_of[i], uid = packed >> 3, lane = packed & 7;
 		u32 t = slot_done[(size_t)bucket * slots_per_bucket + uid];
 		u32 batch = (t != NB_NONE) ? complete_off[t] : nfull + left_base[bucket] + slot_left[(size_t)bucket * slots_per_bucket + uid];
 		batch_of[i] = batch;
+		u32 slot = batch * 8 + lane;
+		slot_idx[i] = slot;
+		if (slot < max_slots) slot_contact[slot] = sorted[i];
 		uint2 ab = bodies[sorted[i]];
 		chain_keys[2*i] = ab.x ? (((u64)ab.x << batchbits) | batch) : ~(u64)0;
 		chain_keys[2*i + 1] = ab.y ? (((u64)ab.y << batchbits) | batch) : ~(u64)0;
@@ -211,98 +269,42 @@ __global__ void __launch_bounds__(NB_BLOCK) k_batch_index(const u32* sorted, con
 	}
 }
 
-// predecessor of each contact on body a and body b = previous entry of the same body in (body, batch) order
-__global__ void __launch_bounds__(NB_BLOCK) k_preds(const u64* chain_keys, const u32* chain_vals, u32 batchbits, u32* pred /*[2n]*/, const u32* counts) {
+// For each contact side: the slot whose token it must see on that body before it may run.  In (body, batch) order the
+// predecessor is the previous entry of the same body; the first entry of a body waits for the body's LAST entry of the
+// previous sweep (flag bit 31).  Body 0 (static world) is never waited for.
+#define NB_WAIT_PREV 0x80000000u
+__global__ void __launch_bounds__(NB_BLOCK) k_waits(const u64* chain_keys, const u32* chain_vals, u32 batchbits, const u32* slot_idx, u32* wait /*[2][stride]*/, u32 stride, const u32* counts) {
 	u32 n2 = counts[CNT_ENTRIES];
 	for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += gridDim.x * blockDim.x) {
 		u64 k = chain_keys[e];
 		u32 v = chain_vals[e];
-		u32 p = NB_NONE;
-		if (k != ~(u64)0 && e > 0) {
-			u64 kp = chain_keys[e - 1];
-			if ((kp >> batchbits) == (k >> batchbits)) p = chain_vals[e - 1] >> 1;
+		u32 slot = slot_idx[v >> 1], side = v & 1;
+		u32 w = NB_NONE;
+		if (k != ~(u64)0) {
+			u64 body = k >> batchbits;
+			if (e > 0 && (chain_keys[e - 1] >> batchbits) == body) w = slot_idx[chain_vals[e - 1] >> 1];
+			else {  // first of its body: find the end of the run
+				u32 lo = e, hi = n2;  // first index with a larger body
+				while (lo < hi) { u32 mid = (lo + hi) >> 1; u64 km = chain_keys[mid]; if (km != ~(u64)0 && (km >> batchbits) <= body) lo = mid + 1; else hi = mid; }
+				w = slot_idx[chain_vals[lo - 1] >> 1] | NB_WAIT_PREV;
+			}
 		}
-		pred[v] = p;
-	}
-}
-
-// dependency levels by relaxation, all inside one co-resident kernel (one grid barrier per round)
-__global__ void __launch_bounds__(NB_BLOCK) k_levels(const u32* pred, u32* level, u32* level_count, u32 max_levels, u32* counts) {
-	u32 n = counts[CNT_CONTACTS];
-	u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-	for (u32 i = tid; i < n; i += nth) level[i] = 0;
-	for (u32 l = tid; l < max_levels; l += nth) level_count[l] = 0;
-	if (tid == 0) { counts[CNT_LVCH0] = 0; counts[CNT_LVCH0 + 1] = 0; counts[CNT_LVCH0 + 2] = 0; counts[CNT_SCRATCH0] = 0; }
-	grid_barrier(&counts[CNT_BAR0], gridDim.x);
-	// Round r raises flag r%3, everybody reads it after the barrier of round r, and it is cleared during round r+2
-	// (after the barrier of round r+1, which every reader of round r has passed) for its next use in round r+3.
-	for (u32 iter = 0; iter <= max_levels; ++iter) {
-		if (tid == 0) counts[CNT_LVCH0 + (iter + 1) % 3] = 0;
-		bool changed = false;
-		for (u32 i = tid; i < n; i += nth) {
-			u32 pa = pred[2*i], pb = pred[2*i + 1];
-			u32 l = 0;
-			if (pa != NB_NONE) l = max(l, __ldcg(&level[pa]) + 1);
-			if (pb != NB_NONE) l = max(l, __ldcg(&level[pb]) + 1);
-			if (l != __ldcg(&level[i])) { __stcg(&level[i], l); changed = true; }
-		}
-		if (changed) atomicOr(&counts[CNT_LVCH0 + iter % 3], 1u);
-		grid_barrier(&counts[CNT_BAR0], gridDim.x);
-		if (!ld_acquire_u32(&counts[CNT_LVCH0 + iter % 3])) break;
-	}
-	// histogram of levels
-	for (u32 i = tid; i < n; i += nth) {
-		u32 l = __ldcg(&level[i]);
-		if (l >= max_levels) { atomicOr(&counts[CNT_OVERFLOW], OVF_LEVELS); l = max_levels - 1; }
-		atomicAdd(&level_count[l], 1u);
-		atomicMax(&counts[CNT_SCRATCH0], l + 1);
-	}
-}
-
-__global__ void __launch_bounds__(1024) k_level_starts(const u32* level_count, u32* level_start, u32* level_fill, u32 max_levels, u32* counts) {
-	// one block: exclusive scan of level_count (max_levels <= 4096)
-	__shared__ u32 sm[33];
-	__shared__ u32 carry;
-	if (threadIdx.x == 0) { carry = 0; counts[CNT_LEVELS] = counts[CNT_SCRATCH0]; }
-	__syncthreads();
-	for (u32 base = 0; base < max_levels; base += 1024) {
-		u32 i = base + threadIdx.x;
-		u32 v = i < max_levels ? level_count[i] : 0;
-		u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-		u32 incl = warp_incl_scan(v);
-		if (lane == 31) sm[wid] = incl;
-		__syncthreads();
-		if (wid == 0) { u32 w = sm[lane]; u32 wi = warp_incl_scan(w); sm[lane] = wi - w; if (lane == 31) sm[32] = wi; }
-		__syncthreads();
-		u32 ex = incl - v + sm[wid] + carry;
-		if (i < max_levels) { level_start[i] = ex; level_fill[i] = 0; }
-		__syncthreads();
-		if (threadIdx.x == 0) carry += sm[32];
-		__syncthreads();
-	}
-	if (threadIdx.x == 0) level_start[max_levels] = carry;
-}
-
-__global__ void __launch_bounds__(NB_BLOCK) k_level_scatter(const u32* level, const u32* level_start, u32* level_fill, u32* slot_to_sorted, u32 max_levels, const u32* counts) {
-	u32 n = counts[CNT_CONTACTS];
-	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		u32 l = min(level[i], max_levels - 1);
-		u32 pos = level_start[l] + atomicAdd(&level_fill[l], 1u);  // order inside a level is free: its contacts touch disjoint bodies
-		slot_to_sorted[pos] = i;
+		if (slot < stride) wait[side * stride + slot] = w;
 	}
 }
 
 // ---------------- constraint rows (nudge.cpp:4350-4561), one thread per contact, SoA planes ----------------
-struct Rows { float* plane; u32 stride; u32* a; u32* b; u32* contact; float* state; };  // plane[k*stride + j], state[k*stride + j]
+struct Rows { float* plane; u32 stride; u32* a; u32* b; u32* contact; float* state; u32* wait; };  // plane[k*stride + slot], wait[side*stride + slot]
 
-__global__ void __launch_bounds__(NB_BLOCK) k_build_rows(const u32* slot_to_sorted, const u32* sorted, const float4* contacts, const uint2* bodies,
+__global__ void __launch_bounds__(NB_BLOCK) k_build_rows(const float4* contacts, const uint2* bodies,
 		const nb_transform* xf, const float4* inertia, const nb_body_momentum* momentum, Rows R, const u32* counts) {
 	__shared__ u32 s_rsqrt[2048];
 	for (u32 i = threadIdx.x; i < 2048; i += blockDim.x) s_rsqrt[i] = g_rsqrt_lut[i];
 	__syncthreads();
-	u32 n = counts[CNT_CONTACTS];
+	u32 n = 8 * counts[CNT_BATCHES];
 	for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-		u32 c = sorted[slot_to_sorted[j]];
+		u32 c = R.contact[j];
+		if (c == NB_NONE) continue;  // unset lane of a leftover batch (the reference repeats lane 0 there, nudge.cpp:4321-4336)
 		float4 cp = contacts[2*c], cn = contacts[2*c + 1];
 		uint2 ab = bodies[c];
 		u32 a = ab.x, b = ab.y;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(NB_BLOCK) k_build_rows(const u32* slot_to_sort
 		P[NA_X*S] = nb_neg(na_x); P[NA_Y*S] = nb_neg(na_y); P[NA_Z*S] = nb_neg(na_z);
 		P[UB_X*S] = ub_xt; P[UB_Y*S] = ub_yt; P[UB_Z*S] = ub_zt; P[VB_X*S] = vb_xt; P[VB_Y*S] = vb_yt; P[VB_Z*S] = vb_zt;
 		P[NB_X*S] = nb_x; P[NB_Y*S] = nb_y; P[NB_Z*S] = nb_z;
-		R.a[j] = a; R.b[j] = b; R.contact[j] = c;
+		R.a[j] = a; R.b[j] = b;
 	}
 }
 
@@ -520,30 +522,57 @@ NB_DEV void solve_contact(const Rows& R, u32 j, nb_body_momentum* momentum, cons
 	if (b) st_momentum(momentum, b, make_float4(b_velocity_x, b_velocity_y, b_velocity_z, b_mass_inverse), make_float4(b_angular_velocity_x, b_angular_velocity_y, b_angular_velocity_z, 0.0f));
 }
 
-// mode 0: warm start (one pass); mode 1: `sweeps` PGS sweeps.  Co-resident grid, barrier between levels.
-__global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impulses, nb_body_momentum* momentum, const u32* level_start, int mode, u32 sweeps, u32* counts) {
+// mode 0: warm start (one pass); mode 1: `sweeps` PGS sweeps.  Co-resident grid, no barrier: work item q = sweep*NS + slot
+// is handled by thread q % threads in increasing q, which is a topological order of the dependency graph, so the lowest
+// unfinished item is always runnable.  Inside a warp the lanes poll instead of blocking, so a lane may depend on another
+// lane of its own warp.  version[] must be zero at launch.
+__global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impulses, nb_body_momentum* momentum, u32* version, int mode, u32 sweeps, u32* counts) {
 	__shared__ u32 s_rcp[2048];
 	__shared__ u32 s_rsqrt[2048];
 	for (u32 i = threadIdx.x; i < 2048; i += blockDim.x) { s_rcp[i] = g_rcp_lut[i]; s_rsqrt[i] = g_rsqrt_lut[i]; }
 	__syncthreads();
-	u32 levels = counts[CNT_LEVELS];
-	u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-	u32 passes = mode ? sweeps : 1;
-	for (u32 s = 0; s < passes; ++s)
-		for (u32 l = 0; l < levels; ++l) {
-			u32 begin = level_start[l], end = level_start[l + 1];
-			for (u32 j = begin + tid; j < end; j += nth) {
-				if (mode) solve_contact(R, j, momentum, s_rcp, s_rsqrt);
-				else warm_start_contact(R, j, impulses, momentum, s_rsqrt);
+	const u32 NS = 8 * counts[CNT_BATCHES];
+	const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+	const u32 passes = mode ? sweeps : 1;
+	const u64 total = (u64)passes * NS;
+	const u32 S = R.stride;
+	for (u64 q0 = 0; q0 < total; q0 += nth) {  // uniform trip count for the whole grid
+		u64 q = q0 + tid;
+		bool pending = false;
+		u32 slot = 0, a = 0, b = 0, exp_a = 0, exp_b = 0, token = 0;
+		if (q < total) {
+			u32 w = (u32)(q / NS); slot = (u32)(q - (u64)w * NS);
+			if (R.contact[slot] != NB_NONE) {
+				pending = true;
+				a = R.a[slot]; b = R.b[slot];
+				u32 wa = R.wait[slot], wb = R.wait[S + slot];
+				token = w * NS + slot + 1;
+				// expected token on each body: predecessor in this sweep, or the body's last contact of the previous sweep
+				exp_a = (wa & NB_WAIT_PREV) ? (w ? (w - 1) * NS + (wa & ~NB_WAIT_PREV) + 1 : 0) : w * NS + wa + 1;
+				exp_b = (wb & NB_WAIT_PREV) ? (w ? (w - 1) * NS + (wb & ~NB_WAIT_PREV) + 1 : 0) : w * NS + wb + 1;
 			}
-			grid_barrier(&counts[CNT_BAR0], gridDim.x);
 		}
+		while (__any_sync(0xffffffffu, pending)) {
+			if (pending) {
+				bool ready = (!a || ld_acquire_u32(version + a) == exp_a) && (!b || ld_acquire_u32(version + b) == exp_b);
+				if (ready) {
+					if (mode) solve_contact(R, slot, momentum, s_rcp, s_rsqrt);
+					else warm_start_contact(R, slot, impulses, momentum, s_rsqrt);
+					__threadfence();
+					if (a) *((volatile u32*)(version + a)) = token;
+					if (b) *((volatile u32*)(version + b)) = token;
+					pending = false;
+				}
+			}
+		}
+	}
 }
 
 // ---------------- update_cached_impulses (nudge.cpp:4857-4884) ----------------
 __global__ void __launch_bounds__(NB_BLOCK) k_update_impulses(Rows R, float4* impulses, const u32* counts) {
-	u32 n = counts[CNT_CONTACTS];
+	u32 n = 8 * counts[CNT_BATCHES];
 	for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+		if (R.contact[j] == NB_NONE) continue;
 		const float* c = R.plane + j; const u32 S = R.stride;
 		float s0 = R.state[0*S + j], s1 = R.state[1*S + j], s2 = R.state[2*S + j];
 		float4* dst = impulses + R.contact[j];

@@ -116,9 +116,12 @@ struct Sets {
 	}
 };
 
+static int g_overflow = 0;
+
 struct Out {
-	nbo_contact* data; nbo_pair* bodies; u64* tags; u32* features; u32 count;
+	nbo_contact* data; nbo_pair* bodies; u64* tags; u32* features; u32 count; u32 capacity;
 	void push(const float p[3], float pen, const float n[3], u32 a, u32 b, u64 tag, u32 feature) {
+		if (count >= capacity) { g_overflow = 1; return; }  // the reference never checks; the oracle refuses to overrun test buffers
 		nbo_contact c = { { p[0], p[1], p[2] }, pen, { n[0], n[1], n[2] }, 0.5f };  // friction fixed: nudge.cpp:2105,2456,2515,2598
 		data[count] = c; bodies[count].a = a; bodies[count].b = b; tags[count] = tag; features[count] = feature; ++count;
 	}
@@ -599,6 +602,7 @@ void nbo_rsqrt(const float* x, float* y, u32 n) { for (u32 i = 0; i < n; ++i) y[
 void nbo_collide(nbo_active_bodies* active_bodies, nbo_contact_data* contacts, const nbo_body_data* bodies_p, const nbo_collider_data* colliders_p, const nbo_connections* connections_p) {
 	const nbo_body_data& bodies = *bodies_p; const nbo_collider_data& colliders = *colliders_p; const nbo_connections& body_connections = *connections_p;
 	contacts->count = 0; contacts->sleeping_count = 0; active_bodies->count = 0;  // nudge.cpp:3001-3003
+	g_overflow = 0;
 	const u32 nboxes = colliders.boxes.count, nspheres = colliders.spheres.count, count = nboxes + nspheres;
 
 	struct AABB { float mn[4], mx[4]; };
@@ -691,7 +695,8 @@ void nbo_collide(nbo_active_bodies* active_bodies, nbo_contact_data* contacts, c
 			if (act[set]) live.push_back(pairs[i]);
 			else {
 				u64 ta = collider_tags[pairs[i].lo], tb = collider_tags[pairs[i].hi];
-				contacts->sleeping_pairs[contacts->sleeping_count++] = ta > tb ? ta | (tb << 32) : tb | (ta << 32);  // nudge.cpp:3697
+				if (contacts->sleeping_count < contacts->capacity) contacts->sleeping_pairs[contacts->sleeping_count++] = ta > tb ? ta | (tb << 32) : tb | (ta << 32);  // nudge.cpp:3697
+				else g_overflow = 1;
 			}
 		}
 	}
@@ -704,7 +709,7 @@ void nbo_collide(nbo_active_bodies* active_bodies, nbo_contact_data* contacts, c
 	}
 	for (size_t i = 0; i < bucket[2].size(); ++i) std::swap(bucket[2][i].lo, bucket[2][i].hi);
 
-	Out out = { contacts->data, contacts->bodies, contacts->tags, contacts->features, 0 };
+	Out out = { contacts->data, contacts->bodies, contacts->tags, contacts->features, 0, contacts->capacity };
 	BoxCtx bc = { colliders.boxes.data, transforms.data(), collider_tags.data() };
 	box_box_collide(bucket[0], bc, out);  // nudge.cpp:3753
 
@@ -753,6 +758,7 @@ void nbo_collide(nbo_active_bodies* active_bodies, nbo_contact_data* contacts, c
 	g_pairs = sorted_pairs_snapshot;
 }
 
+int nbo_last_overflow(void) { return g_overflow; }
 uint32_t nbo_last_pair_count(void) { return (uint32_t)g_pairs.size(); }
 void nbo_last_pairs(uint32_t* lo, uint32_t* hi) { for (size_t i = 0; i < g_pairs.size(); ++i) { lo[i] = g_pairs[i].lo; hi[i] = g_pairs[i].hi; } }
 void nbo_last_morton_order(uint32_t* s) { for (size_t i = 0; i < g_order.size(); ++i) s[i] = g_order[i]; }

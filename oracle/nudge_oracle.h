@@ -55,6 +55,7 @@ void nbo_free_impulses(nbo_impulse_data*);
 void nbo_free_constraints(nbo_constraint_data*);
 
 /* Introspection for stage-by-stage parity tests. */
+int nbo_last_overflow(void);                             /* 1 if the last nbo_collide ran out of contact capacity */
 uint32_t nbo_last_pair_count(void);                      /* broadphase pairs of the last nbo_collide (after the sort, before islands) */
 void nbo_last_pairs(uint32_t* lo, uint32_t* hi);          /* nudge.cpp:3493-3498: lo = later in Morton order, hi = earlier */
 void nbo_last_morton_order(uint32_t* sorted_indices);     /* nudge.cpp:3165-3172 */

@@ -49,7 +49,10 @@ class OracleSim(abi.HostState):
 
     def collide(self):
         self._free()
+        self.contacts.capacity = self.cap
         self.lib.nbo_collide(C.byref(self.active), C.byref(self.contacts), C.byref(self.bodies), C.byref(self.colliders), C.byref(self.conn))
+        if self.lib.nbo_last_overflow():
+            raise RuntimeError("oracle: contact capacity %d exceeded" % self.cap)
 
     def read_cached_impulses(self):
         self.impulses = self.lib.nbo_read_cached_impulses(C.byref(self.cache), C.byref(self.contacts))

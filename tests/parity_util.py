@@ -43,7 +43,7 @@ def rows_by_contact(view, n_contacts):
     first = np.full(n_contacts, lanes, np.int64)
     np.minimum.at(first, view["contact"].astype(np.int64), np.arange(lanes))
     assert (first < lanes).all()
-    return dict(rows=view["rows"][first], states=view["states"][first], batch=(first // 8).astype(np.uint32),
+    return dict(rows=view["rows"][first], states=view["states"][first], batch=(first // 8).astype(np.uint32), slot=first.astype(np.uint32),
                 a=view["a"][first], b=view["b"][first])
 
 
@@ -121,6 +121,7 @@ def compare_oracle_gpu_step(o, g, rep, sweeps_individually=True):
     if n:
         rep.check("row contacts are a permutation", len(order) == n and np.array_equal(np.sort(order), np.arange(n)))
         rep.eq("batch index", ok_["batch"], gk["batch_of_contact"])
+        rep.eq("slot (batch*8 + lane)", ok_["slot"], gk["slot_of_contact"])
         rep.eq("rows", ok_["rows"][order], gk["rows"]); rep.eq("row a", ok_["a"][order], gk["a"]); rep.eq("row b", ok_["b"][order], gk["b"])
         rep.eq("warm-start states", ok_["states"][order], gk["states"])
     g.download_bodies()

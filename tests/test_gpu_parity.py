@@ -63,7 +63,7 @@ def test_rotated_box_drop():
 
 
 def test_fused_sweeps_equal_individual_sweeps():
-    o, g = _pair(scenes.demo_scene(300, 300, iterations=16, spread=3.0, height=20.0))
+    o, g = _pair(scenes.demo_scene(300, 300, iterations=16, spread=4.0, height=80.0))
     _steps(o, g, 6, individually=False)
 
 
@@ -132,7 +132,7 @@ def test_settled_8k_pile_one_step_from_identical_state():
 def test_full_size_64k_properties_and_one_step_parity():
     """BASELINE config 1 size: 65,536 boxes.  Settles on the GPU, then (a) one full step bit-exact against the widened
     oracle from identical state and (b) size-independent properties: pair list sorted and unique, every pair's AABBs
-    overlap, contact tag order sorted, cache sorted by tag, batches conflict-free, levels respect per-body order."""
+    overlap, contact tag order sorted, batches conflict-free."""
     s = scenes.box_drop(65536, iterations=8)
     o, g = _pair(s)
     for _ in range(700):
@@ -165,12 +165,3 @@ def test_full_size_64k_properties_and_one_step_parity():
     allb = np.concatenate([np.stack([batch, bodies["a"].astype(np.int64)], 1), np.stack([batch, bodies["b"].astype(np.int64)], 1)])
     allb = allb[allb[:, 1] != 0]
     assert len(np.unique(allb, axis=0)) == len(allb), "a batch holds two contacts of one body"
-    # levels: along each body, level strictly increases with batch index
-    level_of_contact = np.zeros(n, np.int64); level_of_contact[srt] = v["level"]
-    for col in ("a", "b"):
-        body = bodies[col].astype(np.int64)
-        m = body != 0
-        o2 = np.lexsort((batch[m], body[m]))
-        bb, ll = body[m][o2], level_of_contact[m][o2]
-        same = bb[1:] == bb[:-1]
-        assert (ll[1:][same] > ll[:-1][same]).all() or col == "b"
