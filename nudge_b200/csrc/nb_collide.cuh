@@ -176,16 +176,21 @@ __global__ void k_clamp_count(u32* counts, int which, u32 cap) {
 }
 
 // ---------------- islands: lock-free union-find, smaller index becomes the root (nudge.cpp:3500-3703, 3788-3971) ----------------
-NB_DEV u32 uf_find(u32* parent, u32 x) {  // with path halving: every write points a node at one of its ancestors, so races are benign
-	volatile u32* vp = parent;
+// Invariant: parent[x] <= x, and only a current root is ever hooked (by CAS) under a smaller index.  Finds therefore
+// terminate and stay inside x's set even when they read stale L1 lines, so they use ordinary cacheable loads: the root
+// of the one giant pile component is read by every thread and would otherwise serialise in a single L2 slice.
+NB_DEV u32 uf_find(u32* parent, u32 x) {  // with path halving: every write points a node at one of its ancestors
 	while (true) {
-		u32 p = vp[x];
+		u32 p = parent[x];
 		if (p == x) return x;
-		u32 gp = vp[p];
+		u32 gp = parent[p];
 		if (gp == p) return p;
-		vp[x] = gp;
+		parent[x] = gp;
 		x = gp;
 	}
+}
+NB_DEV u32 uf_find_fresh(u32* parent, u32 x) {  // L2-coherent reads, for the final flatten
+	while (true) { u32 p = __ldcg(parent + x); if (p == x) return x; x = p; }
 }
 NB_DEV void uf_unite(u32* parent, u32 a, u32 b) {
 	if (!a || !b) return;  // body 0 is the static world and is ignored (nudge.cpp:3517-3519, 3583-3585)
@@ -193,7 +198,9 @@ NB_DEV void uf_unite(u32* parent, u32 a, u32 b) {
 		a = uf_find(parent, a); b = uf_find(parent, b);
 		if (a == b) return;
 		if (a < b) { u32 t = a; a = b; b = t; }
-		if (atomicCAS(&parent[a], a, b) == a) return;
+		u32 old = atomicCAS(&parent[a], a, b);
+		if (old == a) return;
+		a = old;  // a was not a root any more: continue from its real parent
 	}
 }
 __global__ void __launch_bounds__(NB_BLOCK) k_uf_init(u32* parent, u32* active, u32 B) {
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(NB_BLOCK) k_uf_union_contacts(u32* parent, con
 }
 __global__ void __launch_bounds__(NB_BLOCK) k_uf_flatten_active(u32* parent, u32* active, const uint8_t* idle, u32 B) {
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
-		u32 r = uf_find(parent, i);
+		u32 r = uf_find_fresh(parent, i);
 		parent[i] = r;  // roots never change here, so concurrent flattening is benign
 		if (i >= 1 && idle[i] != 0xff) active[r] = 1;  // nudge.cpp:3669-3672
 	}

@@ -116,27 +116,132 @@ __global__ void __launch_bounds__(NB_BLOCK) k_inertia(u32 B, const nb_transform*
 // holding neither of its bodies, a slot that receives its 8th contact is emitted and replaced by the last slot of
 // the list.  Buckets only interact through the global emission order, which equals the order of the contact
 // index at which each slot filled up, so 16 warps can replay them independently.
-#define NB_SCHED_SHARED 480  // list positions 32.. live in shared memory, positions 0..31 in registers (one per lane)
-#define NB_SCHED_MAXV (32 + NB_SCHED_SHARED)
-struct SchedSmem {
-	u32 a[8][NB_SCHED_SHARED];  // body ids, lane-major so that 32 threads read 32 consecutive slots
-	u32 b[8][NB_SCHED_SHARED];
-	u32 uid[NB_SCHED_SHARED];
-	u32 filled[NB_SCHED_SHARED];
-};
+// State layout: a slot has 16 entries (8 "a" bodies, 8 "b" bodies, NB_NONE = empty).  List positions 0..7 live in
+// registers, one ENTRY per lane: lane = 16*(position & 1) + entry, register index = position >> 1.  A contact is tested
+// against two positions with one compare and one ballot, so the serial chain per contact is a handful of instructions.
+// Positions 8.. use the same 16-entry layout in shared memory.  Invariant: every position >= vcount is all empty, so the
+// reference's always-free sentinel (nudge.cpp:4225-4227, 4313) is simply "the first position that does not conflict".
+#define NB_SCHED_REGSETS 4
+#define NB_SCHED_REGPOS (2 * NB_SCHED_REGSETS)
+#define NB_SCHED_SHARED 504
+#define NB_SCHED_MAXV (NB_SCHED_REGPOS + NB_SCHED_SHARED - 1)
 
 // slot_of[i] = uid << 3 | lane, where lane is the SIMD lane the contact lands in (= number of contacts already in its slot)
+//
+// ~99.9 % of all contacts go to list position 0 (measured), so the replay speculates: the next 8 - fill(position 0)
+// contacts are tested against position 0 and against each other with ONE __match_any_sync; all contacts before the first
+// conflict are accepted in parallel (they are exactly the ones the sequential first-fit would put there), and only the
+// conflicting contact runs the general search.  A lone warp pays ~8 cycles per instruction, so instructions per contact
+// are what matters here.
 __global__ void __launch_bounds__(32) k_schedule(const u32* sorted, const uint2* bodies, u32* slot_of, u32* slot_done, u32* slot_left, u32 slots_per_bucket,
 												 u32* complete_flag, u32* left_count /*[16]*/, u32* counts) {
-	__shared__ SchedSmem S;
-	const u32 bucket = blockIdx.x, lane = threadIdx.x;
+	__shared__ u32 S_ent[NB_SCHED_SHARED][16];
+	__shared__ u32 S_uid[NB_SCHED_REGPOS + NB_SCHED_SHARED];
+	const u32 bucket = blockIdx.x, lane = threadIdx.x, half = lane >> 4, ent = lane & 15, cidx = lane & 7;
 	const u32 n = counts[CNT_CONTACTS];
+	for (u32 k = lane; k < NB_SCHED_SHARED * 16; k += 32) (&S_ent[0][0])[k] = NB_NONE;
+	__syncwarp();
 	u32 vcount = 0, next_uid = 0;
-	u32 ra[8], rb[8], rf = 0, ruid = 0;  // the slot at list position `lane`
+	u32 f0 = 0, uid0 = 0;  // fill count and uid of list position 0 (warp uniform)
+	u32 reg[NB_SCHED_REGSETS];
 	#pragma unroll
-	for (int l = 0; l < 8; ++l) { ra[l] = 0; rb[l] = 0; }
+	for (int k = 0; k < NB_SCHED_REGSETS; ++k) reg[k] = NB_NONE;
 	u32* done = slot_done + (size_t)bucket * slots_per_bucket;
 	u32* left = slot_left + (size_t)bucket * slots_per_bucket;
+
+	// Removes the completed slot at list position j: the last slot of the list takes its place (nudge.cpp:4294-4306).
+	auto remove_pos = [&](u32 j) {
+		u32 last = vcount - 1;
+		if (last == 0) {  // the list held only this slot
+			if (lane < 16) reg[0] = NB_NONE;
+			vcount = 0; f0 = 0;
+			return;
+		}
+		u32 jh = j & 1;
+		u32 v;  // entry `ent` of the last position, in every lane
+		if (last < NB_SCHED_REGPOS) {
+			u32 src = NB_NONE;
+			#pragma unroll
+			for (u32 k = 0; k < NB_SCHED_REGSETS; ++k) if (k == (last >> 1)) src = reg[k];
+			v = __shfl_sync(0xffffffffu, src, 16 * (last & 1) + ent);
+		}
+		else v = S_ent[last - NB_SCHED_REGPOS][ent];
+		u32 last_uid = S_uid[last];
+		__syncwarp();
+		if (j != last) {
+			if (j < NB_SCHED_REGPOS) {
+				#pragma unroll
+				for (u32 k = 0; k < NB_SCHED_REGSETS; ++k) if (k == (j >> 1) && half == jh) reg[k] = v;
+			}
+			else if (lane < 16) S_ent[j - NB_SCHED_REGPOS][lane] = v;
+			if (lane == 0) S_uid[j] = last_uid;
+			if (j == 0) uid0 = last_uid;
+		}
+		if (last < NB_SCHED_REGPOS) {  // the vacated last position becomes empty again
+			#pragma unroll
+			for (u32 k = 0; k < NB_SCHED_REGSETS; ++k) if (k == (last >> 1) && half == (last & 1)) reg[k] = NB_NONE;
+		}
+		else if (lane < 16) S_ent[last - NB_SCHED_REGPOS][lane] = NB_NONE;
+		--vcount;
+		if (j == 0) f0 = __popc(__ballot_sync(0xffffffffu, reg[0] != NB_NONE) & 0xffu);
+		__syncwarp();
+	};
+
+	// General first-fit for one contact (nudge.cpp:4250-4314).  Returns false on capacity overflow.
+	auto place_general = [&](u32 i, u32 ca, u32 cb) -> bool {
+		u32 j = NB_NONE, f = 0;
+		#pragma unroll
+		for (u32 k = 0; k < NB_SCHED_REGSETS; ++k) {
+			u32 hit = __ballot_sync(0xffffffffu, reg[k] == ca || reg[k] == cb);
+			u32 occ = __ballot_sync(0xffffffffu, reg[k] != NB_NONE);
+			if (j == NB_NONE) {
+				if (!(hit & 0xffffu)) { j = 2 * k; f = __popc(occ & 0xffu); }
+				else if (!(hit >> 16)) { j = 2 * k + 1; f = __popc((occ >> 16) & 0xffu); }
+			}
+		}
+		if (j == NB_NONE) {  // all eight register positions conflict: continue in shared memory, two positions per round
+			for (u32 pb = 0; ; pb += 2) {
+				u32 pos = pb + half;
+				if (pb >= NB_SCHED_SHARED) return false;
+				u32 v = pos < NB_SCHED_SHARED ? S_ent[pos][ent] : ca;
+				u32 hit = __ballot_sync(0xffffffffu, v == ca || v == cb);
+				u32 occ = __ballot_sync(0xffffffffu, v != NB_NONE);
+				if (!(hit & 0xffffu)) { j = NB_SCHED_REGPOS + pb; f = __popc(occ & 0xffu); break; }
+				if (!(hit >> 16)) { j = NB_SCHED_REGPOS + pb + 1; f = __popc((occ >> 16) & 0xffu); break; }
+			}
+		}
+		if (j >= NB_SCHED_MAXV) return false;
+		if (j < NB_SCHED_REGPOS) {
+			u32 jh = j & 1;
+			#pragma unroll
+			for (u32 k = 0; k < NB_SCHED_REGSETS; ++k)
+				if (k == (j >> 1)) {
+					if (lane == 16 * jh + f) reg[k] = ca;
+					if (lane == 16 * jh + 8 + f) reg[k] = cb;
+				}
+			if (j == 0) f0 = f + 1;
+		}
+		else {
+			if (lane == 0) { S_ent[j - NB_SCHED_REGPOS][f] = ca; S_ent[j - NB_SCHED_REGPOS][8 + f] = cb; }
+			__syncwarp();
+		}
+		u32 uid;
+		if (j == vcount) {  // the sentinel was taken: a new slot (f is 0)
+			uid = next_uid++;
+			if (lane == 0) { S_uid[j] = uid; done[uid] = NB_NONE; }
+			if (j == 0) uid0 = uid;
+			++vcount;
+			__syncwarp();
+		}
+		else uid = j ? S_uid[j] : uid0;
+		if (lane == 0) slot_of[i] = (uid << 3) | f;
+		if (f == 7) {
+			if (lane == 0) { done[uid] = i; complete_flag[i] = 1; }
+			remove_pos(j);
+		}
+		return true;
+	};
+
 	// software pipeline: the (ca, cb) of the next 32 contacts of this bucket are fetched while the current 32 are placed
 	u32 nx_ca = 0, nx_cb = 0;
 	{
@@ -149,94 +254,49 @@ __global__ void __launch_bounds__(32) k_schedule(const u32* sorted, const uint2*
 			u32 i1 = base + 16 * 32 + 16 * lane;
 			if (i1 < n) { uint2 ab = bodies[sorted[i1]]; nx_ca = ab.x ? ab.x : ab.y; nx_cb = ab.y ? ab.y : ab.x; complete_flag[i1] = 0; }
 		}
-		u32 steps = min(32u, (n - base + 15) / 16);
-		for (u32 s = 0; s < steps; ++s) {
-			u32 i = base + 16 * s;
-			u32 ca = __shfl_sync(0xffffffffu, my_ca, s), cb = __shfl_sync(0xffffffffu, my_cb, s);
-			// first list position with no conflict; position vcount is the always-free sentinel (nudge.cpp:4250-4257)
-			u32 j = vcount;
-			{
-				bool conflict = false;
-				#pragma unroll
-				for (u32 l = 0; l < 8; ++l)
-					if (l < rf) conflict |= (ra[l] == ca) | (rb[l] == ca) | (ra[l] == cb) | (rb[l] == cb);
-				u32 ballot = __ballot_sync(0xffffffffu, lane < vcount && !conflict);
-				if (ballot) j = __ffs(ballot) - 1;
-				else if (vcount > 32) {
-					for (u32 jb = 0; jb < vcount - 32; jb += 32) {
-						u32 jj = jb + lane;
-						bool free_slot = false;
-						if (jj < vcount - 32) {
-							u32 f = S.filled[jj];
-							bool c2 = false;
-							#pragma unroll
-							for (u32 l = 0; l < 8; ++l)
-								if (l < f) { u32 sa = S.a[l][jj], sb = S.b[l][jj]; c2 |= (sa == ca) | (sb == ca) | (sa == cb) | (sb == cb); }
-							free_slot = !c2;
-						}
-						u32 bl = __ballot_sync(0xffffffffu, free_slot);
-						if (bl) { j = 32 + jb + __ffs(bl) - 1; break; }
-					}
+		const u32 steps = min(32u, (n - base + 15) / 16);
+		u32 s = 0;
+		while (s < steps) {
+			// ---- speculative group: the contacts that would fill list position 0 ----
+			u32 src = s + cidx - f0;                         // chunk index of the contact this lane would hold (lanes 0..15)
+			bool isnew = lane < 16 && cidx >= f0 && src < steps;
+			u32 va = __shfl_sync(0xffffffffu, my_ca, src & 31), vb = __shfl_sync(0xffffffffu, my_cb, src & 31);
+			u32 cand = ent < 8 ? va : vb;
+			u32 merged = isnew ? cand : ((lane < 16 && cidx < f0) ? reg[0] : 0xffffff00u + lane);  // unique dummies never match
+			u32 peers = __match_any_sync(0xffffffffu, merged);
+			u32 low = (1u << cidx) - 1u;
+			bool confl = isnew && (peers & (low | (low << 8))) != 0;  // equal to an entry of an EARLIER contact (its own a/b partner is allowed)
+			u32 cbal = __ballot_sync(0xffffffffu, confl);
+			u32 cm = (cbal | (cbal >> 8)) & 0xffu;
+			u32 avail = min(8u - f0, steps - s);
+			u32 k = cm ? (u32)(__ffs(cm) - 1) : f0 + avail;   // first conflicting lane of position 0, or one past the last candidate
+			if (k > f0) {
+				if (vcount == 0) {  // position 0 was the sentinel: a new slot
+					uid0 = next_uid++; vcount = 1;
+					if (lane == 0) { S_uid[0] = uid0; done[uid0] = NB_NONE; }
 				}
-			}
-			if (j == vcount) {  // open a new slot at the end of the list
-				if (vcount >= NB_SCHED_MAXV) { if (lane == 0) atomicOr(&counts[CNT_OVERFLOW], OVF_SCHED); return; }
-				if (j < 32) { if (lane == j) { ra[0] = ca; rb[0] = cb; rf = 1; ruid = next_uid; } }
-				else if (lane == 0) { S.a[0][j - 32] = ca; S.b[0][j - 32] = cb; S.filled[j - 32] = 1; S.uid[j - 32] = next_uid; }
-				if (lane == 0) { slot_of[i] = next_uid << 3; done[next_uid] = NB_NONE; }
-				++next_uid; ++vcount;
-				__syncwarp();
-			}
-			else {
-				u32 f, uid;
-				if (j < 32) { f = __shfl_sync(0xffffffffu, rf, j); uid = __shfl_sync(0xffffffffu, ruid, j); }
-				else { f = S.filled[j - 32]; uid = S.uid[j - 32]; }
-				__syncwarp();
-				if (j < 32) {
-					if (lane == j) {
-						#pragma unroll
-						for (u32 l = 0; l < 8; ++l) if (l == f) { ra[l] = ca; rb[l] = cb; }
-						rf = f + 1;
-					}
-				}
-				else if (lane == 0) { S.a[f][j - 32] = ca; S.b[f][j - 32] = cb; S.filled[j - 32] = f + 1; }
-				if (lane == 0) slot_of[i] = (uid << 3) | f;
-				__syncwarp();
-				if (f == 7) {  // slot complete: emitted now, the last slot of the list takes its place (nudge.cpp:4294-4306)
-					if (lane == 0) { done[uid] = i; complete_flag[i] = 1; }
-					u32 last = vcount - 1;
-					if (j != last) {
-						if (last < 32) {  // register -> register
-							u32 tf = __shfl_sync(0xffffffffu, rf, last), tu = __shfl_sync(0xffffffffu, ruid, last);
-							#pragma unroll
-							for (u32 l = 0; l < 8; ++l) {
-								u32 ta = __shfl_sync(0xffffffffu, ra[l], last), tb = __shfl_sync(0xffffffffu, rb[l], last);
-								if (lane == j) { ra[l] = ta; rb[l] = tb; }
-							}
-							if (lane == j) { rf = tf; ruid = tu; }
-						}
-						else if (j < 32) {  // shared -> register
-							if (lane == j) {
-								#pragma unroll
-								for (u32 l = 0; l < 8; ++l) { ra[l] = S.a[l][last - 32]; rb[l] = S.b[l][last - 32]; }
-								rf = S.filled[last - 32]; ruid = S.uid[last - 32];
-							}
-						}
-						else {  // shared -> shared
-							if (lane < 8) { S.a[lane][j - 32] = S.a[lane][last - 32]; S.b[lane][j - 32] = S.b[lane][last - 32]; }
-							if (lane == 8) { S.filled[j - 32] = S.filled[last - 32]; S.uid[j - 32] = S.uid[last - 32]; }
-						}
-					}
-					if (last < 32 && lane == last) rf = 0;
-					--vcount;
+				bool take = isnew && cidx < k;
+				if (take) reg[0] = cand;
+				if (take && ent < 8) slot_of[base + 16 * src] = (uid0 << 3) | cidx;
+				s += k - f0; f0 = k;
+				if (k == 8) {  // position 0 is complete
+					u32 i_last = base + 16 * (s - 1);
+					if (lane == 0) { done[uid0] = i_last; complete_flag[i_last] = 1; }
 					__syncwarp();
+					remove_pos(0);
+					continue;  // re-evaluate against the slot that moved into position 0
 				}
+			}
+			if (cm && s < steps) {  // the contact at s conflicts with position 0: general first-fit
+				u32 ca = __shfl_sync(0xffffffffu, my_ca, s), cb = __shfl_sync(0xffffffffu, my_cb, s);
+				if (!place_general(base + 16 * s, ca, cb)) { if (lane == 0) atomicOr(&counts[CNT_OVERFLOW], OVF_SCHED); return; }
+				++s;
 			}
 		}
 	}
 	// leftovers are flushed bucket-major in list order (nudge.cpp:4316-4338)
-	if (lane < min(vcount, 32u)) left[ruid] = lane;
-	if (vcount > 32) for (u32 jj = lane; jj < vcount - 32; jj += 32) left[S.uid[jj]] = 32 + jj;
+	__syncwarp();
+	for (u32 jj = lane; jj < vcount; jj += 32) left[S_uid[jj]] = jj;
 	if (lane == 0) left_count[bucket] = vcount;
 }
 
