@@ -51,7 +51,7 @@ struct nb_context {
 	u32* sorted; float4* impulses;
 	// setup / solve
 	float4* inertia;
-	u32* slot_of; u32* slot_done; u32* slot_left; u32* left_count; u32* batch_of; u32* slot_idx; u32* version;
+	u32* slot_of; u32* slot_done; u32* slot_left; u32* left_count; u32* batch_of; u32* slot_idx; float4* mw;
 	Rows rows;
 };
 
@@ -144,8 +144,8 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ALLOC(ctx->sorted, C); ALLOC(ctx->impulses, C);
 	ALLOC(ctx->inertia, 2 * (size_t)B);
 	ALLOC(ctx->slot_of, C); ALLOC(ctx->slot_done, 16 * (size_t)ctx->slots_per_bucket); ALLOC(ctx->slot_left, 16 * (size_t)ctx->slots_per_bucket);
-	ALLOC(ctx->left_count, 16); ALLOC(ctx->batch_of, C); ALLOC(ctx->slot_idx, C); ALLOC(ctx->version, B);
-	ALLOC(ctx->rows.plane, (size_t)ROW_PLANES * ctx->cstride); ALLOC(ctx->rows.state, 3 * (size_t)ctx->cstride);
+	ALLOC(ctx->left_count, 16); ALLOC(ctx->batch_of, C); ALLOC(ctx->slot_idx, C); ALLOC(ctx->mw, 2 * (size_t)B);
+	ALLOC(ctx->rows.plane, (size_t)ROW_PLANES_TOTAL * ctx->cstride); ALLOC(ctx->rows.state, 3 * (size_t)ctx->cstride);
 	ALLOC(ctx->rows.a, ctx->cstride); ALLOC(ctx->rows.b, ctx->cstride); ALLOC(ctx->rows.contact, ctx->cstride); ALLOC(ctx->rows.wait, 2 * (size_t)ctx->cstride);
 	ctx->rows.stride = ctx->cstride;
 	ctx->pair_keys = ctx->sb.keys[0];
@@ -163,6 +163,7 @@ int nb_create(const nb_config* config, nb_context** out) {
 	int per_sm = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, NB_BLOCK, 0));
 	if (per_sm < 1) { ctx->error = "k_solve does not fit on an SM"; return NB_ERR_CUDA; }
+	if (const char* e = getenv("NB_SOLVE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
 	ctx->coop_blocks_solve = ctx->sms * per_sm;  // all co-resident: the dataflow solver relies on it
 	CK(cudaDeviceSynchronize());
 	return NB_OK;
@@ -393,13 +394,14 @@ int nb_write_cached_impulses(nb_context* ctx, void* stream) {
 static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) {
 	Rows R = ctx->rows;
 	const float4* impulses = ctx->impulses;
-	nb_body_momentum* mom = ctx->mom;
-	u32* version = ctx->version;
+	float4* mw = ctx->mw;
 	u32* counts = ctx->counts;
-	CK(cudaMemsetAsync(version, 0, sizeof(u32) * (ctx->B ? ctx->B : 1), st));
-	void* args[] = { &R, &impulses, &mom, &version, &mode, &sweeps, &counts };
+	const u32 B = ctx->B;
+	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw);
+	void* args[] = { &R, &impulses, &mw, &mode, &sweeps, &counts };
 	CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
-	++ctx->launches;
+	k_mw_out<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw, mode);
+	ctx->launches += 3;
 	return NB_OK;
 }
 

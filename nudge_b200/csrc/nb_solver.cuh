@@ -20,7 +20,8 @@
 
 enum {  // constraint row planes, member order of ContactConstraintV (nudge.cpp:907-957)
 	PA_Z, PA_X, PA_Y, PB_Z, PB_X, PB_Y, N_X, U_X, V_X, N_Y, U_Y, V_Y, N_Z, U_Z, V_Z, BIAS, FRICTION, NVTNI, FC_X, FC_Y, FC_Z,
-	NA_X, NA_Y, NA_Z, NB_X, NB_Y, NB_Z, UA_X, UA_Y, UA_Z, VA_X, VA_Y, VA_Z, UB_X, UB_Y, UB_Z, VB_X, VB_Y, VB_Z, ROW_PLANES
+	NA_X, NA_Y, NA_Z, NB_X, NB_Y, NB_Z, UA_X, UA_Y, UA_Z, VA_X, VA_Y, VA_Z, UB_X, UB_Y, UB_Z, VB_X, VB_Y, VB_Z, ROW_PLANES,
+	MASS_A = ROW_PLANES, MASS_B, ROW_PLANES_TOTAL  // two extra planes: the bodies' inverse masses (the reference keeps them in BodyMomentum::unused0)
 };
 
 NB_DEV bool key_less(u64 ta, u32 fa, u64 tb, u32 fb) { return ta < tb || (ta == tb && fa < fb); }
@@ -432,27 +433,49 @@ __global__ void __launch_bounds__(NB_BLOCK) k_build_rows(const float4* contacts,
 		P[NA_X*S] = nb_neg(na_x); P[NA_Y*S] = nb_neg(na_y); P[NA_Z*S] = nb_neg(na_z);
 		P[UB_X*S] = ub_xt; P[UB_Y*S] = ub_yt; P[UB_Z*S] = ub_zt; P[VB_X*S] = vb_xt; P[VB_Y*S] = vb_yt; P[VB_Z*S] = vb_zt;
 		P[NB_X*S] = nb_x; P[NB_Y*S] = nb_y; P[NB_Z*S] = nb_z;
+		P[MASS_A*S] = a_mass_inverse; P[MASS_B*S] = b_mass_inverse;
 		R.a[j] = a; R.b[j] = b;
 	}
 }
 
-// body momentum rows are shared between SMs inside the level loop: always go through L2
-NB_DEV void ld_momentum(const nb_body_momentum* m, u32 i, float4& lin, float4& ang) {
-	const float4* p = reinterpret_cast<const float4*>(m + i);
-	lin = __ldcg(p); ang = __ldcg(p + 1);
+// ---------------- solver working set: momentum rows with an embedded token ----------------
+// mw[2*body] = (velocity.xyz, token), mw[2*body+1] = (angular_velocity.xyz, token).  Each 16-byte half is read and written
+// with single 128-bit relaxed GPU-scope accesses, so a half is always seen whole and carries the token of the contact
+// that wrote it: the data validates itself, no fence and no separate flag are needed.
+NB_DEV float4 ld128(const float4* p) {
+	float4 v;
+	asm volatile("{\n .reg .b128 q;\n ld.relaxed.gpu.global.b128 q, [%4];\n mov.b128 {%0,%1,%2,%3}, q;\n}" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+	return v;
 }
-NB_DEV void st_momentum(nb_body_momentum* m, u32 i, float4 lin, float4 ang) {
-	float4* p = reinterpret_cast<float4*>(m + i);
-	__stcg(p, lin); __stcg(p + 1, ang);
+NB_DEV void st128(float4* p, float4 v) {
+	asm volatile("{\n .reg .b128 q;\n mov.b128 q, {%1,%2,%3,%4};\n st.relaxed.gpu.global.b128 [%0], q;\n}" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// One contact of the warm start (nudge.cpp:4563-4632).
-NB_DEV void warm_start_contact(const Rows& R, u32 j, const float4* impulses, nb_body_momentum* momentum, const u32* s_rsqrt) {
+__global__ void __launch_bounds__(NB_BLOCK) k_mw_in(u32 B, const nb_body_momentum* momentum, float4* mw) {
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+		const float4* p = reinterpret_cast<const float4*>(momentum + i);
+		float4 l = p[0], w = p[1];
+		l.w = 0.0f; w.w = 0.0f;  // token 0 = "nobody has written this body yet"
+		mw[2*i] = l; mw[2*i + 1] = w;
+	}
+}
+// mode 1 (sweeps): unused1 of touched bodies is zeroed like nudge.cpp:4823, 4849; unused0 keeps the inverse mass (4825-4827)
+__global__ void __launch_bounds__(NB_BLOCK) k_mw_out(u32 B, nb_body_momentum* momentum, const float4* mw, int mode) {
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+		float4* p = reinterpret_cast<float4*>(momentum + i);
+		float4 l = mw[2*i], w = mw[2*i + 1];
+		float4 ol = p[0], ow = p[1];
+		bool touched = asu(l.w) != 0;
+		p[0] = make_float4(l.x, l.y, l.z, ol.w);
+		p[1] = make_float4(w.x, w.y, w.z, (mode && touched) ? 0.0f : ow.w);
+	}
+}
+
+// One contact of the warm start (nudge.cpp:4563-4632); momentum rows passed in registers and updated in place.
+NB_DEV void warm_start_contact(const Rows& R, u32 j, const float4* impulses, float4& al, float4& aw, float4& bl, float4& bw, const u32* s_rsqrt) {
 	const float* P = R.plane + j; const u32 S = R.stride;
-	u32 a = R.a[j], b = R.b[j];
 	float4 ci = impulses[R.contact[j]];
-	float4 al, aw, bl, bw;
-	ld_momentum(momentum, a, al, aw); ld_momentum(momentum, b, bl, bw);
+	float a_mass_inverse = P[MASS_A*S], b_mass_inverse = P[MASS_B*S];
 	float n_x = P[N_X*S], n_y = P[N_Y*S], n_z = P[N_Z*S];
 	float u_x = P[U_X*S], u_y = P[U_Y*S], u_z = P[U_Z*S], v_x = P[V_X*S], v_y = P[V_Y*S], v_z = P[V_Z*S];
 	float normal_impulse = nb_max(n_x*ci.x + n_y*ci.y + n_z*ci.z, 0.0f);
@@ -473,24 +496,19 @@ NB_DEV void warm_start_contact(const Rows& R, u32 j, const float4* impulses, nb_
 	float bax = fix*P[UB_X*S] + fiy*P[VB_X*S] + normal_impulse*P[NB_X*S];
 	float bay = fix*P[UB_Y*S] + fiy*P[VB_Y*S] + normal_impulse*P[NB_Y*S];
 	float baz = fix*P[UB_Z*S] + fiy*P[VB_Z*S] + normal_impulse*P[NB_Z*S];
-	al.x -= lx * al.w; al.y -= ly * al.w; al.z -= lz * al.w;
+	al.x -= lx * a_mass_inverse; al.y -= ly * a_mass_inverse; al.z -= lz * a_mass_inverse;
 	aw.x += aax; aw.y += aay; aw.z += aaz;
-	bl.x += lx * bl.w; bl.y += ly * bl.w; bl.z += lz * bl.w;
+	bl.x += lx * b_mass_inverse; bl.y += ly * b_mass_inverse; bl.z += lz * b_mass_inverse;
 	bw.x += bax; bw.y += bay; bw.z += baz;
 	R.state[0*S + j] = normal_impulse; R.state[1*S + j] = fix; R.state[2*S + j] = fiy;
-	if (a) st_momentum(momentum, a, al, aw);  // body 0 is static: its row only ever changes by +-0
-	if (b) st_momentum(momentum, b, bl, bw);
 }
 
 // One contact of one projected Gauss-Seidel sweep (nudge.cpp:4646-4853), same operation order, FMAs where the source has madd.
-NB_DEV void solve_contact(const Rows& R, u32 j, nb_body_momentum* momentum, const u32* s_rcp, const u32* s_rsqrt) {
+NB_DEV void solve_contact(const Rows& R, u32 j, float4& al, float4& aw, float4& bl, float4& bw, const u32* s_rcp, const u32* s_rsqrt) {
 	const float* c = R.plane + j; const u32 S = R.stride;
-	u32 a = R.a[j], b = R.b[j];
-	float4 al, aw, bl, bw;
-	ld_momentum(momentum, a, al, aw); ld_momentum(momentum, b, bl, bw);
-	float a_velocity_x = al.x, a_velocity_y = al.y, a_velocity_z = al.z, a_mass_inverse = al.w;
+	float a_velocity_x = al.x, a_velocity_y = al.y, a_velocity_z = al.z, a_mass_inverse = c[MASS_A*S];
 	float a_angular_velocity_x = aw.x, a_angular_velocity_y = aw.y, a_angular_velocity_z = aw.z;
-	float b_velocity_x = bl.x, b_velocity_y = bl.y, b_velocity_z = bl.z, b_mass_inverse = bl.w;
+	float b_velocity_x = bl.x, b_velocity_y = bl.y, b_velocity_z = bl.z, b_mass_inverse = c[MASS_B*S];
 	float b_angular_velocity_x = bw.x, b_angular_velocity_y = bw.y, b_angular_velocity_z = bw.z;
 	float pa_z = c[PA_Z*S], pa_x = c[PA_X*S], pa_y = c[PA_Y*S];
 	float v_xa = nb_madd(a_angular_velocity_y, pa_z, a_velocity_x);
@@ -512,7 +530,7 @@ NB_DEV void solve_contact(const Rows& R, u32 j, nb_body_momentum* momentum, cons
 	float t_z = n_x * v_x, t_x = v_x * fu_x, t_y = v_x * fv_x;
 	float n_z = c[N_Z*S], fu_z = c[U_Z*S], fv_z = c[V_Z*S];
 	float normal_bias = c[BIAS*S];
-	float old_normal_impulse = __ldcg(&R.state[0*S + j]);
+	float old_normal_impulse = R.state[0*S + j];
 	float normal_factor = c[NVTNI*S];
 	t_z = nb_madd(n_y, v_y, t_z); t_x = nb_madd(v_y, fu_y, t_x); t_y = nb_madd(v_y, fv_y, t_y);
 	normal_bias = normal_bias + old_normal_impulse;
@@ -522,7 +540,7 @@ NB_DEV void solve_contact(const Rows& R, u32 j, nb_body_momentum* momentum, cons
 	float tl2 = t_xx + t_yy;
 	normal_impulse = nb_max(normal_impulse, 0.0f);
 	t_x *= tl2; t_y *= tl2;
-	__stcg(&R.state[0*S + j], normal_impulse);
+	R.state[0*S + j] = normal_impulse;
 	float max_friction_impulse = normal_impulse * c[FRICTION*S];
 	normal_impulse = normal_impulse - old_normal_impulse;
 	float friction_factor = t_xx * c[FC_X*S];
@@ -535,7 +553,7 @@ NB_DEV void solve_contact(const Rows& R, u32 j, nb_body_momentum* momentum, cons
 	a_angular_velocity_x = nb_madd(c[NA_X*S], normal_impulse, a_angular_velocity_x);
 	a_angular_velocity_y = nb_madd(c[NA_Y*S], normal_impulse, a_angular_velocity_y);
 	a_angular_velocity_z = nb_madd(c[NA_Z*S], normal_impulse, a_angular_velocity_z);
-	float old_friction_impulse_x = __ldcg(&R.state[1*S + j]), old_friction_impulse_y = __ldcg(&R.state[2*S + j]);
+	float old_friction_impulse_x = R.state[1*S + j], old_friction_impulse_y = R.state[2*S + j];
 	friction_factor = nb_min(1e+6f, friction_factor);  // first operand on NaN
 	float friction_impulse_x = t_x*friction_factor, friction_impulse_y = t_y*friction_factor;
 	friction_impulse_x = old_friction_impulse_x - friction_impulse_x;
@@ -549,7 +567,7 @@ NB_DEV void solve_contact(const Rows& R, u32 j, nb_body_momentum* momentum, cons
 	friction_clamp_scale = nb_min(1.0f, friction_clamp_scale);
 	friction_impulse_x = friction_impulse_x * friction_clamp_scale;
 	friction_impulse_y = friction_impulse_y * friction_clamp_scale;
-	__stcg(&R.state[1*S + j], friction_impulse_x); __stcg(&R.state[2*S + j], friction_impulse_y);
+	R.state[1*S + j] = friction_impulse_x; R.state[2*S + j] = friction_impulse_y;
 	friction_impulse_x -= old_friction_impulse_x;
 	friction_impulse_y -= old_friction_impulse_y;
 	linear_impulse_x = nb_madd(fu_x, friction_impulse_x, linear_impulse_x);
@@ -559,34 +577,32 @@ NB_DEV void solve_contact(const Rows& R, u32 j, nb_body_momentum* momentum, cons
 	linear_impulse_y = nb_madd(fv_y, friction_impulse_y, linear_impulse_y);
 	linear_impulse_z = nb_madd(fv_z, friction_impulse_y, linear_impulse_z);
 	float a_mass_inverse_neg = nb_neg(a_mass_inverse);
-	a_velocity_x = nb_madd(linear_impulse_x, a_mass_inverse_neg, a_velocity_x);
-	a_velocity_y = nb_madd(linear_impulse_y, a_mass_inverse_neg, a_velocity_y);
-	a_velocity_z = nb_madd(linear_impulse_z, a_mass_inverse_neg, a_velocity_z);
+	al.x = nb_madd(linear_impulse_x, a_mass_inverse_neg, a_velocity_x);
+	al.y = nb_madd(linear_impulse_y, a_mass_inverse_neg, a_velocity_y);
+	al.z = nb_madd(linear_impulse_z, a_mass_inverse_neg, a_velocity_z);
 	a_angular_velocity_x = nb_madd(c[UA_X*S], friction_impulse_x, a_angular_velocity_x);
 	a_angular_velocity_y = nb_madd(c[UA_Y*S], friction_impulse_x, a_angular_velocity_y);
 	a_angular_velocity_z = nb_madd(c[UA_Z*S], friction_impulse_x, a_angular_velocity_z);
-	a_angular_velocity_x = nb_madd(c[VA_X*S], friction_impulse_y, a_angular_velocity_x);
-	a_angular_velocity_y = nb_madd(c[VA_Y*S], friction_impulse_y, a_angular_velocity_y);
-	a_angular_velocity_z = nb_madd(c[VA_Z*S], friction_impulse_y, a_angular_velocity_z);
-	b_velocity_x = nb_madd(linear_impulse_x, b_mass_inverse, b_velocity_x);
-	b_velocity_y = nb_madd(linear_impulse_y, b_mass_inverse, b_velocity_y);
-	b_velocity_z = nb_madd(linear_impulse_z, b_mass_inverse, b_velocity_z);
+	aw.x = nb_madd(c[VA_X*S], friction_impulse_y, a_angular_velocity_x);
+	aw.y = nb_madd(c[VA_Y*S], friction_impulse_y, a_angular_velocity_y);
+	aw.z = nb_madd(c[VA_Z*S], friction_impulse_y, a_angular_velocity_z);
+	bl.x = nb_madd(linear_impulse_x, b_mass_inverse, b_velocity_x);
+	bl.y = nb_madd(linear_impulse_y, b_mass_inverse, b_velocity_y);
+	bl.z = nb_madd(linear_impulse_z, b_mass_inverse, b_velocity_z);
 	b_angular_velocity_x = nb_madd(c[UB_X*S], friction_impulse_x, b_angular_velocity_x);
 	b_angular_velocity_y = nb_madd(c[UB_Y*S], friction_impulse_x, b_angular_velocity_y);
 	b_angular_velocity_z = nb_madd(c[UB_Z*S], friction_impulse_x, b_angular_velocity_z);
-	b_angular_velocity_x = nb_madd(c[VB_X*S], friction_impulse_y, b_angular_velocity_x);
-	b_angular_velocity_y = nb_madd(c[VB_Y*S], friction_impulse_y, b_angular_velocity_y);
-	b_angular_velocity_z = nb_madd(c[VB_Z*S], friction_impulse_y, b_angular_velocity_z);
-	// unused1 is zeroed on touched bodies (nudge.cpp:4823, 4849)
-	if (a) st_momentum(momentum, a, make_float4(a_velocity_x, a_velocity_y, a_velocity_z, a_mass_inverse), make_float4(a_angular_velocity_x, a_angular_velocity_y, a_angular_velocity_z, 0.0f));
-	if (b) st_momentum(momentum, b, make_float4(b_velocity_x, b_velocity_y, b_velocity_z, b_mass_inverse), make_float4(b_angular_velocity_x, b_angular_velocity_y, b_angular_velocity_z, 0.0f));
+	bw.x = nb_madd(c[VB_X*S], friction_impulse_y, b_angular_velocity_x);
+	bw.y = nb_madd(c[VB_Y*S], friction_impulse_y, b_angular_velocity_y);
+	bw.z = nb_madd(c[VB_Z*S], friction_impulse_y, b_angular_velocity_z);
 }
 
-// mode 0: warm start (one pass); mode 1: `sweeps` PGS sweeps.  Co-resident grid, no barrier: work item q = sweep*NS + slot
-// is handled by thread q % threads in increasing q, which is a topological order of the dependency graph, so the lowest
+// mode 0: warm start (one pass); mode 1: `sweeps` PGS sweeps.  Co-resident grid, no barrier.  Thread t owns slots t, t+T, ...
+// (so the per-contact solver state stays private to one thread) and walks them sweep by sweep; within and across threads the
+// items are visited in increasing (sweep, slot), which is a topological order of the dependency graph, so the lowest
 // unfinished item is always runnable.  Inside a warp the lanes poll instead of blocking, so a lane may depend on another
-// lane of its own warp.  version[] must be zero at launch.
-__global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impulses, nb_body_momentum* momentum, u32* version, int mode, u32 sweeps, u32* counts) {
+// lane of its own warp.  mw must come from k_mw_in (all tokens 0).
+__global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impulses, float4* mw, int mode, u32 sweeps, u32* counts) {
 	__shared__ u32 s_rcp[2048];
 	__shared__ u32 s_rsqrt[2048];
 	for (u32 i = threadIdx.x; i < 2048; i += blockDim.x) { s_rcp[i] = g_rcp_lut[i]; s_rsqrt[i] = g_rsqrt_lut[i]; }
@@ -594,15 +610,13 @@ __global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impuls
 	const u32 NS = 8 * counts[CNT_BATCHES];
 	const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
 	const u32 passes = mode ? sweeps : 1;
-	const u64 total = (u64)passes * NS;
 	const u32 S = R.stride;
-	for (u64 q0 = 0; q0 < total; q0 += nth) {  // uniform trip count for the whole grid
-		u64 q = q0 + tid;
-		bool pending = false;
-		u32 slot = 0, a = 0, b = 0, exp_a = 0, exp_b = 0, token = 0;
-		if (q < total) {
-			u32 w = (u32)(q / NS); slot = (u32)(q - (u64)w * NS);
-			if (R.contact[slot] != NB_NONE) {
+	for (u32 w = 0; w < passes; ++w)
+		for (u32 s0 = 0; s0 < NS; s0 += nth) {  // uniform trip count for the whole grid
+			u32 slot = s0 + tid;
+			bool pending = false;
+			u32 a = 0, b = 0, exp_a = 0, exp_b = 0, token = 0;
+			if (slot < NS && R.contact[slot] != NB_NONE) {
 				pending = true;
 				a = R.a[slot]; b = R.b[slot];
 				u32 wa = R.wait[slot], wb = R.wait[S + slot];
@@ -611,21 +625,24 @@ __global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impuls
 				exp_a = (wa & NB_WAIT_PREV) ? (w ? (w - 1) * NS + (wa & ~NB_WAIT_PREV) + 1 : 0) : w * NS + wa + 1;
 				exp_b = (wb & NB_WAIT_PREV) ? (w ? (w - 1) * NS + (wb & ~NB_WAIT_PREV) + 1 : 0) : w * NS + wb + 1;
 			}
-		}
-		while (__any_sync(0xffffffffu, pending)) {
-			if (pending) {
-				bool ready = (!a || ld_acquire_u32(version + a) == exp_a) && (!b || ld_acquire_u32(version + b) == exp_b);
-				if (ready) {
-					if (mode) solve_contact(R, slot, momentum, s_rcp, s_rsqrt);
-					else warm_start_contact(R, slot, impulses, momentum, s_rsqrt);
-					__threadfence();
-					if (a) *((volatile u32*)(version + a)) = token;
-					if (b) *((volatile u32*)(version + b)) = token;
-					pending = false;
+			while (__any_sync(0xffffffffu, pending)) {
+				if (pending) {
+					float4 al = ld128(mw + 2*a);
+					if (!a || asu(al.w) == exp_a) {
+						float4 aw = ld128(mw + 2*a + 1), bl = ld128(mw + 2*b), bw = ld128(mw + 2*b + 1);
+						bool ready = (!a || asu(aw.w) == exp_a) && (!b || (asu(bl.w) == exp_b && asu(bw.w) == exp_b));
+						if (ready) {
+							if (mode) solve_contact(R, slot, al, aw, bl, bw, s_rcp, s_rsqrt);
+							else warm_start_contact(R, slot, impulses, al, aw, bl, bw, s_rsqrt);
+							float tk = asf(token);
+							if (a) { al.w = tk; aw.w = tk; st128(mw + 2*a, al); st128(mw + 2*a + 1, aw); }  // body 0 is static: never written
+							if (b) { bl.w = tk; bw.w = tk; st128(mw + 2*b, bl); st128(mw + 2*b + 1, bw); }
+							pending = false;
+						}
+					}
 				}
 			}
 		}
-	}
 }
 
 // ---------------- update_cached_impulses (nudge.cpp:4857-4884) ----------------
