@@ -690,6 +690,7 @@ __global__ void __launch_bounds__(NB_BLOCK) k_narrowphase(const uint2* live, u32
 		}
 	}
 	for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+		if (EMIT && (cnt[0*stride + j] | cnt[1*stride + j] | cnt[2*stride + j]) == 0) continue;  // the counting pass found nothing for this pair
 		uint2 pr = live[j];  // x = low half, y = high half of the reference's pair word
 		u32 nf = 0, ne = 0, no = 0;
 		if (j < n_bb) {

@@ -198,6 +198,23 @@ __global__ void __launch_bounds__(NB_BLOCK) k_sort_scatter(const u64* keys_in, u
 	}
 }
 
+// in-place exclusive scan of n <= 1024*64 words by one block: each thread owns a contiguous run
+__global__ void __launch_bounds__(1024) k_scan_single(u32* data, u32 n) {
+	__shared__ u32 sm[33];
+	u32 per = (n + 1023) / 1024;
+	u32 begin = min(n, threadIdx.x * per), end = min(n, begin + per);
+	u32 sum = 0;
+	for (u32 i = begin; i < end; ++i) sum += data[i];
+	u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	u32 incl = warp_incl_scan(sum);
+	if (lane == 31) sm[wid] = incl;
+	__syncthreads();
+	if (wid == 0) { u32 w = sm[lane]; u32 wi = warp_incl_scan(w); sm[lane] = wi - w; }
+	__syncthreads();
+	u32 run = incl - sum + sm[wid];
+	for (u32 i = begin; i < end; ++i) { u32 v = data[i]; data[i] = run; run += v; }
+}
+
 struct SortBuffers { u64* keys[2]; u32* vals[2]; u32* hist; u32* block_sums; };
 
 // Sorts bits [begin_bit, end_bit) of keys[cur] (+vals[cur]); returns which buffer (0/1) holds the result.
