@@ -85,6 +85,7 @@ int nb_upload_bodies(nb_context*, const nb_body_data* host, void* stream);
 int nb_upload_colliders(nb_context*, const nb_collider_data* host, void* stream);
 int nb_upload_connections(nb_context*, const nb_body_connections* host, void* stream);
 int nb_upload_cache(nb_context*, const nb_contact_cache* host, void* stream);
+int nb_upload_contacts(nb_context*, const nb_contact_data* host /* may be null */, const nb_active_bodies* host_active /* may be null */, void* stream); /* synchronises */
 int nb_download_bodies(nb_context*, nb_body_data* host, void* stream);
 int nb_download_contacts(nb_context*, nb_contact_data* host, nb_active_bodies* host_active, void* stream); /* synchronises */
 int nb_download_cache(nb_context*, nb_contact_cache* host, void* stream);                                  /* synchronises */

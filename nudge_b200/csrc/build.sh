@@ -9,4 +9,5 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=fa
 g++ -O2 -fPIC -msse2 -c nb_lut_host.cpp -o ../lib/nb_lut_host.o
 $NVCC $FLAGS ${NB_PTXAS_V:+-Xptxas -v} -c nb_api.cu -o ../lib/nb_api.o
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/libnudge_b200.so ../lib/nb_api.o ../lib/nb_lut_host.o -lcudart_static -ldl -lrt -lpthread
-echo "built nudge_b200/lib/libnudge_b200.so"
+g++ -O2 -fPIC -shared -o ../lib/libnudge_compat.so nudge_compat.cpp -L../lib -lnudge_b200 -Wl,-rpath,'$ORIGIN'
+echo "built nudge_b200/lib/libnudge_b200.so and libnudge_compat.so"

@@ -262,6 +262,27 @@ int nb_download_contacts(nb_context* ctx, nb_contact_data* h, nb_active_bodies* 
 	CK(cudaStreamSynchronize((cudaStream_t)stream));
 	return c[CNT_OVERFLOW] ? NB_ERR_OVERFLOW : NB_OK;
 }
+// Host -> HBM for the outputs of collide (the reference lets user code add or edit contacts between the calls, example/main.cpp:288).
+int nb_upload_contacts(nb_context* ctx, const nb_contact_data* h, const nb_active_bodies* ha, void* stream) {
+	if (h) {
+		if (h->count > ctx->cfg.max_contacts || h->sleeping_count > ctx->cfg.max_contacts) { ctx->error = "too many contacts"; return NB_ERR_CAPACITY; }
+		H2D(ctx->fin.data, h->data, h->count, nb_contact); H2D(ctx->fin.bodies, h->bodies, h->count, nb_body_pair);
+		H2D(ctx->fin.tags, h->tags, h->count, u64); H2D(ctx->fin.features, h->features, h->count, u32);
+		if (h->sleeping_count) H2D(ctx->sleeping, h->sleeping_pairs, h->sleeping_count, u64);
+		u32 n[2] = { h->count, h->sleeping_count };
+		CK(cudaMemcpyAsync(ctx->counts + CNT_CONTACTS, &n[0], 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+		CK(cudaMemcpyAsync(ctx->counts + CNT_SLEEPING, &n[1], 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+	}
+	if (ha) {
+		if (ha->count > ctx->cfg.max_bodies) { ctx->error = "too many active bodies"; return NB_ERR_CAPACITY; }
+		H2D(ctx->active_idx, ha->indices, ha->count, u32);
+		u32 n = ha->count;
+		CK(cudaMemcpyAsync(ctx->counts + CNT_ACTIVE, &n, 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+	}
+	CK(cudaStreamSynchronize((cudaStream_t)stream));
+	return NB_OK;
+}
+
 int nb_download_cache(nb_context* ctx, nb_contact_cache* h, void* stream) {
 	u32 c[CNT__COUNT];
 	int r = get_counts(ctx, c, stream); if (r) return r;

@@ -57,8 +57,9 @@ def aligned_array(n, dtype, align=64):
     return _aligned(max(n, 1) * dtype.itemsize, align).view(dtype)[:n] if n else _aligned(dtype.itemsize, align).view(dtype)[:0]
 
 
-def load(fast=False):
-    path = os.path.join(HERE, "_ref", "libnudge_ref_fast.so" if fast else "libnudge_ref.so")
+def load(fast=False, gpu_dropin=False):
+    """gpu_dropin=True loads the same shim linked against nudge_b200's namespace-nudge drop-in instead of nudge.cpp."""
+    path = os.path.join(HERE, "_ref", "libnudge_gpu_shim.so" if gpu_dropin else ("libnudge_ref_fast.so" if fast else "libnudge_ref.so"))
     if not os.path.exists(path):
         raise FileNotFoundError(path + " missing: run `make -C oracle ref` in the build container")
     lib = C.CDLL(path)
@@ -83,11 +84,11 @@ def load(fast=False):
 class RefSim:
     """Runs the unmodified reference on a nudge_b200.scenes.Scene (must fit the reference's uint16 limits)."""
 
-    def __init__(self, scene, fast=False, ftz=False, contact_capacity=None, arena_mb=256):
+    def __init__(self, scene, fast=False, ftz=False, contact_capacity=None, arena_mb=256, gpu_dropin=False):
         from nudge_b200 import scenes as S
         assert scene.fits_reference(), "scene exceeds the reference's limits (nudge.cpp:3010, nudge.h:68-71)"
         self.S = S
-        self.lib = load(fast)
+        self.lib = load(fast, gpu_dropin)
         self.lib.ref_set_ftz_daz(1 if ftz else 0)
         self.scene = scene
         nb = scene.n_bodies

@@ -165,3 +165,35 @@ def test_full_size_64k_properties_and_one_step_parity():
     allb = np.concatenate([np.stack([batch, bodies["a"].astype(np.int64)], 1), np.stack([batch, bodies["b"].astype(np.int64)], 1)])
     allb = allb[allb[:, 1] != 0]
     assert len(np.unique(allb, axis=0)) == len(allb), "a batch holds two contacts of one body"
+
+
+def test_reference_own_test_program_on_the_gpu_dropin():
+    """The reference's tests/main.cpp, compiled UNMODIFIED against nudge.h and linked against nudge_b200's namespace-nudge drop-in
+    (oracle/_ref/ref_tests_on_gpu, built by oracle/Makefile), must print "All tests passed." — its six known-answer tests
+    (20k collide() calls: contact counts 4 / 8 / 3 / 1 / 2, tag algebra, tests/main.cpp:130-1002) on the CUDA path."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(G.HERE), "oracle", "_ref", "ref_tests_on_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_tests_on_gpu not built (needs /root/reference in the build container)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "All tests passed." in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_dropin_nudge_h_calls_equal_reference_on_a_trajectory():
+    """Same Python harness, same nudge.h calls (uint16 layout, host pointers): reference CPU library vs the GPU drop-in, bit for bit."""
+    from oracle import pyref
+    if not os.path.exists(os.path.join(os.path.dirname(G.HERE), "oracle", "_ref", "libnudge_gpu_shim.so")):
+        pytest.skip("oracle/_ref/libnudge_gpu_shim.so not built")
+    s = scenes.demo_scene(200, 200, iterations=8, spread=3.0, height=30.0)
+    r = pyref.RefSim(s); g = pyref.RefSim(s, gpu_dropin=True)
+    for k in range(30):
+        r.step_staged(); g.step_staged()
+        assert r.contacts.count == g.contacts.count and r.cache.count == g.cache.count, "step %d" % k
+        rv, gv = r.contacts_view(), g.contacts_view()
+        for key in ("data", "bodies", "tags", "sleeping", "active"):
+            assert np.array_equal(rv[key].view(np.uint8), gv[key].view(np.uint8)), "contacts.%s differs at step %d" % (key, k)
+        assert np.array_equal(r.transforms.view(np.uint8), g.transforms.view(np.uint8)), "transforms differ at step %d" % k
+        assert np.array_equal(r.momentum.view(np.uint8), g.momentum.view(np.uint8)), "momentum differs at step %d" % k
+        assert np.array_equal(r.idle, g.idle)
+        rc, gc = r.cache_view(), g.cache_view()
+        assert np.array_equal(rc["tags"], gc["tags"]) and np.array_equal(rc["data"].view(np.uint8), gc["data"].view(np.uint8)), "cache differs at step %d" % k
