@@ -77,8 +77,12 @@ def run_ours(args):
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    def staged_step(ev=None):
-        sim.collide(); sim.apply_gravity_damping(); sim.read_cached_impulses(); sim.setup_contact_constraints()
+    def staged_step(ev=None, st=None):
+        sim.collide()
+        if st: st[0].record()
+        sim.apply_gravity_damping(); sim.read_cached_impulses()
+        if st: st[1].record()
+        sim.setup_contact_constraints()
         if ev: ev[0].record()
         sim.apply_impulses(scene.iterations)
         if ev: ev[1].record()
@@ -88,7 +92,7 @@ def run_ours(args):
         staged_step()
     K = args.steps
     E = lambda: torch.cuda.Event(enable_timing=True)
-    step_ev = [(E(), E()) for _ in range(K)]; solve_ev = [(E(), E()) for _ in range(K)]
+    step_ev = [(E(), E()) for _ in range(K)]; solve_ev = [(E(), E()) for _ in range(K)]; stage_ev = [(E(), E()) for _ in range(K)]
     sampler = ClockSampler(local); sampler.start()
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
@@ -99,7 +103,7 @@ def run_ours(args):
     for k in range(K):
         flush.fill_(k & 255)                      # L2 flush between timed iterations (not part of the step time)
         step_ev[k][0].record()
-        staged_step(solve_ev[k])
+        staged_step(solve_ev[k], stage_ev[k])
         step_ev[k][1].record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
@@ -111,6 +115,11 @@ def run_ours(args):
     step_ms = [a.elapsed_time(b) for a, b in step_ev]
     solve_ms = [a.elapsed_time(b) for a, b in solve_ev]
     total_ms = float(sum(step_ms))
+    stage_ms = {"collide": float(np.mean([step_ev[k][0].elapsed_time(stage_ev[k][0]) for k in range(K)])),
+                "gravity+read_cached_impulses": float(np.mean([stage_ev[k][0].elapsed_time(stage_ev[k][1]) for k in range(K)])),
+                "setup_contact_constraints": float(np.mean([stage_ev[k][1].elapsed_time(solve_ev[k][0]) for k in range(K)])),
+                "apply_impulses": float(np.mean(solve_ms)),
+                "update+write_cache+advance": float(np.mean([solve_ev[k][1].elapsed_time(step_ev[k][1]) for k in range(K)]))}
     cnt = sim.counts()
 
     # ---- end to end through the public API with HOST buffers (pinned): upload state, step, read state back ----
@@ -171,7 +180,7 @@ def run_ours(args):
                    "l2": "flushed between timed steps (256 MiB write), flush excluded from step time", "timing": "CUDA events per step, summed; max over ranks"},
         "contacts_solved_per_s": contacts_all * sweeps * K / (total_ms * 1e-3),
         "wall_ms_per_step_incl_flush": wall * 1e3 / K,
-        "solver_share_of_step": float(sum(solve_ms)) / float(sum(step_ms)),
+        "solver_share_of_step": float(sum(solve_ms)) / float(sum(step_ms)), "stage_ms": stage_ms,
         "roofline": {"bound": "hbm", "kernel": "k_solve (8 sweeps per launch)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": solve_avg_ms,
                      "note": "latency bound: the reference's Gauss-Seidel order is a dependency chain per body; rows stay L2 resident"},

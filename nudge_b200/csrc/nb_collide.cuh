@@ -141,33 +141,125 @@ __global__ void __launch_bounds__(NB_BLOCK) k_build_level(const float4* cmin, co
 struct Tree { const float4* mn[NB_MAX_LEVELS]; const float4* mx[NB_MAX_LEVELS]; u32 n[NB_MAX_LEVELS]; int levels; };
 
 // ---------------- K5: all strictly overlapping AABB pairs (the set nudge.cpp:3275-3489 produces) ----------------
-// Each unordered pair is reported by exactly one side: the leaf with the smaller (volume, position).  Subtrees
-// whose largest leaf volume is below the query's are skipped, so a giant collider (the ground) costs nothing.
+// Each unordered pair is reported by exactly one side: the leaf with the smaller (volume, position).  Subtrees whose
+// largest leaf volume is below every member's are skipped, so a giant collider (the ground) costs nothing.
+// Warp-cooperative: a warp owns 32 Morton-adjacent leaves ("members", staged in shared memory) and walks the tree once with
+// a warp-uniform stack.  One step expands a node: lane = (child c = lane & 7, member subset lane >> 3), every lane loads its
+// child's box (one coalesced 256-byte read for the 8 children) and tests it against its 8 members, so the walk pays one
+// dependent memory round trip per NODE instead of per child.  Hits are staged in shared memory and flushed 32 at a time.
+struct PairStage { float lo[3][32]; float hi[3][32]; float vol[32]; u32 orig[32]; u64 buf[32 + 256]; };  // one block of 8 leaves can yield 8 x 32 pairs
+
 __global__ void __launch_bounds__(NB_BLOCK) k_find_pairs(Tree T, u32 K, const u32* order, u32 kbits, u64* pair_keys, u32 max_pairs, u32* counts) {
-	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < K; p += gridDim.x * blockDim.x) {
-		float4 qlo = T.mn[0][p], qhi = T.mx[0][p];
-		float qvol = qhi.w;
-		u32 idx[NB_MAX_LEVELS], end[NB_MAX_LEVELS];
-		int top = T.levels - 1, level = top;
-		idx[top] = 0; end[top] = T.n[top];
+	__shared__ PairStage stage[NB_WARPS];
+	const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	PairStage& S = stage[wid];
+	const u32 c = lane & 7, sub = lane >> 3;
+	const u32 warps_total = gridDim.x * NB_WARPS;
+	const u32 groups = (K + 31) / 32;
+	const int top = T.levels - 1;
+	for (u32 g = blockIdx.x * NB_WARPS + wid; g < groups; g += warps_total) {
+		{
+			const u32 p = g * 32 + lane;
+			float4 qlo = make_float4(INFINITY, INFINITY, INFINITY, 0.0f), qhi = make_float4(-INFINITY, -INFINITY, -INFINITY, INFINITY);  // padding: overlaps nothing, prunes everything
+			u32 o = 0;
+			if (p < K) { qlo = T.mn[0][p]; qhi = T.mx[0][p]; o = order[p]; }
+			S.lo[0][lane] = qlo.x; S.lo[1][lane] = qlo.y; S.lo[2][lane] = qlo.z;
+			S.hi[0][lane] = qhi.x; S.hi[1][lane] = qhi.y; S.hi[2][lane] = qhi.z;
+			S.vol[lane] = qhi.w; S.orig[lane] = o;
+		}
+		__syncwarp();
+		u32 cnt = 0;
+		// warp-uniform stack: per level the node whose children are being visited and the mask of children still to expand
+		u32 parent[NB_MAX_LEVELS], todo[NB_MAX_LEVELS];
+		int level = top;  // "level" = level of the children being tested
+		parent[top] = 0; todo[top] = 0;
+		bool first = true;
 		while (true) {
-			if (idx[level] == end[level]) { if (++level > top) break; continue; }
-			u32 node = idx[level]++;
-			float4 lo = T.mn[level][node], hi = T.mx[level][node];
-			// strict interval overlap on three axes: nudge.cpp:3306-3310 / 3386-3390
-			bool hit = hi.x > qlo.x && qhi.x > lo.x && hi.y > qlo.y && qhi.y > lo.y && hi.z > qlo.z && qhi.z > lo.z;
-			if (!hit) continue;
-			if (level) {
-				if (hi.w < qvol) continue;
-				--level; idx[level] = node * 8; end[level] = min(node * 8 + 8, T.n[level]);
+			u32 base_child, nchild;
+			if (first) { base_child = 0; nchild = T.n[top]; first = false; }  // the top level has at most 8 nodes: treat it as one child block
+			else {
+				// next node to expand: lowest set bit of todo at the current level, else pop
+				while (level <= top && todo[level] == 0) ++level;
+				if (level > top) break;
+				u32 bit = __ffs(todo[level]) - 1;
+				todo[level] &= todo[level] - 1;
+				u32 node = parent[level] * 8 + bit;  // a node of `level`; its children live one level down
+				--level;
+				parent[level] = node; todo[level] = 0;
+				base_child = node * 8; nchild = min(8u, T.n[level] - base_child);
 			}
-			else if (node != p && (hi.w > qvol || (hi.w == qvol && node > p))) {
-				u32 slot = warp_append_slot(&counts[CNT_PAIRS]);
-				u32 a = min(p, node), b = max(p, node);  // Morton positions: a earlier, b later
-				if (slot < max_pairs) pair_keys[slot] = ((u64)order[a] << kbits) | (u64)order[b];  // hi = earlier, lo = later (nudge.cpp:3495)
+			// ---- test the children of this block against all 32 members ----
+			const u32 child = base_child + c;
+			const bool cvalid = c < nchild;
+			float4 lo = make_float4(0, 0, 0, 0), hi = lo;
+			if (cvalid) { lo = T.mn[level][child]; hi = T.mx[level][child]; }
+			u32 hits = 0;  // bit k: member sub*8+k hits this child
+			#pragma unroll
+			for (u32 k = 0; k < 8; ++k) {
+				const u32 mbr = sub * 8 + k;
+				// strict interval overlap on three axes: nudge.cpp:3306-3310 / 3386-3390
+				bool hit = cvalid && hi.x > S.lo[0][mbr] && S.hi[0][mbr] > lo.x && hi.y > S.lo[1][mbr] && S.hi[1][mbr] > lo.y && hi.z > S.lo[2][mbr] && S.hi[2][mbr] > lo.z;
+				const float qvol = S.vol[mbr];
+				if (level) hit = hit && !(hi.w < qvol);
+				else { const u32 p = g * 32 + mbr; hit = hit && child != p && (hi.w > qvol || (hi.w == qvol && child > p)); }
+				hits |= (hit ? 1u : 0u) << k;
+			}
+			if (level) {
+				const u32 m = __ballot_sync(0xffffffffu, hits != 0);
+				todo[level] = (m | (m >> 8) | (m >> 16) | (m >> 24)) & 0xffu;  // child accepted if any member subset wants it
+				if (level == top) parent[level] = 0;
+			}
+			else {
+				// leaves: every set bit of `hits` is a pair (member sub*8+k, leaf child)
+				const u32 mine = __popc(hits);
+				u32 incl = mine;
+				#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (u32)d) incl += t; }
+				const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+				if (total) {
+					u32 at = cnt + incl - mine;
+					if (hits) {
+						const u32 on = order[child];
+						u32 h = hits;
+						while (h) {
+							const u32 k = __ffs(h) - 1; h &= h - 1;
+							const u32 mbr = sub * 8 + k, p = g * 32 + mbr;
+							const u32 po = S.orig[mbr];
+							// Morton positions: the earlier one goes to the high half, the later one to the low half (nudge.cpp:3495)
+							S.buf[at++] = p < child ? (((u64)po << kbits) | on) : (((u64)on << kbits) | po);
+						}
+					}
+					cnt += total;  // at most 31 + 256
+					__syncwarp();
+					const u32 full = cnt & ~31u;
+					for (u32 off = 0; off < full; off += 32) {
+						u32 base = 0;
+						if (lane == 0) base = atomicAdd(&counts[CNT_PAIRS], 32u);
+						base = __shfl_sync(0xffffffffu, base, 0);
+						if (base + lane < max_pairs) pair_keys[base + lane] = S.buf[off + lane];
+						else atomicOr(&counts[CNT_OVERFLOW], OVF_PAIRS);
+					}
+					if (full) {
+						const u64 rest = S.buf[full + lane];  // only the first cnt - full entries are meaningful
+						__syncwarp();
+						S.buf[lane] = rest;
+						cnt -= full;
+						__syncwarp();
+					}
+				}
+				++level;  // back to the level whose todo mask we were consuming
+			}
+		}
+		if (cnt) {
+			u32 base = 0;
+			if (lane == 0) base = atomicAdd(&counts[CNT_PAIRS], cnt);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (lane < cnt) {
+				if (base + lane < max_pairs) pair_keys[base + lane] = S.buf[lane];
 				else atomicOr(&counts[CNT_OVERFLOW], OVF_PAIRS);
 			}
 		}
+		__syncwarp();
 	}
 }
 

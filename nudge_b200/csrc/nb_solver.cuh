@@ -258,17 +258,30 @@ __global__ void __launch_bounds__(32) k_schedule(const u32* sorted, const uint2*
 		const u32 steps = min(32u, (n - base + 15) / 16);
 		u32 s = 0;
 		while (s < steps) {
-			// ---- speculative group: the contacts that would fill list position 0 ----
-			u32 src = s + cidx - f0;                         // chunk index of the contact this lane would hold (lanes 0..15)
-			bool isnew = lane < 16 && cidx >= f0 && src < steps;
+			// ---- speculative groups: the contacts that would fill list position 0 (lanes 0-15); when the list is empty the
+			// upper half-warp speculates on the following eight as well ----
+			const bool fresh = vcount == 0;  // implies f0 == 0
+			u32 src = s + cidx - f0 + (half ? 8u : 0u);      // chunk index of the contact this lane would hold
+			bool isnew = (half ? fresh : cidx >= f0) && src < steps;
 			u32 va = __shfl_sync(0xffffffffu, my_ca, src & 31), vb = __shfl_sync(0xffffffffu, my_cb, src & 31);
 			u32 cand = ent < 8 ? va : vb;
-			u32 merged = isnew ? cand : ((lane < 16 && cidx < f0) ? reg[0] : 0xffffff00u + lane);  // unique dummies never match
-			u32 peers = __match_any_sync(0xffffffffu, merged);
-			u32 low = (1u << cidx) - 1u;
-			bool confl = isnew && (peers & (low | (low << 8))) != 0;  // equal to an entry of an EARLIER contact (its own a/b partner is allowed)
+			u32 merged = isnew ? cand : ((!half && cidx < f0) ? reg[0] : 0xffffff00u + lane);  // unique dummies never match
+			u32 peers = __match_any_sync(0xffffffffu, merged) & (half ? 0xffff0000u : 0x0000ffffu);
+			u32 low = ((1u << cidx) - 1u) * 0x101u << (half ? 16 : 0);
+			bool confl = isnew && (peers & low) != 0;  // equal to an entry of an EARLIER contact of its group (its own a/b partner is allowed)
 			u32 cbal = __ballot_sync(0xffffffffu, confl);
+			u32 vbal = __ballot_sync(0xffffffffu, isnew);
 			u32 cm = (cbal | (cbal >> 8)) & 0xffu;
+			if (fresh && cm == 0 && (vbal & 0xffu) == 0xffu) {
+				// the first eight contacts are conflict free: a whole slot, emitted at once; same for the second eight if clean
+				bool two = ((cbal >> 16) == 0) && (((vbal >> 16) & 0xffu) == 0xffu);
+				u32 uid = next_uid + half;
+				if ((!half || two) && ent < 8) slot_of[base + 16 * src] = (uid << 3) | cidx;
+				if ((!half || two) && ent == 7) { u32 il = base + 16 * src; done[uid] = il; complete_flag[il] = 1; }
+				next_uid += two ? 2 : 1;
+				s += two ? 16 : 8;
+				continue;
+			}
 			u32 avail = min(8u - f0, steps - s);
 			u32 k = cm ? (u32)(__ffs(cm) - 1) : f0 + avail;   // first conflicting lane of position 0, or one past the last candidate
 			if (k > f0) {
@@ -276,7 +289,7 @@ __global__ void __launch_bounds__(32) k_schedule(const u32* sorted, const uint2*
 					uid0 = next_uid++; vcount = 1;
 					if (lane == 0) { S_uid[0] = uid0; done[uid0] = NB_NONE; }
 				}
-				bool take = isnew && cidx < k;
+				bool take = !half && isnew && cidx < k;
 				if (take) reg[0] = cand;
 				if (take && ent < 8) slot_of[base + 16 * src] = (uid0 << 3) | cidx;
 				s += k - f0; f0 = k;
@@ -627,10 +640,9 @@ __global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impuls
 			}
 			while (__any_sync(0xffffffffu, pending)) {
 				if (pending) {
-					float4 al = ld128(mw + 2*a);
-					if (!a || asu(al.w) == exp_a) {
-						float4 aw = ld128(mw + 2*a + 1), bl = ld128(mw + 2*b), bw = ld128(mw + 2*b + 1);
-						bool ready = (!a || asu(aw.w) == exp_a) && (!b || (asu(bl.w) == exp_b && asu(bw.w) == exp_b));
+					float4 al = ld128(mw + 2*a), aw = ld128(mw + 2*a + 1), bl = ld128(mw + 2*b), bw = ld128(mw + 2*b + 1);  // one round trip
+					{
+						bool ready = (!a || (asu(al.w) == exp_a && asu(aw.w) == exp_a)) && (!b || (asu(bl.w) == exp_b && asu(bw.w) == exp_b));
 						if (ready) {
 							if (mode) solve_contact(R, slot, al, aw, bl, bw, s_rcp, s_rsqrt);
 							else warm_start_contact(R, slot, impulses, al, aw, bl, bw, s_rsqrt);
