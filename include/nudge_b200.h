@@ -95,6 +95,11 @@ int nb_upload_transforms(nb_context*, const nb_transform* host, uint32_t count, 
 int nb_download_momentum(nb_context*, nb_body_momentum* host, uint32_t count, void* stream);
 int nb_download_transforms(nb_context*, nb_transform* host, uint32_t count, void* stream);
 
+/* Ghost exchange of a scene sharded across GPUs: gather momentum rows of `dev_indices` into a contiguous DEVICE buffer (n x 32 B), and
+ * scatter rows `dev_sources[i]` of a DEVICE buffer into body `dev_indices[i]`.  The buffer in between travels through one ncclAllGather. */
+int nb_pack_momentum(nb_context*, const uint32_t* dev_indices, uint32_t n, void* dev_out, void* stream);
+int nb_unpack_momentum(nb_context*, const uint32_t* dev_indices, const uint32_t* dev_sources, uint32_t n, const void* dev_in, void* stream);
+
 /* The simulation step, device resident.  Same order of calls as example/main.cpp:274-328. */
 int nb_collide(nb_context*, void* stream);
 int nb_apply_gravity_damping(nb_context*, float time_step, float gravity, float damping, void* stream);

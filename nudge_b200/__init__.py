@@ -16,7 +16,7 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_upload_contacts", "nb_download_bodies", "nb_download_contacts", "nb_download_cache", "nb_download_counts", "nb_upload_momentum", "nb_upload_transforms",
            "nb_download_momentum", "nb_download_transforms", "nb_collide", "nb_apply_gravity_damping", "nb_read_cached_impulses",
            "nb_setup_contact_constraints", "nb_apply_impulses", "nb_update_cached_impulses", "nb_write_cached_impulses", "nb_advance", "nb_step",
-           "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact", "nb_debug_sort", "nb_debug_scan", "nb_debug_enable"]
+           "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact", "nb_debug_sort", "nb_debug_scan", "nb_debug_enable", "nb_pack_momentum", "nb_unpack_momentum"]
 
 
 class Config(C.Structure):
@@ -61,6 +61,8 @@ def load_library():
         lib.nb_debug_sort.argtypes = [V, V, V, C.c_uint32, C.c_int, C.c_int]
         lib.nb_debug_scan.argtypes = [V, V, C.c_uint32, V]
         lib.nb_debug_enable.argtypes = [V, C.c_int]
+        lib.nb_pack_momentum.argtypes = [V, V, C.c_uint32, V, V]
+        lib.nb_unpack_momentum.argtypes = [V, V, V, C.c_uint32, V, V]
         _lib = lib
     return _lib
 
@@ -75,12 +77,14 @@ class Sim(abi.HostState):
     Host arrays (self.transforms, self.momentum, ...) are the caller-owned copies; `upload()` / `download_bodies()`
     move them across.  `stream` is a raw cudaStream_t (0 = default stream)."""
 
-    def __init__(self, scene, contact_capacity=None, pair_capacity=None, device=0, stream=0, debug=False):
-        super().__init__(scene, contact_capacity)
+    def __init__(self, scene, contact_capacity=None, pair_capacity=None, device=0, stream=0, debug=False, max_bodies=None, max_boxes=None, max_spheres=None):
+        """max_* reserve room for scenes loaded later with reload() (a sharded scene changes size when it is re-partitioned)."""
+        mb, mx, ms = max(scene.n_bodies, max_bodies or 0), max(scene.n_boxes, max_boxes or 0), max(scene.n_spheres, max_spheres or 0)
+        super().__init__(scene, contact_capacity or max(1024, 24 * mb))
         self.lib = load_library()
         self.stream = C.c_void_p(stream)
-        cfg = Config(scene.n_bodies, scene.n_boxes, scene.n_spheres, max(1, len(scene.connections)),
-                     pair_capacity or max(4096, 16 * scene.n_colliders), self.cap, device)
+        cfg = Config(mb, mx, ms, max(1, len(scene.connections)),
+                     pair_capacity or max(4096, 16 * (mx + ms)), self.cap, device)
         self.ctx = C.c_void_p()
         r = self.lib.nb_create(C.byref(cfg), C.byref(self.ctx))
         if r != 0:
@@ -104,6 +108,20 @@ class Sim(abi.HostState):
     def _ck(self, r, what):
         if r != 0:
             raise NudgeError("%s: %s (%d)" % (what, self.lib.nb_last_error(self.ctx).decode(), r))
+
+    def reload(self, scene):
+        """Replaces the scene (bodies and colliders) inside the same device context; the contact cache in HBM is kept (it is keyed by collider tags)."""
+        cap = self.cap
+        abi.HostState.__init__(self, scene, cap)
+        self._ck(self.lib.nb_upload_bodies(self.ctx, C.byref(self.bodies), self.stream), "nb_upload_bodies")
+        self._ck(self.lib.nb_upload_colliders(self.ctx, C.byref(self.colliders), self.stream), "nb_upload_colliders")
+        self._ck(self.lib.nb_upload_connections(self.ctx, C.byref(self.conn), self.stream), "nb_upload_connections")
+
+    def pack_momentum(self, dev_indices_ptr, n, dev_out_ptr):
+        self._ck(self.lib.nb_pack_momentum(self.ctx, C.c_void_p(dev_indices_ptr), int(n), C.c_void_p(dev_out_ptr), self.stream), "nb_pack_momentum")
+
+    def unpack_momentum(self, dev_indices_ptr, dev_sources_ptr, n, dev_in_ptr):
+        self._ck(self.lib.nb_unpack_momentum(self.ctx, C.c_void_p(dev_indices_ptr), C.c_void_p(dev_sources_ptr), int(n), C.c_void_p(dev_in_ptr), self.stream), "nb_unpack_momentum")
 
     # ---- host <-> HBM ----
     def upload(self):

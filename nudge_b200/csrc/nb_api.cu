@@ -92,7 +92,30 @@ __global__ void __launch_bounds__(NB_BLOCK) k_debug_rcp(const float* x, float* y
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = rsq ? nb_rsqrt(x[i]) : nb_rcp(x[i]);
 }
 
+// Ghost exchange for a scene sharded across GPUs: gather / scatter whole 32-byte BodyMomentum rows.
+__global__ void __launch_bounds__(NB_BLOCK) k_pack_rows(const float4* rows, const u32* idx, u32 n, float4* out) {
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += gridDim.x * blockDim.x) out[i] = rows[2 * idx[i >> 1] + (i & 1)];
+}
+__global__ void __launch_bounds__(NB_BLOCK) k_unpack_rows(float4* rows, const u32* idx, const u32* src, u32 n, const float4* in) {
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += gridDim.x * blockDim.x) rows[2 * idx[i >> 1] + (i & 1)] = in[2 * src[i >> 1] + (i & 1)];
+}
+
 extern "C" {
+
+int nb_pack_momentum(nb_context* ctx, const uint32_t* dev_indices, uint32_t n, void* dev_out, void* stream) {
+	if (!n) return NB_OK;
+	k_pack_rows<<<GRID(2 * n), NB_BLOCK, 0, (cudaStream_t)stream>>>((const float4*)ctx->mom, dev_indices, n, (float4*)dev_out);
+	++ctx->launches;
+	CK(cudaGetLastError());
+	return NB_OK;
+}
+int nb_unpack_momentum(nb_context* ctx, const uint32_t* dev_indices, const uint32_t* dev_sources, uint32_t n, const void* dev_in, void* stream) {
+	if (!n) return NB_OK;
+	k_unpack_rows<<<GRID(2 * n), NB_BLOCK, 0, (cudaStream_t)stream>>>((float4*)ctx->mom, dev_indices, dev_sources, n, (const float4*)dev_in);
+	++ctx->launches;
+	CK(cudaGetLastError());
+	return NB_OK;
+}
 
 int nb_create(const nb_config* config, nb_context** out) {
 	if (!config || !out) return NB_ERR_ARGUMENT;

@@ -197,3 +197,37 @@ def test_dropin_nudge_h_calls_equal_reference_on_a_trajectory():
         assert np.array_equal(r.idle, g.idle)
         rc, gc = r.cache_view(), g.cache_view()
         assert np.array_equal(rc["tags"], gc["tags"]) and np.array_equal(rc["data"].view(np.uint8), gc["data"].view(np.uint8)), "cache differs at step %d" % k
+
+
+def test_pack_unpack_momentum_kernels():
+    import torch
+    s = scenes.box_drop(2000, iterations=4)
+    g = nudge_b200.Sim(s)
+    rng = np.random.default_rng(3)
+    g.momentum["velocity"][:] = rng.normal(size=(s.n_bodies, 3)); g.momentum["angular_velocity"][:] = rng.normal(size=(s.n_bodies, 3))
+    g.upload_bodies()
+    idx = torch.from_numpy(rng.permutation(s.n_bodies)[:500].astype(np.int32)).cuda()
+    out = torch.zeros((500, 8), dtype=torch.float32, device="cuda")
+    g.pack_momentum(idx.data_ptr(), 500, out.data_ptr())
+    torch.cuda.synchronize()
+    rows = g.momentum.view(np.float32).reshape(-1, 8)
+    assert np.array_equal(out.cpu().numpy(), rows[idx.cpu().numpy()])
+    # scatter rows src[i] of a buffer into bodies dst[i]
+    dst = torch.from_numpy(np.arange(100, 600, dtype=np.int32)).cuda()
+    src = torch.from_numpy(rng.integers(0, 500, 500).astype(np.int32)).cuda()
+    g.unpack_momentum(dst.data_ptr(), src.data_ptr(), 500, out.data_ptr())
+    g.download_bodies()
+    want = rows.copy(); want[100:600] = out.cpu().numpy()[src.cpu().numpy()]
+    assert np.array_equal(g.momentum.view(np.float32).reshape(-1, 8), want)
+
+
+def test_sharded_scene_two_ranks_gpu_equals_oracle_ranks():
+    """world_size 2 over gloo, both ranks on cuda:0: the sharded algorithm is a deterministic function of the partition, so the CUDA
+    ranks must reproduce the oracle ranks bit for bit (ghost exchange after the warm start and after every sweep, two re-partitions)."""
+    from tests import shard_util
+    a = shard_util.run_ranks(2, "gpu", steps=12, reshard_every=5, n_boxes=600)
+    b = shard_util.run_ranks(2, "oracle", steps=12, reshard_every=5, n_boxes=600)
+    for r in range(2):
+        assert np.array_equal(a[r]["transforms"].view(np.uint8), b[r]["transforms"].view(np.uint8))
+        assert np.array_equal(a[r]["momentum"]["velocity"], b[r]["momentum"]["velocity"])
+        assert np.array_equal(a[r]["counts"], b[r]["counts"])
