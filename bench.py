@@ -7,6 +7,7 @@
 Workload (BASELINE.json configs[1]): 65,536 random boxes dropped onto a ground plane, 8 solver iterations, measured on the
 settled pile.  One "step" = one sub-step of example/main.cpp:274-328.  Prints ONE JSON line (see README / DESIGN.md §5)."""
 import argparse, json, os, subprocess, sys, threading, time
+os.environ["NCCL_DEBUG"] = "WARN"  # NCCL otherwise prints its version banner on stdout, which must carry exactly one JSON line
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
