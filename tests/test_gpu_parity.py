@@ -231,3 +231,60 @@ def test_sharded_scene_two_ranks_gpu_equals_oracle_ranks():
         assert np.array_equal(a[r]["transforms"].view(np.uint8), b[r]["transforms"].view(np.uint8))
         assert np.array_equal(a[r]["momentum"]["velocity"], b[r]["momentum"]["velocity"])
         assert np.array_equal(a[r]["counts"], b[r]["counts"])
+
+
+def test_body_connections_join_islands():
+    """BodyConnections only feed the island passes (nudge.cpp:3511-3575, 3799-3863): a sleeping body connected to an awake one stays active."""
+    s = scenes.demo_scene(60, 0, iterations=4, spread=40.0, height=2.0, seed=9)   # far apart: no contacts between boxes
+    rng = np.random.default_rng(1)
+    pairs = rng.integers(1, s.n_bodies, (25, 2))
+    s.connections = np.zeros(len(pairs), scenes.PAIR32); s.connections["a"] = pairs[:, 0]; s.connections["b"] = pairs[:, 1]
+    s.idle[:] = 0xff
+    s.idle[pairs[:5, 0]] = 0     # a few awake bodies keep their connected partners active
+    o, g = _pair(s)
+    _steps(o, g, 3)
+    assert 0 < g.active.count < s.n_bodies - 1
+
+
+def test_config2_mixed_box_sphere_stack():
+    """BASELINE configs[2] shape (50/50 box/sphere lattice stack, 16 iterations) at 20k bodies: settle on the GPU, then one step bit-exact vs the oracle."""
+    s = scenes.mixed_stack(20000, iterations=16)
+    o, g = _pair(s)
+    for _ in range(150):
+        g.step()
+    assert g.counts().overflow == 0
+    sync_oracle_from_gpu(o, g)
+    _steps(o, g, 1)
+
+
+def test_config4_brick_wall():
+    """BASELINE configs[4] shape (running-bond wall of identical bricks: equal volumes, many 8-point manifolds, 20 iterations) at 20k bricks."""
+    s = scenes.brick_wall(20000, iterations=20)
+    o, g = _pair(s)
+    for _ in range(60):
+        g.step()
+    assert g.counts().overflow == 0
+    sync_oracle_from_gpu(o, g)
+    _steps(o, g, 1)
+
+
+def test_config3_one_million_boxes_runs_and_keeps_invariants():
+    """BASELINE configs[3] size on ONE GPU: 1,048,576 boxes.  Too large for the CPU oracle in a test; checks capacity, that the pair list is
+    sorted/unique, that every contact's bodies are a broadphase pair, and that nothing falls through the ground."""
+    s = scenes.box_drop(1 << 20, iterations=8)
+    g = nudge_b200.Sim(s, debug=True)
+    for _ in range(40):
+        g.step()
+    c = g.counts()
+    assert c.overflow == 0 and c.active == s.n_bodies - 1
+    g.collide(); g.download_contacts()
+    p = g.pairs_view()
+    key = (p["hi"].astype(np.uint64) << np.uint64(32)) | p["lo"].astype(np.uint64)
+    assert (np.diff(key.astype(np.int64)) > 0).all()
+    n = g.contacts.count
+    b = g.contact_bodies[:n]
+    pk = np.minimum(b["a"], b["b"]).astype(np.uint64) << np.uint64(32) | np.maximum(b["a"], b["b"]).astype(np.uint64)
+    allp = np.minimum(p["hi"], p["lo"]).astype(np.uint64) << np.uint64(32) | np.maximum(p["hi"], p["lo"]).astype(np.uint64)   # collider k sits on body k here
+    assert np.isin(pk, allp).all()
+    g.download_bodies()
+    assert np.isfinite(g.transforms["position"]).all() and g.transforms["position"][1:, 1].min() > -1.0
