@@ -26,6 +26,7 @@ struct nb_context {
 	u32 cstride;   // row plane stride
 	u32 slots_per_bucket;
 	int coop_blocks_solve;
+	u32 solve_backoff_ns;
 
 	// scene
 	nb_transform* xf; nb_body_properties* props; nb_body_momentum* mom; uint8_t* idle;
@@ -51,7 +52,7 @@ struct nb_context {
 	u32* sorted; float4* impulses;
 	// setup / solve
 	float4* inertia;
-	u32* slot_of; u32* slot_done; u32* slot_left; u32* left_count; u32* batch_of; u32* slot_idx; float4* mw;
+	u32* slot_of; u32* slot_done; u32* slot_left; u32* left_count; u32* batch_of; u32* slot_idx; float4* mw; uint2* cab; uint8_t* back;
 	Rows rows;
 };
 
@@ -167,7 +168,7 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ALLOC(ctx->sorted, C); ALLOC(ctx->impulses, C);
 	ALLOC(ctx->inertia, 2 * (size_t)B);
 	ALLOC(ctx->slot_of, C); ALLOC(ctx->slot_done, 16 * (size_t)ctx->slots_per_bucket); ALLOC(ctx->slot_left, 16 * (size_t)ctx->slots_per_bucket);
-	ALLOC(ctx->left_count, 16); ALLOC(ctx->batch_of, C); ALLOC(ctx->slot_idx, C); ALLOC(ctx->mw, 2 * (size_t)B);
+	ALLOC(ctx->left_count, 16); ALLOC(ctx->batch_of, C); ALLOC(ctx->slot_idx, C); ALLOC(ctx->mw, 2 * (size_t)B); ALLOC(ctx->cab, C); ALLOC(ctx->back, C);
 	ALLOC(ctx->rows.plane, (size_t)ROW_PLANES_TOTAL * ctx->cstride); ALLOC(ctx->rows.state, 3 * (size_t)ctx->cstride);
 	ALLOC(ctx->rows.a, ctx->cstride); ALLOC(ctx->rows.b, ctx->cstride); ALLOC(ctx->rows.contact, ctx->cstride); ALLOC(ctx->rows.wait, 2 * (size_t)ctx->cstride);
 	ctx->rows.stride = ctx->cstride;
@@ -187,6 +188,8 @@ int nb_create(const nb_config* config, nb_context** out) {
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, NB_BLOCK, 0));
 	if (per_sm < 1) { ctx->error = "k_solve does not fit on an SM"; return NB_ERR_CUDA; }
 	if (const char* e = getenv("NB_SOLVE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
+	ctx->solve_backoff_ns = 0;
+	if (const char* e = getenv("NB_SOLVE_BACKOFF_NS")) ctx->solve_backoff_ns = (u32)atoi(e);
 	ctx->coop_blocks_solve = ctx->sms * per_sm;  // all co-resident: the dataflow solver relies on it
 	CK(cudaDeviceSynchronize());
 	return NB_OK;
@@ -442,7 +445,8 @@ static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) 
 	u32* counts = ctx->counts;
 	const u32 B = ctx->B;
 	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw);
-	void* args[] = { &R, &impulses, &mw, &mode, &sweeps, &counts };
+	u32 backoff = ctx->solve_backoff_ns;
+	void* args[] = { &R, &impulses, &mw, &mode, &sweeps, &backoff, &counts };
 	CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
 	k_mw_out<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw, mode);
 	ctx->launches += 3;
@@ -455,9 +459,10 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 	u32* counts = ctx->counts;
 	const u32 C = ctx->cfg.max_contacts, S = ctx->stride, B = ctx->B;
 	k_inertia<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->xf, ctx->props, ctx->inertia, ctx->mom);
-	k_schedule<<<16, 32, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,
+	k_sched_prep<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->cab, ctx->back, counts);
+	k_schedule<<<16, 32, 0, st>>>(ctx->cab, ctx->back, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,
 		ctx->flags, ctx->left_count, counts);
-	ctx->launches += 2;
+	ctx->launches += 3;
 	nb_scan<1>(L, ctx->flags, ctx->offs, S, counts + CNT_CONTACTS, 0, ctx->block_sums, counts + CNT_FULL_BATCHES);
 	CK(cudaMemsetAsync(ctx->rows.contact, 0xff, sizeof(u32) * ctx->cstride, st));
 	k_batch_index<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,

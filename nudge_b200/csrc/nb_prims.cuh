@@ -159,13 +159,13 @@ __global__ void __launch_bounds__(NB_BLOCK) k_sort_hist(const u64* keys, const u
 
 template<bool HAS_VALS>
 __global__ void __launch_bounds__(NB_BLOCK) k_sort_scatter(const u64* keys_in, u64* keys_out, const u32* vals_in, u32* vals_out,
-															const u32* n_ptr, u32 shift, const u32* hist_scanned) {
+															const u32* n_ptr, u32 shift, const u32* hist_scanned, const u32* digit_base) {
 	__shared__ u32 running[256];
 	__shared__ u32 chunk_base[256];
 	__shared__ u32 wc[NB_WARPS][256];
 	u32 n = *n_ptr;
 	u32 begin, end; sort_tile_range(n, begin, end);
-	running[threadIdx.x] = hist_scanned[threadIdx.x * NB_SORT_GRID + blockIdx.x];
+	running[threadIdx.x] = digit_base[threadIdx.x] + hist_scanned[threadIdx.x * NB_SORT_GRID + blockIdx.x];
 	u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	for (u32 base = begin; base < end; base += NB_BLOCK) {
 		u32 i = base + threadIdx.x;
@@ -198,21 +198,41 @@ __global__ void __launch_bounds__(NB_BLOCK) k_sort_scatter(const u64* keys_in, u
 	}
 }
 
-// in-place exclusive scan of n <= 1024*64 words by one block: each thread owns a contiguous run
-__global__ void __launch_bounds__(1024) k_scan_single(u32* data, u32 n) {
+// Turns the block histogram hist[digit][block] into scatter offsets in ONE launch: block d scans row d in place (exclusive over
+// the sort blocks) and publishes the digit total; the last block to finish (completion counter) prefixes the 256 totals into
+// digit_base[].  A key's final position is digit_base[d] + hist[d][block] + its rank inside the block.
+__global__ void __launch_bounds__(1024) k_sort_offsets(u32* hist /*[256][NB_SORT_GRID]*/, u32* digit_base /*[256] + [256] totals + [1] counter*/) {
 	__shared__ u32 sm[33];
-	u32 per = (n + 1023) / 1024;
-	u32 begin = min(n, threadIdx.x * per), end = min(n, begin + per);
-	u32 sum = 0;
-	for (u32 i = begin; i < end; ++i) sum += data[i];
+	__shared__ bool last;
+	const u32 d = blockIdx.x;
+	u32* totals = digit_base + 256;
+	u32* counter = digit_base + 512;
+	u32 v = threadIdx.x < NB_SORT_GRID ? hist[d * NB_SORT_GRID + threadIdx.x] : 0;
 	u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	u32 incl = warp_incl_scan(sum);
+	u32 incl = warp_incl_scan(v);
 	if (lane == 31) sm[wid] = incl;
 	__syncthreads();
-	if (wid == 0) { u32 w = sm[lane]; u32 wi = warp_incl_scan(w); sm[lane] = wi - w; }
+	if (wid == 0) { u32 w = sm[lane]; u32 wi = warp_incl_scan(w); sm[lane] = wi - w; if (lane == 31) sm[32] = wi; }
 	__syncthreads();
-	u32 run = incl - sum + sm[wid];
-	for (u32 i = begin; i < end; ++i) { u32 v = data[i]; data[i] = run; run += v; }
+	if (threadIdx.x < NB_SORT_GRID) hist[d * NB_SORT_GRID + threadIdx.x] = incl - v + sm[wid];
+	if (threadIdx.x == 0) {
+		totals[d] = sm[32];
+		__threadfence();
+		last = atomicAdd(counter, 1u) == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (last) {
+		__threadfence();
+		u32 t = threadIdx.x < 256 ? ((volatile u32*)totals)[threadIdx.x] : 0;
+		u32 inc2 = warp_incl_scan(t);
+		__syncthreads();
+		if (lane == 31) sm[wid] = inc2;
+		__syncthreads();
+		if (wid == 0) { u32 w = sm[lane]; u32 wi = warp_incl_scan(w); sm[lane] = wi - w; }
+		__syncthreads();
+		if (threadIdx.x < 256) digit_base[threadIdx.x] = inc2 - t + sm[wid];
+		if (threadIdx.x == 0) *counter = 0;  // ready for the next pass
+	}
 }
 
 struct SortBuffers { u64* keys[2]; u32* vals[2]; u32* hist; u32* block_sums; };
@@ -222,10 +242,10 @@ static int nb_radix_sort(const Launch& L, const SortBuffers& B, const u32* n_ptr
 	for (int shift = begin_bit; shift < end_bit; shift += 8) {
 		k_sort_hist<<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], n_ptr, (u32)shift, B.hist);
 		*L.counter += 1;
-		nb_scan<1>(L, B.hist, B.hist, 0, nullptr, 256u * NB_SORT_GRID, B.block_sums, nullptr);
-		if (has_vals) k_sort_scatter<true><<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], B.keys[cur ^ 1], B.vals[cur], B.vals[cur ^ 1], n_ptr, (u32)shift, B.hist);
-		else k_sort_scatter<false><<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], B.keys[cur ^ 1], nullptr, nullptr, n_ptr, (u32)shift, B.hist);
-		*L.counter += 1;
+		k_sort_offsets<<<256, 1024, 0, L.stream>>>(B.hist, B.block_sums);
+		if (has_vals) k_sort_scatter<true><<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], B.keys[cur ^ 1], B.vals[cur], B.vals[cur ^ 1], n_ptr, (u32)shift, B.hist, B.block_sums);
+		else k_sort_scatter<false><<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], B.keys[cur ^ 1], nullptr, nullptr, n_ptr, (u32)shift, B.hist, B.block_sums);
+		*L.counter += 2;
 		cur ^= 1;
 	}
 	return cur;

@@ -127,6 +127,29 @@ __global__ void __launch_bounds__(NB_BLOCK) k_inertia(u32 B, const nb_transform*
 #define NB_SCHED_SHARED 504
 #define NB_SCHED_MAXV (NB_SCHED_REGPOS + NB_SCHED_SHARED - 1)
 
+// Parallel pre-pass for the replay: the body pair of every contact in tag order with the body-0 substitution of
+// nudge.cpp:4238-4240 applied, and `back` = distance (in contacts of the same bucket, 1..7) to the nearest earlier contact of
+// the bucket that shares a body, 0 if there is none within 7.  A run of 8 consecutive bucket contacts starting at a fresh
+// slot is conflict free iff none of them has 0 < back <= its offset in the run.
+__global__ void __launch_bounds__(NB_BLOCK) k_sched_prep(const u32* sorted, const uint2* bodies, uint2* cab, uint8_t* back, const u32* counts) {
+	u32 n = counts[CNT_CONTACTS];
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		uint2 ab = bodies[sorted[i]];
+		u32 ca = ab.x ? ab.x : ab.y, cb = ab.y ? ab.y : ab.x;
+		cab[i] = make_uint2(ca, cb);
+		u32 b = 0;
+		#pragma unroll
+		for (u32 k = 1; k <= 7; ++k) {
+			if (!b && i >= 16 * k) {
+				uint2 o = bodies[sorted[i - 16 * k]];
+				u32 oa = o.x ? o.x : o.y, ob = o.y ? o.y : o.x;
+				if (oa == ca || ob == ca || oa == cb || ob == cb) b = k;
+			}
+		}
+		back[i] = (uint8_t)b;
+	}
+}
+
 // slot_of[i] = uid << 3 | lane, where lane is the SIMD lane the contact lands in (= number of contacts already in its slot)
 //
 // ~99.9 % of all contacts go to list position 0 (measured), so the replay speculates: the next 8 - fill(position 0)
@@ -134,7 +157,7 @@ __global__ void __launch_bounds__(NB_BLOCK) k_inertia(u32 B, const nb_transform*
 // conflict are accepted in parallel (they are exactly the ones the sequential first-fit would put there), and only the
 // conflicting contact runs the general search.  A lone warp pays ~8 cycles per instruction, so instructions per contact
 // are what matters here.
-__global__ void __launch_bounds__(32) k_schedule(const u32* sorted, const uint2* bodies, u32* slot_of, u32* slot_done, u32* slot_left, u32 slots_per_bucket,
+__global__ void __launch_bounds__(32) k_schedule(const uint2* cab, const uint8_t* back, u32* slot_of, u32* slot_done, u32* slot_left, u32 slots_per_bucket,
 												 u32* complete_flag, u32* left_count /*[16]*/, u32* counts) {
 	__shared__ u32 S_ent[NB_SCHED_SHARED][16];
 	__shared__ u32 S_uid[NB_SCHED_REGPOS + NB_SCHED_SHARED];
@@ -244,20 +267,39 @@ __global__ void __launch_bounds__(32) k_schedule(const u32* sorted, const uint2*
 	};
 
 	// software pipeline: the (ca, cb) of the next 32 contacts of this bucket are fetched while the current 32 are placed
-	u32 nx_ca = 0, nx_cb = 0;
+	u32 nx_ca = 0, nx_cb = 0, nx_back = 0;
 	{
 		u32 i0 = bucket + 16 * lane;
-		if (i0 < n) { uint2 ab = bodies[sorted[i0]]; nx_ca = ab.x ? ab.x : ab.y; nx_cb = ab.y ? ab.y : ab.x; complete_flag[i0] = 0; }  // body 0 is ignored (nudge.cpp:4238-4240)
+		if (i0 < n) { uint2 ab = cab[i0]; nx_ca = ab.x; nx_cb = ab.y; nx_back = back[i0]; complete_flag[i0] = 0; }
 	}
 	for (u32 base = bucket; base < n; base += 16 * 32) {
-		u32 my_ca = nx_ca, my_cb = nx_cb;
+		const u32 my_ca = nx_ca, my_cb = nx_cb, my_back = nx_back;
 		{
 			u32 i1 = base + 16 * 32 + 16 * lane;
-			if (i1 < n) { uint2 ab = bodies[sorted[i1]]; nx_ca = ab.x ? ab.x : ab.y; nx_cb = ab.y ? ab.y : ab.x; complete_flag[i1] = 0; }
+			if (i1 < n) { uint2 ab = cab[i1]; nx_ca = ab.x; nx_cb = ab.y; nx_back = back[i1]; complete_flag[i1] = 0; }
 		}
 		const u32 steps = min(32u, (n - base + 15) / 16);
 		u32 s = 0;
 		while (s < steps) {
+			// ---- fresh list: whole 8-contact runs with no internal conflict are complete slots; accept as many as are clean with one ballot ----
+			if (vcount == 0 && steps - s >= 8) {
+				const u32 off = (lane - s) & 7;                       // offset of this lane's contact in its run (runs start at s)
+				const bool bad = lane >= s && lane < steps && my_back != 0 && my_back <= off;
+				const u32 bal = __ballot_sync(0xffffffffu, bad);
+				const u32 first_bad = bal ? (u32)(__ffs(bal) - 1) : steps;
+				const u32 runs = (first_bad - s) >> 3;
+				if (runs) {
+					const u32 rel = lane - s;
+					if (lane >= s && rel < 8 * runs) {
+						const u32 uid = next_uid + (rel >> 3);
+						const u32 i = base + 16 * lane;
+						slot_of[i] = (uid << 3) | (rel & 7);
+						if ((rel & 7) == 7) { done[uid] = i; complete_flag[i] = 1; }
+					}
+					next_uid += runs; s += 8 * runs;
+					continue;
+				}
+			}
 			// ---- speculative groups: the contacts that would fill list position 0 (lanes 0-15); when the list is empty the
 			// upper half-warp speculates on the following eight as well ----
 			const bool fresh = vcount == 0;  // implies f0 == 0
@@ -615,7 +657,7 @@ NB_DEV void solve_contact(const Rows& R, u32 j, float4& al, float4& aw, float4& 
 // items are visited in increasing (sweep, slot), which is a topological order of the dependency graph, so the lowest
 // unfinished item is always runnable.  Inside a warp the lanes poll instead of blocking, so a lane may depend on another
 // lane of its own warp.  mw must come from k_mw_in (all tokens 0).
-__global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impulses, float4* mw, int mode, u32 sweeps, u32* counts) {
+__global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impulses, float4* mw, int mode, u32 sweeps, u32 backoff_ns, u32* counts) {
 	__shared__ u32 s_rcp[2048];
 	__shared__ u32 s_rsqrt[2048];
 	for (u32 i = threadIdx.x; i < 2048; i += blockDim.x) { s_rcp[i] = g_rcp_lut[i]; s_rsqrt[i] = g_rsqrt_lut[i]; }
@@ -651,6 +693,7 @@ __global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impuls
 							if (b) { bl.w = tk; bw.w = tk; st128(mw + 2*b, bl); st128(mw + 2*b + 1, bw); }
 							pending = false;
 						}
+						else if (backoff_ns) __nanosleep(backoff_ns);
 					}
 				}
 			}
