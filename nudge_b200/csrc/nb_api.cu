@@ -37,6 +37,7 @@ struct nb_context {
 	// collide
 	nb_transform* world_xf; float4* aabb_min; float4* aabb_max; u32* col_tag; u32* col_body; u32* order; u32* rank;
 	float4* tree_min; float4* tree_max;
+	u64* mkeys; uint8_t* smallf; u32* large_list; u64* table_keys; u64* table_vals; u32 table_mask; int use_tree;
 	SortBuffers sb; u32 sort_cap;
 	u64* pair_keys;  // alias into sb.keys[] after the pair sort
 	u64* pair_keys_debug;  // copy kept for parity tests when debug is enabled (the sort buffers are reused later in the step)
@@ -77,7 +78,7 @@ static Launch mk_launch(nb_context* ctx, void* stream) { Launch L = { (cudaStrea
 
 __global__ void k_reset_collide(u32* counts) {
 	if (threadIdx.x == 0) {
-		counts[CNT_PAIRS] = 0; counts[CNT_OVERFLOW] = 0;
+		counts[CNT_PAIRS] = 0; counts[CNT_OVERFLOW] = 0; counts[CNT_EXT_SUM] = 0;
 		for (int k = 0; k < 4; ++k) { counts[CNT_BMIN0 + k] = 0xffffffffu; counts[CNT_BMAX0 + k] = 0; }
 	}
 }
@@ -154,6 +155,13 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ALLOC(ctx->order, K); ALLOC(ctx->rank, K);
 	size_t tree_nodes = 0; { u32 n = K ? K : 1; tree_nodes = n; while (n > 8) { n = (n + 7) / 8; tree_nodes += n; } }
 	ALLOC(ctx->tree_min, tree_nodes + 8); ALLOC(ctx->tree_max, tree_nodes + 8);
+	{
+		u32 tsz = 1024; while (tsz < 2 * (K ? K : 1)) tsz *= 2;
+		ctx->table_mask = tsz - 1;
+		ALLOC(ctx->mkeys, K); ALLOC(ctx->smallf, K); ALLOC(ctx->large_list, K); ALLOC(ctx->table_keys, tsz); ALLOC(ctx->table_vals, tsz);
+		const char* e = getenv("NB_BROADPHASE");
+		ctx->use_tree = e && !strcmp(e, "tree");
+	}
 	ctx->sort_cap = std::max(std::max(K, P), 2 * C);
 	for (int i = 0; i < 2; ++i) { ALLOC(ctx->sb.keys[i], ctx->sort_cap); ALLOC(ctx->sb.vals[i], ctx->sort_cap); }
 	ALLOC(ctx->sb.hist, 256 * NB_SORT_GRID); ALLOC(ctx->sb.block_sums, 8 * NB_SCAN_GRID);
@@ -341,15 +349,26 @@ int nb_collide(nb_context* ctx, void* stream) {
 		while (true) { T.mn[l] = ctx->tree_min + off; T.mx[l] = ctx->tree_max + off; T.n[l] = n; off += n; ++l; if (n <= 8) break; n = (n + 7) / 8; }
 		T.levels = l;
 	}
-	k_leaves<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->sb.vals[cur], ctx->aabb_min, ctx->aabb_max, ctx->order, ctx->rank, (float4*)T.mn[0], (float4*)T.mx[0]);
+	k_leaves<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->sb.vals[cur], ctx->sb.keys[cur], ctx->aabb_min, ctx->aabb_max, ctx->order, ctx->rank, (float4*)T.mn[0], (float4*)T.mx[0], ctx->mkeys);
 	++ctx->launches;
-	for (int l = 1; l < T.levels; ++l) {
-		k_build_level<<<GRID(T.n[l]), NB_BLOCK, 0, st>>>(T.mn[l - 1], T.mx[l - 1], T.n[l - 1], (float4*)T.mn[l], (float4*)T.mx[l], T.n[l]);
+	if (ctx->use_tree) {  // NB_BROADPHASE=tree: the implicit 8-ary AABB tree (kept for comparison)
+		for (int l = 1; l < T.levels; ++l) {
+			k_build_level<<<GRID(T.n[l]), NB_BLOCK, 0, st>>>(T.mn[l - 1], T.mx[l - 1], T.n[l - 1], (float4*)T.mn[l], (float4*)T.mx[l], T.n[l]);
+			++ctx->launches;
+		}
+		k_find_pairs<<<GRID(K), NB_BLOCK, 0, st>>>(T, K, ctx->order, ctx->kbits, ctx->sb.keys[0], ctx->cfg.max_pairs, counts);
 		++ctx->launches;
 	}
-	k_find_pairs<<<GRID(K), NB_BLOCK, 0, st>>>(T, K, ctx->order, ctx->kbits, ctx->sb.keys[0], ctx->cfg.max_pairs, counts);
+	else {
+		CK(cudaMemsetAsync(ctx->table_keys, 0xff, sizeof(u64) * ((size_t)ctx->table_mask + 1), st));
+		k_grid_setup<<<1, 1, 0, st>>>(K, counts);
+		k_grid_build<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->order, T.mn[0], T.mx[0], ctx->mkeys, ctx->smallf, ctx->large_list, ctx->table_keys, ctx->table_vals, ctx->table_mask, counts);
+		k_grid_pairs<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->order, T.mn[0], T.mx[0], ctx->smallf, ctx->table_keys, ctx->table_vals, ctx->table_mask, ctx->kbits, ctx->sb.keys[0], ctx->cfg.max_pairs, counts);
+		k_large_pairs<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->order, T.mn[0], T.mx[0], ctx->smallf, ctx->large_list, ctx->kbits, ctx->sb.keys[0], ctx->cfg.max_pairs, counts);
+		ctx->launches += 4;
+	}
 	k_clamp_count<<<1, 1, 0, st>>>(counts, CNT_PAIRS, ctx->cfg.max_pairs);
-	ctx->launches += 2;
+	++ctx->launches;
 	cur = nb_radix_sort(L, ctx->sb, counts + CNT_PAIRS, 0, (int)(2 * ctx->kbits), false, 0);  // nudge.cpp:3498
 	ctx->pair_keys = ctx->sb.keys[cur];
 	if (ctx->debug) { k_copy_u64<<<GRID(ctx->cfg.max_pairs), NB_BLOCK, 0, st>>>(ctx->pair_keys, ctx->pair_keys_debug, counts + CNT_PAIRS); ++ctx->launches; }

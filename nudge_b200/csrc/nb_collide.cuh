@@ -18,7 +18,7 @@ enum {  // device counters (u32 each)
 	CNT_FACE, CNT_EDGE, CNT_OTHER, CNT_STAGED, CNT_CONTACTS, CNT_SLEEP_FINE, CNT_SLEEPING, CNT_ACTIVE,
 	CNT_CACHE, CNT_CULLED, CNT_FULL_BATCHES, CNT_BATCHES, CNT_LEVELS, CNT_ENTRIES, CNT_OVERFLOW, CNT_LVCH0, CNT_LVCH1, CNT_LVCH2,
 	CNT_BMIN0, CNT_BMIN1, CNT_BMIN2, CNT_BMIN3, CNT_BMAX0, CNT_BMAX1, CNT_BMAX2, CNT_BMAX3,
-	CNT_BAR0, CNT_BAR1, CNT_SCRATCH0, CNT_SCRATCH1, CNT__COUNT = 64
+	CNT_BAR0, CNT_BAR1, CNT_SCRATCH0, CNT_SCRATCH1, CNT_EXT_SUM, CNT_GRID_LEVEL, CNT_LARGE, CNT__COUNT = 64
 };
 enum { OVF_PAIRS = 1, OVF_CONTACTS = 2, OVF_SCHED = 4, OVF_LEVELS = 8 };
 
@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(NB_BLOCK) k_collider_world(u32 nboxes, u32 nsp
 		nb_transform* world_xf, float4* aabb_min, float4* aabb_max, u32* col_tag, u32* col_body, u32* counts) {
 	u32 K = nboxes + nspheres;
 	float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
+	float ext_sum = 0.0f;
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
 		bool is_box = i < nboxes;
 		xform l = is_box ? ld_xform(box_xf, i) : ld_xform(sph_xf, i - nboxes);
@@ -58,7 +59,12 @@ __global__ void __launch_bounds__(NB_BLOCK) k_collider_world(u32 nboxes, u32 nsp
 		col_body[i] = body;
 		mn[0] = fminf(mn[0], lo.x); mn[1] = fminf(mn[1], lo.y); mn[2] = fminf(mn[2], lo.z);
 		mx[0] = fmaxf(mx[0], lo.x); mx[1] = fmaxf(mx[1], lo.y); mx[2] = fmaxf(mx[2], lo.z);
+		ext_sum += 2.0f * fmaxf(ext.x, fmaxf(ext.y, ext.z));
 	}
+	// mean AABB extent (only steers the grid cell size of the broadphase, never a result): warp sum, one float atomic per warp
+	#pragma unroll
+	for (int d = 16; d; d >>= 1) ext_sum += __shfl_xor_sync(0xffffffffu, ext_sum, d);
+	if ((threadIdx.x & 31) == 0 && ext_sum > 0.0f) atomicAdd(reinterpret_cast<float*>(&counts[CNT_EXT_SUM]), ext_sum);
 	// scene bounds over AABB *mins* (nudge.cpp:3087-3094): min/max are exact, so any reduction order gives the same bits
 	#pragma unroll
 	for (int k = 0; k < 3; ++k) {
@@ -87,6 +93,26 @@ NB_DEV void dilate3(u32 x, u32 offset, u32& lo32, u32& hi32) {
 	hi32 = hi24 >> (8 - offset);
 }
 
+struct MortonFrame { float L[4]; float ms[3]; };
+NB_DEV MortonFrame morton_frame(const u32* counts) {
+	MortonFrame f;
+	float smin[4], smax[4], sc[4];
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) { smin[k] = ord2f(counts[CNT_BMIN0 + k]); smax[k] = ord2f(counts[CNT_BMAX0 + k]); }
+	smin[3] = 0.0f; smax[3] = 0.0f;
+	#pragma unroll
+	for (int k = 0; k < 4; ++k) sc[k] = 65535.0f * nb_rcp(smax[k] - smin[k]);
+	float A[4] = { nb_min(sc[0], sc[2]), nb_min(sc[1], sc[2]), nb_min(sc[2], sc[0]), nb_min(sc[2], sc[1]) };
+	f.L[0] = nb_min(A[0], A[1]); f.L[1] = nb_min(A[1], A[0]); f.L[2] = nb_min(A[2], A[3]); f.L[3] = nb_min(A[3], A[2]);
+	f.ms[0] = smin[0] * f.L[0]; f.ms[1] = smin[1] * f.L[1]; f.ms[2] = smin[2] * f.L[2];
+	return f;
+}
+// quantised min corner of collider i exactly as k_morton computes it (i = ORIGINAL collider index: the lane-dependent scale)
+NB_DEV void morton_quantise(const MortonFrame& f, float4 p, u32 i, u32& x, u32& y, u32& z) {
+	float s = f.L[i & 3];
+	x = (u32)nb_toint(nb_msub(p.x, s, f.ms[0])); y = (u32)nb_toint(nb_msub(p.y, s, f.ms[1])); z = (u32)nb_toint(nb_msub(p.z, s, f.ms[2]));
+}
+
 __global__ void __launch_bounds__(NB_BLOCK) k_morton(u32 K, const float4* aabb_min, const u32* counts, u64* keys, u32* vals) {
 	float smin[4], smax[4], sc[4];
 	#pragma unroll
@@ -111,11 +137,11 @@ __global__ void __launch_bounds__(NB_BLOCK) k_morton(u32 K, const float4* aabb_m
 }
 
 // ---------------- K3/K4: Morton-ordered leaves and the implicit 8-ary AABB tree ----------------
-__global__ void __launch_bounds__(NB_BLOCK) k_leaves(u32 K, const u32* sorted_vals, const float4* aabb_min, const float4* aabb_max,
-													 u32* order, u32* rank, float4* leaf_min, float4* leaf_max) {
+__global__ void __launch_bounds__(NB_BLOCK) k_leaves(u32 K, const u32* sorted_vals, const u64* sorted_keys, const float4* aabb_min, const float4* aabb_max,
+													 u32* order, u32* rank, float4* leaf_min, float4* leaf_max, u64* mkeys) {
 	for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < K; pos += gridDim.x * blockDim.x) {
 		u32 i = sorted_vals[pos];
-		order[pos] = i; rank[i] = pos;
+		order[pos] = i; rank[i] = pos; mkeys[pos] = sorted_keys[pos];
 		float4 lo = aabb_min[i], hi = aabb_max[i];
 		float vol = (hi.x - lo.x) * (hi.y - lo.y) * (hi.z - lo.z);
 		lo.w = vol; hi.w = vol;
@@ -260,6 +286,110 @@ __global__ void __launch_bounds__(NB_BLOCK) k_find_pairs(Tree T, u32 K, const u3
 			}
 		}
 		__syncwarp();
+	}
+}
+
+// ---------------- K5b: grid broadphase on top of the Morton order (default) ----------------
+// The Morton-sorted colliders are already sorted by octree cell at every level: the colliders of the level-j cell with integer
+// coordinates (cx,cy,cz) are the contiguous range of sorted positions whose 48-bit code has the prefix morton(cx,cy,cz) >> 3j.
+// Level j is chosen per step so that a cell is at least twice the mean AABB extent.  A collider whose extent (in quantised
+// units, +2 for rounding) fits one cell is "small": two overlapping small colliders have min-corner cells that differ by at
+// most 1 per axis, so a small collider only has to look into the 27 cells around its own (found through a hash table
+// cell -> sorted range).  The few "large" colliders (the ground; also anything whose quantised corner wrapped past 65535,
+// nudge.cpp:2613-2616 masks it) are tested against everybody by brute force.  The union is exactly the set of strictly
+// overlapping pairs, reported once, oriented by Morton position like nudge.cpp:3495.
+#define NB_GRID_EMPTY (~(u64)0)
+NB_DEV u64 morton48_of(u32 x, u32 y, u32 z) {
+	u32 lx, hx, ly, hy, lz, hz;
+	dilate3(x, 2, lx, hx); dilate3(y, 1, ly, hy); dilate3(z, 0, lz, hz);
+	return (u64)(lx | ly | lz) | ((u64)(hx | hy | hz) << 32);
+}
+NB_DEV u32 grid_hash(u64 prefix, u32 mask) { return (u32)((prefix * 0x9E3779B97F4A7C15ull) >> 32) & mask; }
+
+__global__ void k_grid_setup(u32 K, u32* counts) {
+	MortonFrame f = morton_frame(counts);
+	float mean = asf(counts[CNT_EXT_SUM]) / (float)K;
+	float need = 2.0f * mean * f.L[0] + 2.0f;  // cell edge in quantised units
+	u32 j = 1;
+	while (j < 16 && (float)(1u << j) < need) ++j;
+	if (!(need == need)) j = 16;
+	counts[CNT_GRID_LEVEL] = j; counts[CNT_LARGE] = 0;
+}
+
+__global__ void __launch_bounds__(NB_BLOCK) k_grid_build(u32 K, const u32* order, const float4* leaf_min, const float4* leaf_max, const u64* mkeys,
+		uint8_t* smallf, u32* large_list, u64* table_keys, u64* table_vals, u32 table_mask, u32* counts) {
+	const MortonFrame f = morton_frame(counts);
+	const u32 j = counts[CNT_GRID_LEVEL];
+	const float cell = (float)(1u << j);
+	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < K; p += gridDim.x * blockDim.x) {
+		float4 lo = leaf_min[p], hi = leaf_max[p];
+		u32 qx, qy, qz; morton_quantise(f, lo, order[p], qx, qy, qz);
+		float ext = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z)) * f.L[0] + 2.0f;
+		bool small = ext <= cell && qx < 65536u && qy < 65536u && qz < 65536u;  // NaN extents are "large" too
+		smallf[p] = small ? 1 : 0;
+		if (!small) large_list[atomicAdd(&counts[CNT_LARGE], 1u)] = p;
+		const u64 prefix = mkeys[p] >> (3 * j);
+		if (p == 0 || (mkeys[p - 1] >> (3 * j)) != prefix) {  // first collider of its cell: publish the cell's range
+			u32 e = p + 1;
+			while (e < K && (mkeys[e] >> (3 * j)) == prefix) ++e;
+			u32 slot = grid_hash(prefix, table_mask);
+			while (true) {
+				u64 old = atomicCAS((unsigned long long*)&table_keys[slot], (unsigned long long)NB_GRID_EMPTY, (unsigned long long)prefix);
+				if (old == NB_GRID_EMPTY) break;
+				slot = (slot + 1) & table_mask;
+			}
+			table_vals[slot] = (u64)p | ((u64)e << 32);
+		}
+	}
+}
+
+NB_DEV bool boxes_overlap(float4 alo, float4 ahi, float4 blo, float4 bhi) {  // strict, nudge.cpp:3306-3310 / 3386-3390
+	return bhi.x > alo.x && ahi.x > blo.x && bhi.y > alo.y && ahi.y > blo.y && bhi.z > alo.z && ahi.z > blo.z;
+}
+NB_DEV void emit_pair(u32 p, u32 q, const u32* order, u32 kbits, u64* pair_keys, u32 max_pairs, u32* counts) {  // p < q: Morton positions
+	u32 slot = warp_append_slot(&counts[CNT_PAIRS]);
+	if (slot < max_pairs) pair_keys[slot] = ((u64)order[p] << kbits) | (u64)order[q];  // hi = earlier, lo = later (nudge.cpp:3495)
+	else atomicOr(&counts[CNT_OVERFLOW], OVF_PAIRS);
+}
+
+__global__ void __launch_bounds__(NB_BLOCK) k_grid_pairs(u32 K, const u32* order, const float4* leaf_min, const float4* leaf_max, const uint8_t* smallf,
+		const u64* table_keys, const u64* table_vals, u32 table_mask, u32 kbits, u64* pair_keys, u32 max_pairs, u32* counts) {
+	const MortonFrame f = morton_frame(counts);
+	const u32 j = counts[CNT_GRID_LEVEL];
+	const int ncell = 1 << (16 - j);
+	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < K; p += gridDim.x * blockDim.x) {
+		if (!smallf[p]) continue;
+		const float4 lo = leaf_min[p], hi = leaf_max[p];
+		u32 qx, qy, qz; morton_quantise(f, lo, order[p], qx, qy, qz);
+		const int cx = (int)(qx >> j), cy = (int)(qy >> j), cz = (int)(qz >> j);
+		for (int dz = -1; dz <= 1; ++dz)
+			for (int dy = -1; dy <= 1; ++dy)
+				for (int dx = -1; dx <= 1; ++dx) {
+					const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+					if (nx < 0 || ny < 0 || nz < 0 || nx >= ncell || ny >= ncell || nz >= ncell) continue;
+					const u64 prefix = morton48_of((u32)nx << j, (u32)ny << j, (u32)nz << j) >> (3 * j);
+					u32 slot = grid_hash(prefix, table_mask);
+					u64 k;
+					while ((k = table_keys[slot]) != prefix && k != NB_GRID_EMPTY) slot = (slot + 1) & table_mask;
+					if (k == NB_GRID_EMPTY) continue;
+					const u64 range = table_vals[slot];
+					const u32 e = (u32)(range >> 32);
+					for (u32 q = max((u32)range, p + 1); q < e; ++q)  // each pair once: from its earlier Morton position
+						if (smallf[q] && boxes_overlap(lo, hi, leaf_min[q], leaf_max[q])) emit_pair(p, q, order, kbits, pair_keys, max_pairs, counts);
+				}
+	}
+}
+
+__global__ void __launch_bounds__(NB_BLOCK) k_large_pairs(u32 K, const u32* order, const float4* leaf_min, const float4* leaf_max, const uint8_t* smallf,
+		const u32* large_list, u32 kbits, u64* pair_keys, u32 max_pairs, u32* counts) {
+	const u32 nlarge = counts[CNT_LARGE];
+	for (u32 l = 0; l < nlarge; ++l) {
+		const u32 pl = large_list[l];
+		const float4 lo = leaf_min[pl], hi = leaf_max[pl];
+		for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < K; q += gridDim.x * blockDim.x) {
+			if (q == pl || (!smallf[q] && q < pl)) continue;  // a pair of two large colliders is reported from the earlier one
+			if (boxes_overlap(lo, hi, leaf_min[q], leaf_max[q])) emit_pair(min(pl, q), max(pl, q), order, kbits, pair_keys, max_pairs, counts);
+		}
 	}
 }
 
