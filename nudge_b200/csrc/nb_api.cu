@@ -46,7 +46,7 @@ struct nb_context {
 	uint2* live;
 	ContactOut staged, fin;
 	u64* sleeping;
-	u32* parent; u32* active; u32* active_idx;
+	u32* parent; u32* active; u32* active_idx; u32* taint;
 	// cache
 	u64* cache_tags; u32* cache_features; float4* cache_data;
 	u64* culled_tags; u32* culled_features; float4* culled_data;
@@ -170,7 +170,7 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ALLOC(ctx->staged.data, 2 * (size_t)C); ALLOC(ctx->staged.bodies, C); ALLOC(ctx->staged.tags, C); ALLOC(ctx->staged.features, C);
 	ALLOC(ctx->fin.data, 2 * (size_t)C); ALLOC(ctx->fin.bodies, C); ALLOC(ctx->fin.tags, C); ALLOC(ctx->fin.features, C);
 	ALLOC(ctx->sleeping, (size_t)P + C);
-	ALLOC(ctx->parent, B); ALLOC(ctx->active, B); ALLOC(ctx->active_idx, B);
+	ALLOC(ctx->parent, B); ALLOC(ctx->active, B); ALLOC(ctx->active_idx, B); ALLOC(ctx->taint, B);
 	ALLOC(ctx->cache_tags, C); ALLOC(ctx->cache_features, C); ALLOC(ctx->cache_data, C);
 	ALLOC(ctx->culled_tags, C); ALLOC(ctx->culled_features, C); ALLOC(ctx->culled_data, C);
 	ALLOC(ctx->sorted, C); ALLOC(ctx->impulses, C);
@@ -375,10 +375,10 @@ int nb_collide(nb_context* ctx, void* stream) {
 
 	// coarse islands (nudge.cpp:3500-3703)
 	const u32 P = ctx->cfg.max_pairs, S = ctx->stride;
-	k_uf_init<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, B); ++ctx->launches;
-	if (ctx->nconn) { k_uf_union_conn<<<GRID(ctx->nconn), NB_BLOCK, 0, st>>>(ctx->parent, ctx->conn, ctx->nconn); ++ctx->launches; }
-	k_uf_union_pairs<<<GRID(P), NB_BLOCK, 0, st>>>(ctx->parent, ctx->pair_keys, ctx->kbits, ctx->col_body, counts);
-	k_uf_flatten_active<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, ctx->idle, B);
+	k_uf_init<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, ctx->taint, B); ++ctx->launches;
+	if (ctx->nconn) { k_uf_union_conn<<<GRID(ctx->nconn), NB_BLOCK, 0, st>>>(ctx->parent, ctx->taint, ctx->idle, ctx->conn, ctx->nconn); ++ctx->launches; }
+	k_uf_union_pairs<<<GRID(P), NB_BLOCK, 0, st>>>(ctx->parent, ctx->taint, ctx->idle, ctx->pair_keys, ctx->kbits, ctx->col_body, counts);
+	k_uf_flatten_active<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, ctx->taint, ctx->idle, B);
 	k_pair_flags<<<GRID(P), NB_BLOCK, 0, st>>>(ctx->pair_keys, ctx->kbits, nboxes, ctx->col_body, ctx->parent, ctx->active, ctx->flags, S, counts);
 	ctx->launches += 3;
 	nb_scan<5>(L, ctx->flags, ctx->offs, S, counts + CNT_PAIRS, 0, ctx->block_sums, counts + CNT_LIVE0);  // -> LIVE0..3, SLEEP_COARSE
@@ -394,10 +394,10 @@ int nb_collide(nb_context* ctx, void* stream) {
 
 	// fine islands, active bodies, contact compaction (nudge.cpp:3788-4006)
 	const u32 C = ctx->cfg.max_contacts;
-	k_uf_init<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, B); ++ctx->launches;
-	if (ctx->nconn) { k_uf_union_conn<<<GRID(ctx->nconn), NB_BLOCK, 0, st>>>(ctx->parent, ctx->conn, ctx->nconn); ++ctx->launches; }
-	k_uf_union_contacts<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->parent, ctx->staged.bodies, counts);
-	k_uf_flatten_active<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, ctx->idle, B);
+	k_uf_init<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, ctx->taint, B); ++ctx->launches;
+	if (ctx->nconn) { k_uf_union_conn<<<GRID(ctx->nconn), NB_BLOCK, 0, st>>>(ctx->parent, ctx->taint, ctx->idle, ctx->conn, ctx->nconn); ++ctx->launches; }
+	k_uf_union_contacts<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->parent, ctx->taint, ctx->idle, ctx->staged.bodies, counts);
+	k_uf_flatten_active<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, ctx->taint, ctx->idle, B);
 	k_body_flags<<<GRID(B), NB_BLOCK, 0, st>>>(ctx->parent, ctx->active, ctx->flags, B);
 	ctx->launches += 3;
 	nb_scan<1>(L, ctx->flags, ctx->offs, S, nullptr, B, ctx->block_sums, counts + CNT_ACTIVE);

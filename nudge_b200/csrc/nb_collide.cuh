@@ -425,29 +425,41 @@ NB_DEV void uf_unite(u32* parent, u32 a, u32 b) {
 		a = old;  // a was not a root any more: continue from its real parent
 	}
 }
-__global__ void __launch_bounds__(NB_BLOCK) k_uf_init(u32* parent, u32* active, u32 B) {
-	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) { parent[i] = i; active[i] = 0; }
+// Islands and sleeping (nudge.cpp:3500-3703, 3788-3971): a set is active iff ANY member is awake (idle counter != 0xff), so a set
+// can only be inactive if ALL its bodies are asleep.  Hence only edges between two asleep bodies need a union; an edge between an
+// asleep and an awake body "taints" the asleep one (its whole asleep component is then active), and edges between awake bodies
+// carry no information.  The resulting active/inactive decision per body is exactly the reference's, at almost no cost while the
+// scene is moving.  active[] is indexed by the root of a body's asleep-component (an awake body is its own root).
+NB_DEV void island_edge(u32* parent, u32* taint, const uint8_t* idle, u32 a, u32 b) {
+	if (!a || !b || a == b) return;  // body 0 is the static world and is ignored (nudge.cpp:3517-3519, 3583-3585)
+	const bool sa = idle[a] == 0xff, sb = idle[b] == 0xff;
+	if (sa && sb) uf_unite(parent, a, b);
+	else if (sa) taint[a] = 1;
+	else if (sb) taint[b] = 1;
 }
-__global__ void __launch_bounds__(NB_BLOCK) k_uf_union_conn(u32* parent, const nb_body_pair* conn, u32 n) {
-	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) uf_unite(parent, conn[i].a, conn[i].b);
+__global__ void __launch_bounds__(NB_BLOCK) k_uf_init(u32* parent, u32* active, u32* taint, u32 B) {
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) { parent[i] = i; active[i] = 0; taint[i] = 0; }
 }
-__global__ void __launch_bounds__(NB_BLOCK) k_uf_union_pairs(u32* parent, const u64* pair_keys, u32 kbits, const u32* col_body, const u32* counts) {
+__global__ void __launch_bounds__(NB_BLOCK) k_uf_union_conn(u32* parent, u32* taint, const uint8_t* idle, const nb_body_pair* conn, u32 n) {
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) island_edge(parent, taint, idle, conn[i].a, conn[i].b);
+}
+__global__ void __launch_bounds__(NB_BLOCK) k_uf_union_pairs(u32* parent, u32* taint, const uint8_t* idle, const u64* pair_keys, u32 kbits, const u32* col_body, const u32* counts) {
 	u32 n = counts[CNT_PAIRS];
 	u64 mask = ((u64)1 << kbits) - 1;
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		u64 k = pair_keys[i];
-		uf_unite(parent, col_body[(u32)(k & mask)], col_body[(u32)(k >> kbits)]);
+		island_edge(parent, taint, idle, col_body[(u32)(k & mask)], col_body[(u32)(k >> kbits)]);
 	}
 }
-__global__ void __launch_bounds__(NB_BLOCK) k_uf_union_contacts(u32* parent, const uint2* bodies, const u32* counts) {
+__global__ void __launch_bounds__(NB_BLOCK) k_uf_union_contacts(u32* parent, u32* taint, const uint8_t* idle, const uint2* bodies, const u32* counts) {
 	u32 n = counts[CNT_STAGED];
-	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { uint2 ab = bodies[i]; uf_unite(parent, ab.x, ab.y); }
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { uint2 ab = bodies[i]; island_edge(parent, taint, idle, ab.x, ab.y); }
 }
-__global__ void __launch_bounds__(NB_BLOCK) k_uf_flatten_active(u32* parent, u32* active, const uint8_t* idle, u32 B) {
+__global__ void __launch_bounds__(NB_BLOCK) k_uf_flatten_active(u32* parent, u32* active, const u32* taint, const uint8_t* idle, u32 B) {
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
 		u32 r = uf_find_fresh(parent, i);
 		parent[i] = r;  // roots never change here, so concurrent flattening is benign
-		if (i >= 1 && idle[i] != 0xff) active[r] = 1;  // nudge.cpp:3669-3672
+		if (i >= 1 && (idle[i] != 0xff || taint[i])) active[r] = 1;  // nudge.cpp:3669-3672
 	}
 }
 
