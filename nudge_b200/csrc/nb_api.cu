@@ -26,6 +26,7 @@ struct nb_context {
 	u32 cstride;   // row plane stride
 	u32 slots_per_bucket;
 	int coop_blocks_solve;
+	bool contacts_internal;  // the current contact set came from nb_collide (not nb_upload_contacts)
 	u32 solve_backoff_ns;
 
 	// scene
@@ -43,7 +44,7 @@ struct nb_context {
 	u64* pair_keys_debug;  // copy kept for parity tests when debug is enabled (the sort buffers are reused later in the step)
 	int debug;
 	u32* flags; u32* offs; u32* block_sums;
-	uint2* live;
+	uint2* live; float* np_pen; u32* np_info; u32* np_list; u32* np_start;
 	ContactOut staged, fin;
 	u64* sleeping;
 	u32* parent; u32* active; u32* active_idx; u32* taint;
@@ -76,8 +77,9 @@ static u32 bits_for(u64 n) { u32 b = 1; while (((u64)1 << b) < n) ++b; return b;
 static Launch mk_launch(nb_context* ctx, void* stream) { Launch L = { (cudaStream_t)stream, &ctx->launches, ctx->sms }; return L; }
 #define GRID(n) nb_grid_for((unsigned)(n), ctx->sms)
 
-__global__ void k_reset_collide(u32* counts) {
+__global__ void k_reset_collide(u32* counts, u32 K) {
 	if (threadIdx.x == 0) {
+		counts[CNT_SCRATCH1] = K;  // key count of the Morton sort
 		counts[CNT_PAIRS] = 0; counts[CNT_OVERFLOW] = 0; counts[CNT_EXT_SUM] = 0;
 		for (int k = 0; k < 4; ++k) { counts[CNT_BMIN0 + k] = 0xffffffffu; counts[CNT_BMAX0 + k] = 0; }
 	}
@@ -164,9 +166,11 @@ int nb_create(const nb_config* config, nb_context** out) {
 	}
 	ctx->sort_cap = std::max(std::max(K, P), 2 * C);
 	for (int i = 0; i < 2; ++i) { ALLOC(ctx->sb.keys[i], ctx->sort_cap); ALLOC(ctx->sb.vals[i], ctx->sort_cap); }
-	ALLOC(ctx->sb.hist, 256 * NB_SORT_GRID); ALLOC(ctx->sb.block_sums, 8 * NB_SCAN_GRID);
+	ALLOC(ctx->sb.hist, 256 * NB_SORT_GRID);
+	ctx->sb.bar = ctx->counts + CNT_BAR0;
+	{ const char* e = getenv("NB_SORT"); ctx->sb.coop_blocks = (e && !strcmp(e, "legacy")) ? 0 : ctx->sms; } ALLOC(ctx->sb.block_sums, 8 * NB_SCAN_GRID);
 	ALLOC(ctx->flags, 5 * (size_t)ctx->stride); ALLOC(ctx->offs, 5 * (size_t)ctx->stride); ALLOC(ctx->block_sums, 8 * NB_SCAN_GRID);
-	ALLOC(ctx->live, P);
+	ALLOC(ctx->live, P); ALLOC(ctx->np_pen, P); ALLOC(ctx->np_info, P); ALLOC(ctx->np_list, P); ALLOC(ctx->np_start, P);
 	ALLOC(ctx->staged.data, 2 * (size_t)C); ALLOC(ctx->staged.bodies, C); ALLOC(ctx->staged.tags, C); ALLOC(ctx->staged.features, C);
 	ALLOC(ctx->fin.data, 2 * (size_t)C); ALLOC(ctx->fin.bodies, C); ALLOC(ctx->fin.tags, C); ALLOC(ctx->fin.features, C);
 	ALLOC(ctx->sleeping, (size_t)P + C);
@@ -300,6 +304,7 @@ int nb_download_contacts(nb_context* ctx, nb_contact_data* h, nb_active_bodies* 
 int nb_upload_contacts(nb_context* ctx, const nb_contact_data* h, const nb_active_bodies* ha, void* stream) {
 	if (h) {
 		if (h->count > ctx->cfg.max_contacts || h->sleeping_count > ctx->cfg.max_contacts) { ctx->error = "too many contacts"; return NB_ERR_CAPACITY; }
+		ctx->contacts_internal = false;
 		H2D(ctx->fin.data, h->data, h->count, nb_contact); H2D(ctx->fin.bodies, h->bodies, h->count, nb_body_pair);
 		H2D(ctx->fin.tags, h->tags, h->count, u64); H2D(ctx->fin.features, h->features, h->count, u32);
 		if (h->sleeping_count) H2D(ctx->sleeping, h->sleeping_pairs, h->sleeping_count, u64);
@@ -334,14 +339,13 @@ int nb_collide(nb_context* ctx, void* stream) {
 	cudaStream_t st = L.stream;
 	const u32 K = ctx->nboxes + ctx->nspheres, B = ctx->B, nboxes = ctx->nboxes;
 	u32* counts = ctx->counts;
-	k_reset_collide<<<1, 32, 0, st>>>(counts); ++ctx->launches;
+	k_reset_collide<<<1, 32, 0, st>>>(counts, K); ++ctx->launches;
 	if (K == 0 || B == 0) return NB_OK;
 	k_collider_world<<<GRID(K), NB_BLOCK, 0, st>>>(ctx->nboxes, ctx->nspheres, ctx->xf, ctx->box_xf, ctx->box_data, ctx->box_tags,
 		ctx->sph_xf, ctx->sph_data, ctx->sph_tags, ctx->world_xf, ctx->aabb_min, ctx->aabb_max, ctx->col_tag, ctx->col_body, counts);
 	k_morton<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->aabb_min, counts, ctx->sb.keys[0], ctx->sb.vals[0]);
 	ctx->launches += 2;
 	// radix sort on the 48-bit code; ties keep index order like the stable sort of nudge.cpp:3165
-	CK(cudaMemcpyAsync(counts + CNT_SCRATCH1, &K, 4, cudaMemcpyHostToDevice, st));
 	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_SCRATCH1, 0, 48, true, 0);
 	Tree T;
 	{
@@ -386,10 +390,16 @@ int nb_collide(nb_context* ctx, void* stream) {
 	++ctx->launches;
 
 	// narrowphase: count, scan, emit (nudge.cpp:3753-3786)
-	k_narrowphase<false><<<GRID(P), NB_BLOCK, 0, st>>>(ctx->live, nboxes, ctx->world_xf, ctx->box_data, ctx->sph_data, ctx->col_tag, ctx->flags, ctx->offs, S, ctx->staged, ctx->cfg.max_contacts, counts);
+	k_np_faces<<<GRID(P), NB_BLOCK, 0, st>>>(ctx->live, nboxes, ctx->world_xf, ctx->box_data, ctx->sph_data, ctx->col_tag, ctx->flags, S, ctx->np_pen, ctx->np_info, counts);
 	++ctx->launches;
+	nb_scan<1>(L, ctx->flags + 3 * (size_t)S, ctx->offs + 3 * (size_t)S, S, counts + CNT_LIVE0, 0, ctx->block_sums, counts + CNT_SURV);
+	k_np_list<<<GRID(P), NB_BLOCK, 0, st>>>(ctx->flags, ctx->offs, S, ctx->np_list, counts);
+	k_np_clip<<<GRID(P), NB_BLOCK, 0, st>>>(ctx->live, ctx->np_list, ctx->np_pen, ctx->np_info, ctx->world_xf, ctx->box_data, ctx->col_tag, ctx->flags, S,
+		ctx->fin /* scratch: rewritten by k_contact_compact below */, ctx->np_start, ctx->cfg.max_contacts, counts);
+	ctx->launches += 2;
 	nb_scan<3>(L, ctx->flags, ctx->offs, S, counts + CNT_LIVE_TOTAL, 0, ctx->block_sums, counts + CNT_FACE);  // -> FACE, EDGE, OTHER
-	k_narrowphase<true><<<GRID(P), NB_BLOCK, 0, st>>>(ctx->live, nboxes, ctx->world_xf, ctx->box_data, ctx->sph_data, ctx->col_tag, ctx->flags, ctx->offs, S, ctx->staged, ctx->cfg.max_contacts, counts);
+	k_np_emit<<<GRID(P), NB_BLOCK, 0, st>>>(ctx->live, ctx->np_list, ctx->np_start, ctx->fin, nboxes, ctx->world_xf, ctx->box_data, ctx->sph_data, ctx->col_tag,
+		ctx->flags, ctx->offs, S, ctx->staged, ctx->cfg.max_contacts, counts);
 	++ctx->launches;
 
 	// fine islands, active bodies, contact compaction (nudge.cpp:3788-4006)
@@ -410,9 +420,9 @@ int nb_collide(nb_context* ctx, void* stream) {
 
 	// sort sleeping pairs (nudge.cpp:4008): key X | Y<<32, both below 2^tagbits
 	k_copy_u64<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sleeping, ctx->sb.keys[0], counts + CNT_SLEEPING); ++ctx->launches;
-	cur = nb_radix_sort(L, ctx->sb, counts + CNT_SLEEPING, 0, (int)ctx->tagbits, false, 0);
-	cur = nb_radix_sort(L, ctx->sb, counts + CNT_SLEEPING, 32, (int)(32 + ctx->tagbits), false, cur);
+	cur = nb_radix_sort(L, ctx->sb, counts + CNT_SLEEPING, 0, (int)ctx->tagbits, false, 0, 32, (int)(32 + ctx->tagbits));
 	k_copy_u64<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sleeping, counts + CNT_SLEEPING); ++ctx->launches;
+	ctx->contacts_internal = true;
 	CK(cudaGetLastError());
 	return NB_OK;
 }
@@ -431,10 +441,17 @@ int nb_read_cached_impulses(nb_context* ctx, void* stream) {
 	u32* counts = ctx->counts;
 	const u32 C = ctx->cfg.max_contacts, S = ctx->stride;
 	// order contacts by tag: stable sort on the feature word, then on the pair word (nudge.cpp:4024-4044)
-	k_tag_keys_feature<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.features, ctx->sb.keys[0], ctx->sb.vals[0], counts); ++ctx->launches;
-	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_CONTACTS, 0, 32, true, 0);
-	k_tag_keys_pair<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.tags, ctx->sb.vals[cur], ctx->sb.keys[cur], ctx->tagbits, counts); ++ctx->launches;
-	cur = nb_radix_sort(L, ctx->sb, counts + CNT_CONTACTS, 0, (int)(2 * ctx->tagbits), true, cur);
+	int cur;
+	if (ctx->contacts_internal && 2 * ctx->tagbits + 16 <= 64) {
+		k_tag_keys_packed<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.tags, ctx->fin.features, ctx->sb.keys[0], ctx->sb.vals[0], ctx->tagbits, counts); ++ctx->launches;
+		cur = nb_radix_sort(L, ctx->sb, counts + CNT_CONTACTS, 0, (int)(2 * ctx->tagbits + 16), true, 0);
+	}
+	else {  // contacts supplied through nb_upload_contacts: arbitrary feature words
+		k_tag_keys_feature<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.features, ctx->sb.keys[0], ctx->sb.vals[0], counts); ++ctx->launches;
+		cur = nb_radix_sort(L, ctx->sb, counts + CNT_CONTACTS, 0, 32, true, 0);
+		k_tag_keys_pair<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.tags, ctx->sb.vals[cur], ctx->sb.keys[cur], ctx->tagbits, counts); ++ctx->launches;
+		cur = nb_radix_sort(L, ctx->sb, counts + CNT_CONTACTS, 0, (int)(2 * ctx->tagbits), true, cur);
+	}
 	k_copy_u32<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sb.vals[cur], ctx->sorted, counts + CNT_CONTACTS);
 	k_cache_lookup<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.tags, ctx->fin.features, ctx->cache_tags, ctx->cache_features, ctx->cache_data, ctx->impulses, counts);
 	k_culled_flags<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->cache_tags, ctx->sleeping, ctx->flags, counts);

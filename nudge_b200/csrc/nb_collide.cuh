@@ -562,9 +562,26 @@ NB_DEV void put_contact(const ContactOut& o, u32 at, float px, float py, float p
 
 // Pass 2 (nudge.cpp:1432-2136).  A owns the most separating face.  Returns 0 = separated, 1 = face contacts
 // (count in n_out; written at `at` when EMIT), 2 = edge candidate (edge_pen / edge_feature / edge_swap set).
+// Reserves n (< 32) consecutive slots for each calling lane with one atomic per converged group of lanes.
+NB_DEV u32 warp_reserve(u32* counter, u32 n) {
+	u32 m = __activemask();
+	u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+	u32 prefix = 0, total = 0;
+	#pragma unroll
+	for (int b = 0; b < 5; ++b) {
+		u32 v = __ballot_sync(m, (n >> b) & 1u);
+		prefix += __popc(v & lt) << b; total += __popc(v) << b;
+	}
+	u32 leader = __ffs(m) - 1, base = 0;
+	if (lane == leader) base = atomicAdd(counter, total);
+	return __shfl_sync(m, base, leader) + prefix;
+}
+
+// `reserve` (optional, EMIT only): the contacts go to slots reserved from this counter once their number is known; `at` returns the first slot.
 template<bool EMIT>
-NB_DEV int bb_face_or_edge(const BoxIn& A, const BoxIn& B, float face_penetration, u32 a_face, const ContactOut& out, u32 at, u32 limit,
-						   u32& n_out, float& edge_pen, u32& edge_feature, bool& edge_swap) {
+NB_DEV int bb_face_or_edge(const BoxIn& A, const BoxIn& B, float face_penetration, u32 a_face, const ContactOut& out, u32& at_io, u32 limit,
+						   u32& n_out, float& edge_pen, u32& edge_feature, bool& edge_swap, u32* reserve = nullptr) {
+	u32 at = at_io;
 	float a_to_b[9]; rel_rotation(A.t.q, B.t.q, a_to_b);
 	float3 sa = A.s, sb = B.s;
 	f3 delta = mk3(A.t.p.x - B.t.p.x, A.t.p.y - B.t.p.y, A.t.p.z - B.t.p.z);
@@ -718,6 +735,7 @@ NB_DEV int bb_face_or_edge(const BoxIn& A, const BoxIn& B, float face_penetratio
 	mask &= penetration_mask;
 	n_out = __popc(mask);
 	if (!EMIT) return 1;
+	if (reserve) { at = warp_reserve(reserve, n_out); at_io = at; }
 
 	// labels: nudge.cpp:1902-1970
 	u32 a_sign_face_bit = b_offset_neg ? (1u << a_face) : 0;
@@ -908,64 +926,107 @@ NB_DEV BoxIn load_box(const nb_transform* world_xf, const nb_box_collider* box_d
 	return b;
 }
 
-// One thread per live pair.  EMIT=false: counts[3][stride] (face, edge, other).  EMIT=true: writes staged contacts.
-template<bool EMIT>
-__global__ void __launch_bounds__(NB_BLOCK) k_narrowphase(const uint2* live, u32 nboxes, const nb_transform* world_xf, const nb_box_collider* box_data,
-		const nb_sphere_collider* sph_data, const u32* col_tag, u32* cnt, const u32* offs, u32 stride, ContactOut out, u32 max_contacts, u32* counts) {
+// The narrowphase runs in three thread-per-pair passes so that the expensive face clipping only runs on dense warps:
+//   k_np_faces  every live pair: box-box -> pass 1 (face SAT, cheap, rejects ~85 %); sphere pairs -> the whole (cheap) test
+//   k_np_clip   surviving box-box pairs (compacted): pass 2 (+ pass 3 for edge contacts) -> contacts in a scratch buffer + counts
+//   k_np_emit   moves the scratch contacts (and computes the sphere contacts) to the scanned offsets, in the reference's contact order
+//               (box-box face contacts, box-box edge contacts, box-sphere, sphere-sphere: nudge.cpp:3753-3786)
+enum { CNT_SURV = CNT_LARGE + 1, CNT_TMP };
+
+__global__ void __launch_bounds__(NB_BLOCK) k_np_faces(const uint2* live, u32 nboxes, const nb_transform* world_xf, const nb_box_collider* box_data,
+		const nb_sphere_collider* sph_data, const u32* col_tag, u32* cnt /*[4][stride]: face, edge, other, survivor*/, u32 stride, float* np_pen, u32* np_info, u32* counts) {
 	u32 n = counts[CNT_LIVE_TOTAL];
 	u32 n_bb = counts[CNT_LIVE0], n_bs_end = n_bb + counts[CNT_LIVE1] + counts[CNT_LIVE2];
-	u32 face_total = 0, edge_base = 0, other_base = 0;
-	if (EMIT) {
-		face_total = counts[CNT_FACE]; edge_base = face_total; other_base = face_total + counts[CNT_EDGE];
-		if (blockIdx.x == 0 && threadIdx.x == 0) {
-			u32 staged = other_base + counts[CNT_OTHER];
-			if (staged > max_contacts) { atomicOr(&counts[CNT_OVERFLOW], OVF_CONTACTS); staged = max_contacts; }
-			counts[CNT_STAGED] = staged;
-		}
-	}
 	for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-		if (EMIT && (cnt[0*stride + j] | cnt[1*stride + j] | cnt[2*stride + j]) == 0) continue;  // the counting pass found nothing for this pair
 		uint2 pr = live[j];  // x = low half, y = high half of the reference's pair word
-		u32 nf = 0, ne = 0, no = 0;
+		u32 surv = 0, other = 0;
 		if (j < n_bb) {
 			BoxIn A = load_box(world_xf, box_data, col_tag, pr.x), B = load_box(world_xf, box_data, col_tag, pr.y);  // a = low, b = high (nudge.cpp:1202-1203)
 			float pen; u32 face; bool swapped;
-			if (bb_faces(A, B, pen, face, swapped)) {
-				if (swapped) { BoxIn t = A; A = B; B = t; }
-				float epen; u32 efeat; bool eswap; u32 cnt_face = 0;
-				u32 at = EMIT ? offs[0*stride + j] : 0;
-				int kind = bb_face_or_edge<EMIT>(A, B, pen, face, out, at, max_contacts, cnt_face, epen, efeat, eswap);
-				if (kind == 1) nf = cnt_face;
-				else if (kind == 2) {
-					ne = 1;
-					if (EMIT) {
-						u32 eat = edge_base + offs[1*stride + j];
-						if (eswap) { BoxIn t = A; A = B; B = t; }
-						if (eat < max_contacts) bb_edge(A, B, epen, efeat, out, eat);
-					}
-				}
-			}
+			if (bb_faces(A, B, pen, face, swapped)) { surv = 1; np_pen[j] = pen; np_info[j] = face | (swapped ? 4u : 0u); }
 		}
 		else {
 			float o[7];
-			bool hit;
 			u32 a = pr.y, b = pr.x;  // a = high half, b = low half (nudge.cpp:3759-3760, 3775-3776)
 			xform ta = ld_xform(world_xf, a), tb = ld_xform(world_xf, b);
-			if (j < n_bs_end) {
-				float4 s = reinterpret_cast<const float4*>(box_data)[a];
-				hit = box_sphere(make_float3(s.x, s.y, s.z), sph_data[b - nboxes].radius, ta, tb, o);
-			}
+			bool hit;
+			if (j < n_bs_end) { float4 sz = reinterpret_cast<const float4*>(box_data)[a]; hit = box_sphere(make_float3(sz.x, sz.y, sz.z), sph_data[b - nboxes].radius, ta, tb, o); }
 			else hit = sphere_sphere(sph_data[a - nboxes].radius, sph_data[b - nboxes].radius, ta, tb, o);
-			if (hit) {
-				no = 1;
-				if (EMIT) {
-					u32 at = other_base + offs[2*stride + j];
-					if (at < max_contacts)
-						put_contact(out, at, o[0], o[1], o[2], o[3], o[4], o[5], o[6], asu(ta.p.w), asu(tb.p.w), (u64)col_tag[a] | ((u64)col_tag[b] << 32), 0);  // nudge.cpp:3767, 3784
-				}
-			}
+			other = hit ? 1u : 0u;
 		}
-		if (!EMIT) { cnt[0*stride + j] = nf; cnt[1*stride + j] = ne; cnt[2*stride + j] = no; }
+		cnt[0*stride + j] = 0; cnt[1*stride + j] = 0; cnt[2*stride + j] = other; cnt[3*stride + j] = surv;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) counts[CNT_TMP] = 0;
+}
+
+__global__ void __launch_bounds__(NB_BLOCK) k_np_list(const u32* cnt, const u32* offs, u32 stride, u32* np_list, const u32* counts) {
+	u32 n = counts[CNT_LIVE0];
+	for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+		if (cnt[3*stride + j]) np_list[offs[3*stride + j]] = j;
+}
+
+// Clips the surviving box-box pairs ONCE: the contacts go to a scratch contact buffer in arrival order (np_start[j] = first slot),
+// and k_np_emit moves them to their final, pair-ordered place after the scan.
+__global__ void __launch_bounds__(NB_BLOCK) k_np_clip(const uint2* live, const u32* np_list, const float* np_pen, const u32* np_info, const nb_transform* world_xf,
+		const nb_box_collider* box_data, const u32* col_tag, u32* cnt, u32 stride, ContactOut tmp, u32* np_start, u32 max_contacts, u32* counts) {
+	u32 n = counts[CNT_SURV];
+	for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		u32 j = np_list[k];
+		uint2 pr = live[j];
+		u32 info = np_info[j];
+		BoxIn A = load_box(world_xf, box_data, col_tag, (info & 4) ? pr.y : pr.x), B = load_box(world_xf, box_data, col_tag, (info & 4) ? pr.x : pr.y);  // a owns the best face (nudge.cpp:1381-1387)
+		float epen; u32 efeat; bool eswap; u32 nface = 0, at = 0;
+		int kind = bb_face_or_edge<true>(A, B, np_pen[j], info & 3, tmp, at, max_contacts, nface, epen, efeat, eswap, &counts[CNT_TMP]);
+		if (kind == 2) {
+			at = warp_reserve(&counts[CNT_TMP], 1);
+			if (eswap) { BoxIn t = A; A = B; B = t; }
+			if (at < max_contacts) bb_edge(A, B, epen, efeat, tmp, at);
+		}
+		np_start[j] = at;
+		cnt[0*stride + j] = kind == 1 ? nface : 0;
+		cnt[1*stride + j] = kind == 2 ? 1u : 0u;
+	}
+}
+
+NB_DEV void move_contact(const ContactOut& from, u32 src, const ContactOut& to, u32 dst) {
+	to.data[2*dst + 0] = from.data[2*src + 0]; to.data[2*dst + 1] = from.data[2*src + 1];
+	to.bodies[dst] = from.bodies[src]; to.tags[dst] = from.tags[src]; to.features[dst] = from.features[src];
+}
+
+__global__ void __launch_bounds__(NB_BLOCK) k_np_emit(const uint2* live, const u32* np_list, const u32* np_start, ContactOut tmp, u32 nboxes, const nb_transform* world_xf,
+		const nb_box_collider* box_data, const nb_sphere_collider* sph_data, const u32* col_tag, const u32* cnt, const u32* offs, u32 stride,
+		ContactOut out, u32 max_contacts, u32* counts) {
+	const u32 n_surv = counts[CNT_SURV], n_bb = counts[CNT_LIVE0], n_all = counts[CNT_LIVE_TOTAL];
+	const u32 n_bs_end = n_bb + counts[CNT_LIVE1] + counts[CNT_LIVE2];
+	const u32 edge_base = counts[CNT_FACE], other_base = edge_base + counts[CNT_EDGE];
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		u32 staged = other_base + counts[CNT_OTHER];
+		if (staged > max_contacts || counts[CNT_TMP] > max_contacts) { atomicOr(&counts[CNT_OVERFLOW], OVF_CONTACTS); staged = min(staged, max_contacts); }
+		counts[CNT_STAGED] = staged;
+	}
+	const u32 total = n_surv + (n_all - n_bb);
+	for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		if (t < n_surv) {
+			u32 j = np_list[t];
+			u32 nf = cnt[0*stride + j], ne = cnt[1*stride + j];
+			if (!(nf | ne)) continue;
+			u32 src = np_start[j], dst = nf ? offs[0*stride + j] : edge_base + offs[1*stride + j];
+			for (u32 i = 0; i < nf + ne; ++i)
+				if (src + i < max_contacts && dst + i < max_contacts) move_contact(tmp, src + i, out, dst + i);
+		}
+		else {
+			u32 j = n_bb + (t - n_surv);
+			if (!cnt[2*stride + j]) continue;
+			uint2 pr = live[j];
+			float o[7];
+			u32 a = pr.y, b = pr.x;
+			xform ta = ld_xform(world_xf, a), tb = ld_xform(world_xf, b);
+			if (j < n_bs_end) { float4 sz = reinterpret_cast<const float4*>(box_data)[a]; box_sphere(make_float3(sz.x, sz.y, sz.z), sph_data[b - nboxes].radius, ta, tb, o); }
+			else sphere_sphere(sph_data[a - nboxes].radius, sph_data[b - nboxes].radius, ta, tb, o);
+			u32 at = other_base + offs[2*stride + j];
+			if (at < max_contacts)
+				put_contact(out, at, o[0], o[1], o[2], o[3], o[4], o[5], o[6], asu(ta.p.w), asu(tb.p.w), (u64)col_tag[a] | ((u64)col_tag[b] << 32), 0);  // nudge.cpp:3767, 3784
+		}
 	}
 }
 

@@ -235,22 +235,6 @@ __global__ void __launch_bounds__(1024) k_sort_offsets(u32* hist /*[256][NB_SORT
 	}
 }
 
-struct SortBuffers { u64* keys[2]; u32* vals[2]; u32* hist; u32* block_sums; };
-
-// Sorts bits [begin_bit, end_bit) of keys[cur] (+vals[cur]); returns which buffer (0/1) holds the result.
-static int nb_radix_sort(const Launch& L, const SortBuffers& B, const u32* n_ptr, int begin_bit, int end_bit, bool has_vals, int cur) {
-	for (int shift = begin_bit; shift < end_bit; shift += 8) {
-		k_sort_hist<<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], n_ptr, (u32)shift, B.hist);
-		*L.counter += 1;
-		k_sort_offsets<<<256, 1024, 0, L.stream>>>(B.hist, B.block_sums);
-		if (has_vals) k_sort_scatter<true><<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], B.keys[cur ^ 1], B.vals[cur], B.vals[cur ^ 1], n_ptr, (u32)shift, B.hist, B.block_sums);
-		else k_sort_scatter<false><<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], B.keys[cur ^ 1], nullptr, nullptr, n_ptr, (u32)shift, B.hist, B.block_sums);
-		*L.counter += 2;
-		cur ^= 1;
-	}
-	return cur;
-}
-
 // ---------------- grid-wide barrier for cooperative (co-resident) launches ----------------
 NB_DEV u32 ld_acquire_u32(const u32* p) {
 	u32 v;
@@ -274,6 +258,122 @@ NB_DEV void grid_barrier(u32* bar /* [0]=arrivals, [1]=generation */, u32 nblock
 		__threadfence();
 	}
 	__syncthreads();
+}
+
+// ---------------- single-launch radix sort (cooperative) ----------------
+// All passes of one sort in ONE cooperative launch: NB_CS_BLOCKS blocks of 1024 threads, two grid barriers per pass
+// (block histograms | offsets + scatter).  Every block derives its own scatter offsets from the [block][digit] histogram
+// matrix (151 KB, L2 resident), so there is no separate offsets kernel.  Small inputs (n <= NB_CS_SMALL) are sorted by
+// block 0 alone with block-level barriers; n == 0 costs one empty launch.  Same stable LSD order as nb_radix_sort.
+#define NB_CS_THREADS 1024
+#define NB_CS_WARPS 32
+#define NB_CS_SMALL 16384
+struct SortPasses { int n; int shift[12]; };
+
+template<bool HAS_VALS>
+__global__ void __launch_bounds__(NB_CS_THREADS) k_sort_coop(u64* k0, u64* k1, u32* v0, u32* v1, const u32* n_ptr, u32* hist /*[gridDim][256]*/, u32* bar, SortPasses P) {
+	__shared__ u32 h[256];
+	__shared__ u32 part[4][256];
+	__shared__ u32 running[256];
+	__shared__ u32 chunk_base[256];
+	__shared__ u32 wc[NB_CS_WARPS][256];
+	__shared__ u32 sm[NB_WARPS + 1];
+	const u32 n = *n_ptr;
+	if (n == 0) return;
+	const bool small = n <= NB_CS_SMALL;
+	if (small && blockIdx.x != 0) return;
+	const u32 G = small ? 1u : gridDim.x, b = blockIdx.x;
+	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	u32 chunks = (n + NB_CS_THREADS - 1) / NB_CS_THREADS, per = (chunks + G - 1) / G;
+	const u32 begin = min(n, b * per * NB_CS_THREADS), end = min(n, begin + per * NB_CS_THREADS);
+	u64* kin = k0; u64* kout = k1; u32* vin = v0; u32* vout = v1;
+	for (int p = 0; p < P.n; ++p) {
+		const u32 shift = (u32)P.shift[p];
+		if (tid < 256) h[tid] = 0;
+		__syncthreads();
+		for (u32 i = begin + tid; i < end; i += NB_CS_THREADS) atomicAdd(&h[(u32)(kin[i] >> shift) & 0xff], 1u);
+		__syncthreads();
+		if (!small) {
+			if (tid < 256) hist[b * 256 + tid] = h[tid];
+			grid_barrier(bar, G);
+			// digit d = tid & 255; quarter q sums rows q, q+4, ...: below-me prefix and total
+			u32 d = tid & 255, q = tid >> 8, below = 0, total = 0;
+			for (u32 r = q; r < G; r += 4) { u32 v = __ldcg(&hist[r * 256 + d]); total += v; if (r < b) below += v; }
+			part[q][d] = below; wc[q][d] = total;
+			__syncthreads();
+			if (tid < 256) { h[tid] = wc[0][tid] + wc[1][tid] + wc[2][tid] + wc[3][tid]; chunk_base[tid] = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]; }
+			__syncthreads();
+		}
+		else if (tid < 256) chunk_base[tid] = 0;
+		{	// exclusive scan of the 256 digit totals (threads 0..255 = warps 0..7)
+			u32 t = tid < 256 ? h[tid] : 0;
+			u32 incl = warp_incl_scan(t);
+			if (tid < 256 && lane == 31) sm[wid] = incl;
+			__syncthreads();
+			if (wid == 0) { u32 w = lane < 8 ? sm[lane] : 0; u32 wi = warp_incl_scan(w); if (lane < 8) sm[lane] = wi - w; }
+			__syncthreads();
+			if (tid < 256) running[tid] = incl - t + sm[wid] + chunk_base[tid];
+			__syncthreads();
+		}
+		for (u32 base = begin; base < end; base += NB_CS_THREADS) {
+			u32 i = base + tid;
+			bool valid = i < end;
+			u64 key = valid ? kin[i] : 0;
+			u32 val = (HAS_VALS && valid) ? vin[i] : 0;
+			u32 d = valid ? ((u32)(key >> shift) & 0xff) : 0xffffffffu;
+			u32 peers = __match_any_sync(0xffffffffu, d);
+			u32 rank = __popc(peers & ((1u << lane) - 1u));
+			for (u32 w = tid; w < NB_CS_WARPS * 256; w += NB_CS_THREADS) (&wc[0][0])[w] = 0;
+			__syncthreads();
+			if (valid && rank == 0) wc[wid][d] = __popc(peers);
+			__syncthreads();
+			if (tid < 256) {
+				u32 sum = 0;
+				#pragma unroll
+				for (int w = 0; w < NB_CS_WARPS; ++w) { u32 c = wc[w][tid]; wc[w][tid] = sum; sum += c; }
+				u32 r0 = running[tid];
+				chunk_base[tid] = r0;
+				running[tid] = r0 + sum;
+			}
+			__syncthreads();
+			if (valid) {
+				u32 pos = chunk_base[d] + wc[wid][d] + rank;
+				kout[pos] = key;
+				if (HAS_VALS) vout[pos] = val;
+			}
+			__syncthreads();
+		}
+		if (!small) grid_barrier(bar, G);
+		else { __threadfence(); __syncthreads(); }
+		{ u64* t = kin; kin = kout; kout = t; u32* tv = vin; vin = vout; vout = tv; }
+	}
+}
+
+struct SortBuffers { u64* keys[2]; u32* vals[2]; u32* hist; u32* block_sums; u32* bar; int coop_blocks; /* 0 = three launches per pass */ };
+
+// Sorts bits [begin_bit, end_bit) of keys[cur] (+vals[cur]); returns which buffer (0/1) holds the result.
+static int nb_radix_sort(const Launch& L, const SortBuffers& B, const u32* n_ptr, int begin_bit, int end_bit, bool has_vals, int cur, int begin_bit2 = 0, int end_bit2 = 0) {
+	if (B.coop_blocks) {
+		SortPasses P; P.n = 0;
+		for (int shift = begin_bit; shift < end_bit; shift += 8) P.shift[P.n++] = shift;
+		for (int shift = begin_bit2; shift < end_bit2; shift += 8) P.shift[P.n++] = shift;
+		u64* k0 = B.keys[cur]; u64* k1 = B.keys[cur ^ 1]; u32* v0 = B.vals[cur]; u32* v1 = B.vals[cur ^ 1]; u32* hist = B.hist; u32* bar = B.bar;
+		void* args[] = { &k0, &k1, &v0, &v1, &n_ptr, &hist, &bar, &P };
+		cudaLaunchCooperativeKernel(has_vals ? (void*)k_sort_coop<true> : (void*)k_sort_coop<false>, dim3(B.coop_blocks), dim3(NB_CS_THREADS), args, 0, L.stream);
+		*L.counter += 1;
+		return cur ^ (P.n & 1);
+	}
+	if (end_bit2 > begin_bit2) { cur = nb_radix_sort(L, B, n_ptr, begin_bit, end_bit, has_vals, cur); begin_bit = begin_bit2; end_bit = end_bit2; }
+	for (int shift = begin_bit; shift < end_bit; shift += 8) {
+		k_sort_hist<<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], n_ptr, (u32)shift, B.hist);
+		*L.counter += 1;
+		k_sort_offsets<<<256, 1024, 0, L.stream>>>(B.hist, B.block_sums);
+		if (has_vals) k_sort_scatter<true><<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], B.keys[cur ^ 1], B.vals[cur], B.vals[cur ^ 1], n_ptr, (u32)shift, B.hist, B.block_sums);
+		else k_sort_scatter<false><<<NB_SORT_GRID, NB_BLOCK, 0, L.stream>>>(B.keys[cur], B.keys[cur ^ 1], nullptr, nullptr, n_ptr, (u32)shift, B.hist, B.block_sums);
+		*L.counter += 2;
+		cur ^= 1;
+	}
+	return cur;
 }
 
 // ---------------- warp-aggregated append ----------------

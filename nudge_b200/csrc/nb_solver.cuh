@@ -39,6 +39,18 @@ __global__ void __launch_bounds__(NB_BLOCK) k_tag_keys_pair(const u64* tags, con
 	}
 }
 
+// Contacts produced by nb_collide carry feature words whose four bytes are each 0..7 or 0xff (nudge.cpp:1902-1970, 2381-2390;
+// sphere contacts: 0), so byte & 15 keeps their order and the whole tag fits one key: B | A | 16 feature bits.
+__global__ void __launch_bounds__(NB_BLOCK) k_tag_keys_packed(const u64* tags, const u32* features, u64* keys, u32* vals, u32 tagbits, const u32* counts) {
+	u32 n = counts[CNT_CONTACTS];
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		u64 t = tags[i]; u32 f = features[i];
+		u32 f16 = (f & 0xf) | ((f >> 4) & 0xf0) | ((f >> 8) & 0xf00) | ((f >> 12) & 0xf000);
+		keys[i] = ((((t >> 32) << tagbits) | (t & 0xffffffffu)) << 16) | f16;
+		vals[i] = i;
+	}
+}
+
 // impulses[c] = cache entry with the same tag, else zero; the lower bound is the entry the reference's merge stops at
 __global__ void __launch_bounds__(NB_BLOCK) k_cache_lookup(const u64* tags, const u32* features, const u64* cache_tags, const u32* cache_features,
 														   const float4* cache_data, float4* impulses, const u32* counts) {

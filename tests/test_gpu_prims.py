@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 def test_scan_and_sort_match_numpy():
     g = nudge_b200.Sim(scenes.box_drop(70000))
     rng = np.random.default_rng(1)
-    for n in [0, 1, 255, 256, 257, 1000, 151552, 151553, 435499, 1000000]:
+    for n in [0, 1, 255, 256, 257, 1000, 16384, 16385, 40000, 151552, 151553, 435499, 1000000]:
         d = rng.integers(0, 5, n).astype(np.uint32)
         out, tot = g.device_scan(d)
         ref = np.concatenate([[0], np.cumsum(d)[:-1]]).astype(np.uint32) if n else d
