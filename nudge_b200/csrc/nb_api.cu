@@ -26,6 +26,7 @@ struct nb_context {
 	u32 cstride;   // row plane stride
 	u32 slots_per_bucket;
 	int coop_blocks_solve;
+	u32* chain_start; u32* chain_len;  // per body: first entry / number of entries in the (body, batch) chain sort
 	bool contacts_internal;  // the current contact set came from nb_collide (not nb_upload_contacts)
 	u32 solve_backoff_ns;
 
@@ -182,7 +183,7 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ALLOC(ctx->slot_of, C); ALLOC(ctx->slot_done, 16 * (size_t)ctx->slots_per_bucket); ALLOC(ctx->slot_left, 16 * (size_t)ctx->slots_per_bucket);
 	ALLOC(ctx->left_count, 16); ALLOC(ctx->batch_of, C); ALLOC(ctx->slot_idx, C); ALLOC(ctx->mw, 2 * (size_t)B); ALLOC(ctx->cab, C); ALLOC(ctx->back, C);
 	ALLOC(ctx->rows.plane, (size_t)ROW_PLANES_TOTAL * ctx->cstride); ALLOC(ctx->rows.state, 3 * (size_t)ctx->cstride);
-	ALLOC(ctx->rows.a, ctx->cstride); ALLOC(ctx->rows.b, ctx->cstride); ALLOC(ctx->rows.contact, ctx->cstride); ALLOC(ctx->rows.wait, 2 * (size_t)ctx->cstride);
+	ALLOC(ctx->rows.a, ctx->cstride); ALLOC(ctx->rows.b, ctx->cstride); ALLOC(ctx->rows.contact, ctx->cstride); ALLOC(ctx->rows.wait, 2 * (size_t)ctx->cstride); ALLOC(ctx->chain_start, B); ALLOC(ctx->chain_len, B);
 	ctx->rows.stride = ctx->cstride;
 	ctx->pair_keys = ctx->sb.keys[0];
 	ctx->pair_keys_debug = nullptr; ctx->debug = 0;
@@ -200,8 +201,8 @@ int nb_create(const nb_config* config, nb_context** out) {
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, NB_BLOCK, 0));
 	if (per_sm < 1) { ctx->error = "k_solve does not fit on an SM"; return NB_ERR_CUDA; }
 	if (const char* e = getenv("NB_SOLVE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
-	ctx->solve_backoff_ns = 0;
-	if (const char* e = getenv("NB_SOLVE_BACKOFF_NS")) ctx->solve_backoff_ns = (u32)atoi(e);
+	ctx->solve_backoff_ns = 150;  // sleep per missing application while a contact is >= 2 applications away (nanosleep may take up to 2x)
+	if (const char* e = getenv("NB_SOLVE_HOP_NS")) ctx->solve_backoff_ns = (u32)atoi(e);
 	ctx->coop_blocks_solve = ctx->sms * per_sm;  // all co-resident: the dataflow solver relies on it
 	CK(cudaDeviceSynchronize());
 	return NB_OK;
@@ -367,7 +368,7 @@ int nb_collide(nb_context* ctx, void* stream) {
 		CK(cudaMemsetAsync(ctx->table_keys, 0xff, sizeof(u64) * ((size_t)ctx->table_mask + 1), st));
 		k_grid_setup<<<1, 1, 0, st>>>(K, counts);
 		k_grid_build<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->order, T.mn[0], T.mx[0], ctx->mkeys, ctx->smallf, ctx->large_list, ctx->table_keys, ctx->table_vals, ctx->table_mask, counts);
-		k_grid_pairs<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->order, T.mn[0], T.mx[0], ctx->smallf, ctx->table_keys, ctx->table_vals, ctx->table_mask, ctx->kbits, ctx->sb.keys[0], ctx->cfg.max_pairs, counts);
+		k_grid_pairs<<<GRID((size_t)K * 32), NB_BLOCK, 0, st>>>(K, ctx->order, T.mn[0], T.mx[0], ctx->smallf, ctx->mkeys, ctx->table_keys, ctx->table_vals, ctx->table_mask, ctx->kbits, ctx->sb.keys[0], ctx->cfg.max_pairs, counts);
 		k_large_pairs<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->order, T.mn[0], T.mx[0], ctx->smallf, ctx->large_list, ctx->kbits, ctx->sb.keys[0], ctx->cfg.max_pairs, counts);
 		ctx->launches += 4;
 	}
@@ -505,7 +506,8 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 		ctx->offs, ctx->left_count, ctx->batch_of, ctx->slot_idx, ctx->rows.contact, ctx->cstride, ctx->sb.keys[0], ctx->sb.vals[0], ctx->batchbits, counts);
 	++ctx->launches;
 	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_ENTRIES, 0, (int)(ctx->bodybits + ctx->batchbits), true, 0);
-	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, ctx->slot_idx, ctx->rows.wait, ctx->cstride, counts);
+	k_chain_heads<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->batchbits, ctx->chain_start, ctx->chain_len, counts); ++ctx->launches;
+	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, ctx->slot_idx, ctx->chain_start, ctx->chain_len, ctx->rows.wait, ctx->cstride, counts);
 	k_build_rows<<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts);
 	ctx->launches += 2;
 	int r = launch_solve(ctx, 0, 1, st); if (r) return r;  // warm start (nudge.cpp:4563-4632)
@@ -570,7 +572,7 @@ int nb_debug_read(nb_context* ctx, const char* name, void* dst, size_t max_bytes
 		{ "row_contact", ctx->rows.contact, sizeof(u32) * 8 * c[CNT_BATCHES] },
 		{ "row_a", ctx->rows.a, sizeof(u32) * 8 * c[CNT_BATCHES] },
 		{ "row_b", ctx->rows.b, sizeof(u32) * 8 * c[CNT_BATCHES] },
-		{ "row_wait", ctx->rows.wait, sizeof(u32) * 2 * (size_t)ctx->cstride },
+		{ "row_wait", ctx->rows.wait, sizeof(uint2) * 2 * (size_t)ctx->cstride },
 		{ "row_planes", ctx->rows.plane, sizeof(float) * (size_t)ROW_PLANES * ctx->cstride },
 		{ "row_states", ctx->rows.state, sizeof(float) * 3 * (size_t)ctx->cstride },
 		{ "inertia", ctx->inertia, sizeof(float4) * 2 * ctx->B },

@@ -261,50 +261,98 @@ NB_DEV void grid_barrier(u32* bar /* [0]=arrivals, [1]=generation */, u32 nblock
 }
 
 // ---------------- single-launch radix sort (cooperative) ----------------
-// All passes of one sort in ONE cooperative launch: NB_CS_BLOCKS blocks of 1024 threads, two grid barriers per pass
-// (block histograms | offsets + scatter).  Every block derives its own scatter offsets from the [block][digit] histogram
-// matrix (151 KB, L2 resident), so there is no separate offsets kernel.  Small inputs (n <= NB_CS_SMALL) are sorted by
-// block 0 alone with block-level barriers; n == 0 costs one empty launch.  Same stable LSD order as nb_radix_sort.
+// All passes of one sort in ONE cooperative launch: one block of 1024 threads per SM, two grid barriers per pass.  A block owns a
+// contiguous range of 4096-key tiles.  Per pass: block digit histogram -> [block][digit] matrix (L2 resident) | barrier | every
+// block derives its own scatter offsets from the matrix, ranks its tiles (match_any per warp, 4 keys per thread) and scatters |
+// barrier.  When every block owns at most one tile (n <= 4096 * blocks) the keys stay in registers between the histogram and
+// the scatter.  Small inputs (n <= NB_CS_SMALL) are sorted by block 0 alone with block-level barriers; n == 0 costs one empty
+// launch.  Same stable LSD order as nb_radix_sort.
 #define NB_CS_THREADS 1024
 #define NB_CS_WARPS 32
-#define NB_CS_SMALL 16384
+#define NB_CS_ITEMS 4
+#define NB_CS_TILE (NB_CS_THREADS * NB_CS_ITEMS)
+#define NB_CS_SMALL (4 * NB_CS_TILE)
 struct SortPasses { int n; int shift[12]; };
 
 template<bool HAS_VALS>
 __global__ void __launch_bounds__(NB_CS_THREADS) k_sort_coop(u64* k0, u64* k1, u32* v0, u32* v1, const u32* n_ptr, u32* hist /*[gridDim][256]*/, u32* bar, SortPasses P) {
-	__shared__ u32 h[256];
-	__shared__ u32 part[4][256];
-	__shared__ u32 running[256];
-	__shared__ u32 chunk_base[256];
+	__shared__ u32 h[256];        // digit totals of this block's range, then of the whole input
+	__shared__ u32 tot[256];      // digit totals of the current tile
+	__shared__ u32 running[256];  // next free output slot per digit for this block
+	__shared__ u32 below[4][256], total[4][256];
 	__shared__ u32 wc[NB_CS_WARPS][256];
-	__shared__ u32 sm[NB_WARPS + 1];
+	__shared__ u32 sm[8];
 	const u32 n = *n_ptr;
 	if (n == 0) return;
 	const bool small = n <= NB_CS_SMALL;
 	if (small && blockIdx.x != 0) return;
 	const u32 G = small ? 1u : gridDim.x, b = blockIdx.x;
-	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	u32 chunks = (n + NB_CS_THREADS - 1) / NB_CS_THREADS, per = (chunks + G - 1) / G;
-	const u32 begin = min(n, b * per * NB_CS_THREADS), end = min(n, begin + per * NB_CS_THREADS);
+	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lt = (1u << lane) - 1u;
+	const u32 tiles = (n + NB_CS_TILE - 1) / NB_CS_TILE, per = (tiles + G - 1) / G;
+	const u32 begin = min(n, b * per * NB_CS_TILE), end = min(n, begin + per * NB_CS_TILE);
+	const bool fused = per == 1;
 	u64* kin = k0; u64* kout = k1; u32* vin = v0; u32* vout = v1;
+	u64 key[NB_CS_ITEMS]; u32 val[NB_CS_ITEMS], dg[NB_CS_ITEMS], rk[NB_CS_ITEMS];
+
 	for (int p = 0; p < P.n; ++p) {
 		const u32 shift = (u32)P.shift[p];
-		if (tid < 256) h[tid] = 0;
+		// ranks one tile: key/val/dg/rk in registers, wc[w][d] = keys of digit d in warps before w, tot[d] = tile total
+		auto rank_tile = [&](u32 base) {
+			for (u32 w = tid; w < NB_CS_WARPS * 256; w += NB_CS_THREADS) (&wc[0][0])[w] = 0;
+			__syncthreads();
+			#pragma unroll
+			for (int r = 0; r < NB_CS_ITEMS; ++r) {
+				u32 i = base + wid * (32 * NB_CS_ITEMS) + r * 32 + lane;
+				bool valid = i < end;
+				key[r] = valid ? __ldcg(kin + i) : 0;
+				if (HAS_VALS) val[r] = valid ? __ldcg(vin + i) : 0;
+				u32 d = valid ? ((u32)(key[r] >> shift) & 0xff) : 0xffffffffu;
+				u32 peers = __match_any_sync(0xffffffffu, d);
+				u32 leader = __ffs(peers) - 1, old = 0;
+				if (valid && lane == leader) { old = wc[wid][d]; wc[wid][d] = old + __popc(peers); }
+				old = __shfl_sync(0xffffffffu, old, leader);
+				dg[r] = d; rk[r] = old + __popc(peers & lt);
+				__syncwarp();
+			}
+			__syncthreads();
+			if (tid < 256) {
+				u32 sum = 0;
+				#pragma unroll 8
+				for (int w = 0; w < NB_CS_WARPS; ++w) { u32 c = wc[w][tid]; wc[w][tid] = sum; sum += c; }
+				tot[tid] = sum;
+			}
+			__syncthreads();
+		};
+		auto scatter_tile = [&]() {
+			#pragma unroll
+			for (int r = 0; r < NB_CS_ITEMS; ++r)
+				if (dg[r] != 0xffffffffu) {
+					u32 pos = running[dg[r]] + wc[wid][dg[r]] + rk[r];
+					kout[pos] = key[r];
+					if (HAS_VALS) vout[pos] = val[r];
+				}
+		};
+
+		if (fused) {
+			rank_tile(begin);
+			if (tid < 256) h[tid] = tot[tid];
+		}
+		else {
+			if (tid < 256) h[tid] = 0;
+			__syncthreads();
+			for (u32 i = begin + tid; i < end; i += NB_CS_THREADS) atomicAdd(&h[(u32)(__ldcg(kin + i) >> shift) & 0xff], 1u);
+		}
 		__syncthreads();
-		for (u32 i = begin + tid; i < end; i += NB_CS_THREADS) atomicAdd(&h[(u32)(kin[i] >> shift) & 0xff], 1u);
-		__syncthreads();
+		u32 mine = 0;  // keys of digit tid in blocks before this one
 		if (!small) {
 			if (tid < 256) hist[b * 256 + tid] = h[tid];
 			grid_barrier(bar, G);
-			// digit d = tid & 255; quarter q sums rows q, q+4, ...: below-me prefix and total
-			u32 d = tid & 255, q = tid >> 8, below = 0, total = 0;
-			for (u32 r = q; r < G; r += 4) { u32 v = __ldcg(&hist[r * 256 + d]); total += v; if (r < b) below += v; }
-			part[q][d] = below; wc[q][d] = total;
+			u32 d = tid & 255, q = tid >> 8, bl = 0, tt = 0;
+			for (u32 r = q; r < G; r += 4) { u32 v = __ldcg(&hist[r * 256 + d]); tt += v; if (r < b) bl += v; }
+			below[q][d] = bl; total[q][d] = tt;
 			__syncthreads();
-			if (tid < 256) { h[tid] = wc[0][tid] + wc[1][tid] + wc[2][tid] + wc[3][tid]; chunk_base[tid] = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]; }
-			__syncthreads();
+			if (tid < 256) { h[tid] = total[0][tid] + total[1][tid] + total[2][tid] + total[3][tid]; mine = below[0][tid] + below[1][tid] + below[2][tid] + below[3][tid]; }
 		}
-		else if (tid < 256) chunk_base[tid] = 0;
 		{	// exclusive scan of the 256 digit totals (threads 0..255 = warps 0..7)
 			u32 t = tid < 256 ? h[tid] : 0;
 			u32 incl = warp_incl_scan(t);
@@ -312,37 +360,17 @@ __global__ void __launch_bounds__(NB_CS_THREADS) k_sort_coop(u64* k0, u64* k1, u
 			__syncthreads();
 			if (wid == 0) { u32 w = lane < 8 ? sm[lane] : 0; u32 wi = warp_incl_scan(w); if (lane < 8) sm[lane] = wi - w; }
 			__syncthreads();
-			if (tid < 256) running[tid] = incl - t + sm[wid] + chunk_base[tid];
+			if (tid < 256) running[tid] = incl - t + sm[wid] + mine;
 			__syncthreads();
 		}
-		for (u32 base = begin; base < end; base += NB_CS_THREADS) {
-			u32 i = base + tid;
-			bool valid = i < end;
-			u64 key = valid ? kin[i] : 0;
-			u32 val = (HAS_VALS && valid) ? vin[i] : 0;
-			u32 d = valid ? ((u32)(key >> shift) & 0xff) : 0xffffffffu;
-			u32 peers = __match_any_sync(0xffffffffu, d);
-			u32 rank = __popc(peers & ((1u << lane) - 1u));
-			for (u32 w = tid; w < NB_CS_WARPS * 256; w += NB_CS_THREADS) (&wc[0][0])[w] = 0;
-			__syncthreads();
-			if (valid && rank == 0) wc[wid][d] = __popc(peers);
-			__syncthreads();
-			if (tid < 256) {
-				u32 sum = 0;
-				#pragma unroll
-				for (int w = 0; w < NB_CS_WARPS; ++w) { u32 c = wc[w][tid]; wc[w][tid] = sum; sum += c; }
-				u32 r0 = running[tid];
-				chunk_base[tid] = r0;
-				running[tid] = r0 + sum;
+		if (fused) scatter_tile();
+		else
+			for (u32 base = begin; base < end; base += NB_CS_TILE) {
+				rank_tile(base);
+				scatter_tile();
+				__syncthreads();
+				if (tid < 256) running[tid] += tot[tid];
 			}
-			__syncthreads();
-			if (valid) {
-				u32 pos = chunk_base[d] + wc[wid][d] + rank;
-				kout[pos] = key;
-				if (HAS_VALS) vout[pos] = val;
-			}
-			__syncthreads();
-		}
 		if (!small) grid_barrier(bar, G);
 		else { __threadfence(); __syncthreads(); }
 		{ u64* t = kin; kin = kout; kout = t; u32* tv = vin; vin = vout; vout = tv; }

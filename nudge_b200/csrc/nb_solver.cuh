@@ -400,29 +400,37 @@ __global__ void __launch_bounds__(NB_BLOCK) k_batch_index(const u32* sorted, con
 // For each contact side: the slot whose token it must see on that body before it may run.  In (body, batch) order the
 // predecessor is the previous entry of the same body; the first entry of a body waits for the body's LAST entry of the
 // previous sweep (flag bit 31).  Body 0 (static world) is never waited for.
-#define NB_WAIT_PREV 0x80000000u
-__global__ void __launch_bounds__(NB_BLOCK) k_waits(const u64* chain_keys, const u32* chain_vals, u32 batchbits, const u32* slot_idx, u32* wait /*[2][stride]*/, u32 stride, const u32* counts) {
+// Per body the solver keeps a sequence token = number of contact applications the body has received in this launch.  The
+// contact at position `seq` of a body's chain of length `len` therefore runs in sweep w when the token reads w*len + seq, and
+// leaves w*len + seq + 1.  (expected - seen) is the number of applications still ahead of a waiting contact, which is what the
+// solver's back-off sleeps on.  Body 0 (static world) is never waited for: its entries carry the key ~0.
+__global__ void __launch_bounds__(NB_BLOCK) k_chain_heads(const u64* chain_keys, u32 batchbits, u32* chain_start, u32* chain_len, const u32* counts) {
+	u32 n2 = counts[CNT_ENTRIES];
+	for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += gridDim.x * blockDim.x) {
+		u64 k = chain_keys[e];
+		if (k == ~(u64)0) continue;
+		u64 body = k >> batchbits;
+		if (e > 0 && (chain_keys[e - 1] >> batchbits) == body) continue;
+		u32 lo = e, hi = n2;  // first index with a larger body
+		while (lo < hi) { u32 mid = (lo + hi) >> 1; u64 km = chain_keys[mid]; if (km != ~(u64)0 && (km >> batchbits) <= body) lo = mid + 1; else hi = mid; }
+		chain_start[body] = e; chain_len[body] = lo - e;
+	}
+}
+__global__ void __launch_bounds__(NB_BLOCK) k_waits(const u64* chain_keys, const u32* chain_vals, u32 batchbits, const u32* slot_idx, const u32* chain_start, const u32* chain_len,
+		uint2* wait /*[2][stride]: seq, len*/, u32 stride, const u32* counts) {
 	u32 n2 = counts[CNT_ENTRIES];
 	for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += gridDim.x * blockDim.x) {
 		u64 k = chain_keys[e];
 		u32 v = chain_vals[e];
 		u32 slot = slot_idx[v >> 1], side = v & 1;
-		u32 w = NB_NONE;
-		if (k != ~(u64)0) {
-			u64 body = k >> batchbits;
-			if (e > 0 && (chain_keys[e - 1] >> batchbits) == body) w = slot_idx[chain_vals[e - 1] >> 1];
-			else {  // first of its body: find the end of the run
-				u32 lo = e, hi = n2;  // first index with a larger body
-				while (lo < hi) { u32 mid = (lo + hi) >> 1; u64 km = chain_keys[mid]; if (km != ~(u64)0 && (km >> batchbits) <= body) lo = mid + 1; else hi = mid; }
-				w = slot_idx[chain_vals[lo - 1] >> 1] | NB_WAIT_PREV;
-			}
-		}
+		uint2 w = make_uint2(0, 0);
+		if (k != ~(u64)0) { u32 body = (u32)(k >> batchbits); w = make_uint2(e - chain_start[body], chain_len[body]); }
 		if (slot < stride) wait[side * stride + slot] = w;
 	}
 }
 
 // ---------------- constraint rows (nudge.cpp:4350-4561), one thread per contact, SoA planes ----------------
-struct Rows { float* plane; u32 stride; u32* a; u32* b; u32* contact; float* state; u32* wait; };  // plane[k*stride + slot], wait[side*stride + slot]
+struct Rows { float* plane; u32 stride; u32* a; u32* b; u32* contact; float* state; uint2* wait; };  // plane[k*stride + slot], wait[side*stride + slot] = (seq, len)
 
 __global__ void __launch_bounds__(NB_BLOCK) k_build_rows(const float4* contacts, const uint2* bodies,
 		const nb_transform* xf, const float4* inertia, const nb_body_momentum* momentum, Rows R, const u32* counts) {
@@ -571,34 +579,35 @@ NB_DEV void warm_start_contact(const Rows& R, u32 j, const float4* impulses, flo
 }
 
 // One contact of one projected Gauss-Seidel sweep (nudge.cpp:4646-4853), same operation order, FMAs where the source has madd.
-NB_DEV void solve_contact(const Rows& R, u32 j, float4& al, float4& aw, float4& bl, float4& bw, const u32* s_rcp, const u32* s_rsqrt) {
-	const float* c = R.plane + j; const u32 S = R.stride;
-	float a_velocity_x = al.x, a_velocity_y = al.y, a_velocity_z = al.z, a_mass_inverse = c[MASS_A*S];
+// The rows arrive in registers (rv[], st[]): they are fetched BEFORE the contact starts waiting for its bodies.
+NB_DEV void solve_contact(const Rows& R, u32 j, const float (&rv)[ROW_PLANES_TOTAL], const float (&st)[3], float4& al, float4& aw, float4& bl, float4& bw, const u32* s_rcp, const u32* s_rsqrt) {
+	const u32 S = R.stride;
+	float a_velocity_x = al.x, a_velocity_y = al.y, a_velocity_z = al.z, a_mass_inverse = rv[MASS_A];
 	float a_angular_velocity_x = aw.x, a_angular_velocity_y = aw.y, a_angular_velocity_z = aw.z;
-	float b_velocity_x = bl.x, b_velocity_y = bl.y, b_velocity_z = bl.z, b_mass_inverse = c[MASS_B*S];
+	float b_velocity_x = bl.x, b_velocity_y = bl.y, b_velocity_z = bl.z, b_mass_inverse = rv[MASS_B];
 	float b_angular_velocity_x = bw.x, b_angular_velocity_y = bw.y, b_angular_velocity_z = bw.z;
-	float pa_z = c[PA_Z*S], pa_x = c[PA_X*S], pa_y = c[PA_Y*S];
+	float pa_z = rv[PA_Z], pa_x = rv[PA_X], pa_y = rv[PA_Y];
 	float v_xa = nb_madd(a_angular_velocity_y, pa_z, a_velocity_x);
 	float v_ya = nb_madd(a_angular_velocity_z, pa_x, a_velocity_y);
 	float v_za = nb_madd(a_angular_velocity_x, pa_y, a_velocity_z);
-	float pb_z = c[PB_Z*S], pb_x = c[PB_X*S], pb_y = c[PB_Y*S];
+	float pb_z = rv[PB_Z], pb_x = rv[PB_X], pb_y = rv[PB_Y];
 	float v_xb = nb_madd(b_angular_velocity_y, pb_z, b_velocity_x);
 	float v_yb = nb_madd(b_angular_velocity_z, pb_x, b_velocity_y);
 	float v_zb = nb_madd(b_angular_velocity_x, pb_y, b_velocity_z);
 	v_xa = nb_madd(b_angular_velocity_z, pb_y, v_xa);
 	v_ya = nb_madd(b_angular_velocity_x, pb_z, v_ya);
 	v_za = nb_madd(b_angular_velocity_y, pb_x, v_za);
-	float n_x = c[N_X*S], fu_x = c[U_X*S], fv_x = c[V_X*S];
+	float n_x = rv[N_X], fu_x = rv[U_X], fv_x = rv[V_X];
 	v_xb = nb_madd(a_angular_velocity_z, pa_y, v_xb);
 	v_yb = nb_madd(a_angular_velocity_x, pa_z, v_yb);
 	v_zb = nb_madd(a_angular_velocity_y, pa_x, v_zb);
-	float n_y = c[N_Y*S], fu_y = c[U_Y*S], fv_y = c[V_Y*S];
+	float n_y = rv[N_Y], fu_y = rv[U_Y], fv_y = rv[V_Y];
 	float v_x = v_xb - v_xa, v_y = v_yb - v_ya, v_z = v_zb - v_za;
 	float t_z = n_x * v_x, t_x = v_x * fu_x, t_y = v_x * fv_x;
-	float n_z = c[N_Z*S], fu_z = c[U_Z*S], fv_z = c[V_Z*S];
-	float normal_bias = c[BIAS*S];
-	float old_normal_impulse = R.state[0*S + j];
-	float normal_factor = c[NVTNI*S];
+	float n_z = rv[N_Z], fu_z = rv[U_Z], fv_z = rv[V_Z];
+	float normal_bias = rv[BIAS];
+	float old_normal_impulse = st[0];
+	float normal_factor = rv[NVTNI];
 	t_z = nb_madd(n_y, v_y, t_z); t_x = nb_madd(v_y, fu_y, t_x); t_y = nb_madd(v_y, fv_y, t_y);
 	normal_bias = normal_bias + old_normal_impulse;
 	t_z = nb_madd(n_z, v_z, t_z); t_x = nb_madd(v_z, fu_z, t_x); t_y = nb_madd(v_z, fv_z, t_y);
@@ -608,28 +617,28 @@ NB_DEV void solve_contact(const Rows& R, u32 j, float4& al, float4& aw, float4& 
 	normal_impulse = nb_max(normal_impulse, 0.0f);
 	t_x *= tl2; t_y *= tl2;
 	R.state[0*S + j] = normal_impulse;
-	float max_friction_impulse = normal_impulse * c[FRICTION*S];
+	float max_friction_impulse = normal_impulse * rv[FRICTION];
 	normal_impulse = normal_impulse - old_normal_impulse;
-	float friction_factor = t_xx * c[FC_X*S];
+	float friction_factor = t_xx * rv[FC_X];
 	float linear_impulse_x = n_x * normal_impulse;
-	friction_factor = nb_madd(t_yy, c[FC_Y*S], friction_factor);
+	friction_factor = nb_madd(t_yy, rv[FC_Y], friction_factor);
 	float linear_impulse_y = n_y * normal_impulse;
-	friction_factor = nb_madd(t_xy, c[FC_Z*S], friction_factor);
+	friction_factor = nb_madd(t_xy, rv[FC_Z], friction_factor);
 	float linear_impulse_z = n_z * normal_impulse;
 	friction_factor = nb_rcp_t(friction_factor, s_rcp);
-	a_angular_velocity_x = nb_madd(c[NA_X*S], normal_impulse, a_angular_velocity_x);
-	a_angular_velocity_y = nb_madd(c[NA_Y*S], normal_impulse, a_angular_velocity_y);
-	a_angular_velocity_z = nb_madd(c[NA_Z*S], normal_impulse, a_angular_velocity_z);
-	float old_friction_impulse_x = R.state[1*S + j], old_friction_impulse_y = R.state[2*S + j];
+	a_angular_velocity_x = nb_madd(rv[NA_X], normal_impulse, a_angular_velocity_x);
+	a_angular_velocity_y = nb_madd(rv[NA_Y], normal_impulse, a_angular_velocity_y);
+	a_angular_velocity_z = nb_madd(rv[NA_Z], normal_impulse, a_angular_velocity_z);
+	float old_friction_impulse_x = st[1], old_friction_impulse_y = st[2];
 	friction_factor = nb_min(1e+6f, friction_factor);  // first operand on NaN
 	float friction_impulse_x = t_x*friction_factor, friction_impulse_y = t_y*friction_factor;
 	friction_impulse_x = old_friction_impulse_x - friction_impulse_x;
 	friction_impulse_y = old_friction_impulse_y - friction_impulse_y;
 	float friction_clamp_scale = friction_impulse_x*friction_impulse_x + friction_impulse_y*friction_impulse_y;
 	friction_clamp_scale = nb_rsqrt_t(friction_clamp_scale, s_rsqrt);
-	b_angular_velocity_x = nb_madd(c[NB_X*S], normal_impulse, b_angular_velocity_x);
-	b_angular_velocity_y = nb_madd(c[NB_Y*S], normal_impulse, b_angular_velocity_y);
-	b_angular_velocity_z = nb_madd(c[NB_Z*S], normal_impulse, b_angular_velocity_z);
+	b_angular_velocity_x = nb_madd(rv[NB_X], normal_impulse, b_angular_velocity_x);
+	b_angular_velocity_y = nb_madd(rv[NB_Y], normal_impulse, b_angular_velocity_y);
+	b_angular_velocity_z = nb_madd(rv[NB_Z], normal_impulse, b_angular_velocity_z);
 	friction_clamp_scale = friction_clamp_scale * max_friction_impulse;
 	friction_clamp_scale = nb_min(1.0f, friction_clamp_scale);
 	friction_impulse_x = friction_impulse_x * friction_clamp_scale;
@@ -647,21 +656,21 @@ NB_DEV void solve_contact(const Rows& R, u32 j, float4& al, float4& aw, float4& 
 	al.x = nb_madd(linear_impulse_x, a_mass_inverse_neg, a_velocity_x);
 	al.y = nb_madd(linear_impulse_y, a_mass_inverse_neg, a_velocity_y);
 	al.z = nb_madd(linear_impulse_z, a_mass_inverse_neg, a_velocity_z);
-	a_angular_velocity_x = nb_madd(c[UA_X*S], friction_impulse_x, a_angular_velocity_x);
-	a_angular_velocity_y = nb_madd(c[UA_Y*S], friction_impulse_x, a_angular_velocity_y);
-	a_angular_velocity_z = nb_madd(c[UA_Z*S], friction_impulse_x, a_angular_velocity_z);
-	aw.x = nb_madd(c[VA_X*S], friction_impulse_y, a_angular_velocity_x);
-	aw.y = nb_madd(c[VA_Y*S], friction_impulse_y, a_angular_velocity_y);
-	aw.z = nb_madd(c[VA_Z*S], friction_impulse_y, a_angular_velocity_z);
+	a_angular_velocity_x = nb_madd(rv[UA_X], friction_impulse_x, a_angular_velocity_x);
+	a_angular_velocity_y = nb_madd(rv[UA_Y], friction_impulse_x, a_angular_velocity_y);
+	a_angular_velocity_z = nb_madd(rv[UA_Z], friction_impulse_x, a_angular_velocity_z);
+	aw.x = nb_madd(rv[VA_X], friction_impulse_y, a_angular_velocity_x);
+	aw.y = nb_madd(rv[VA_Y], friction_impulse_y, a_angular_velocity_y);
+	aw.z = nb_madd(rv[VA_Z], friction_impulse_y, a_angular_velocity_z);
 	bl.x = nb_madd(linear_impulse_x, b_mass_inverse, b_velocity_x);
 	bl.y = nb_madd(linear_impulse_y, b_mass_inverse, b_velocity_y);
 	bl.z = nb_madd(linear_impulse_z, b_mass_inverse, b_velocity_z);
-	b_angular_velocity_x = nb_madd(c[UB_X*S], friction_impulse_x, b_angular_velocity_x);
-	b_angular_velocity_y = nb_madd(c[UB_Y*S], friction_impulse_x, b_angular_velocity_y);
-	b_angular_velocity_z = nb_madd(c[UB_Z*S], friction_impulse_x, b_angular_velocity_z);
-	bw.x = nb_madd(c[VB_X*S], friction_impulse_y, b_angular_velocity_x);
-	bw.y = nb_madd(c[VB_Y*S], friction_impulse_y, b_angular_velocity_y);
-	bw.z = nb_madd(c[VB_Z*S], friction_impulse_y, b_angular_velocity_z);
+	b_angular_velocity_x = nb_madd(rv[UB_X], friction_impulse_x, b_angular_velocity_x);
+	b_angular_velocity_y = nb_madd(rv[UB_Y], friction_impulse_x, b_angular_velocity_y);
+	b_angular_velocity_z = nb_madd(rv[UB_Z], friction_impulse_x, b_angular_velocity_z);
+	bw.x = nb_madd(rv[VB_X], friction_impulse_y, b_angular_velocity_x);
+	bw.y = nb_madd(rv[VB_Y], friction_impulse_y, b_angular_velocity_y);
+	bw.z = nb_madd(rv[VB_Z], friction_impulse_y, b_angular_velocity_z);
 }
 
 // mode 0: warm start (one pass); mode 1: `sweeps` PGS sweeps.  Co-resident grid, no barrier.  Thread t owns slots t, t+T, ...
@@ -669,7 +678,11 @@ NB_DEV void solve_contact(const Rows& R, u32 j, float4& al, float4& aw, float4& 
 // items are visited in increasing (sweep, slot), which is a topological order of the dependency graph, so the lowest
 // unfinished item is always runnable.  Inside a warp the lanes poll instead of blocking, so a lane may depend on another
 // lane of its own warp.  mw must come from k_mw_in (all tokens 0).
-__global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impulses, float4* mw, int mode, u32 sweeps, u32 backoff_ns, u32* counts) {
+//
+// Waiting: the body's token says how many applications are still ahead of this contact (k_chain_heads).  While that number is
+// >= 2 on either body only the linear halves are polled, and the warp sleeps hop_ns per missing application when all of its
+// lanes are that far away; from 1 on, all four halves are fetched in one round trip so the hand-off costs a single L2 access.
+__global__ void __launch_bounds__(NB_BLOCK, 2) k_solve(Rows R, const float4* impulses, float4* mw, int mode, u32 sweeps, u32 hop_ns, u32* counts) {
 	__shared__ u32 s_rcp[2048];
 	__shared__ u32 s_rsqrt[2048];
 	for (u32 i = threadIdx.x; i < 2048; i += blockDim.x) { s_rcp[i] = g_rcp_lut[i]; s_rsqrt[i] = g_rsqrt_lut[i]; }
@@ -681,33 +694,42 @@ __global__ void __launch_bounds__(NB_BLOCK) k_solve(Rows R, const float4* impuls
 	for (u32 w = 0; w < passes; ++w)
 		for (u32 s0 = 0; s0 < NS; s0 += nth) {  // uniform trip count for the whole grid
 			u32 slot = s0 + tid;
-			bool pending = false;
-			u32 a = 0, b = 0, exp_a = 0, exp_b = 0, token = 0;
+			bool pending = false, near = false;
+			u32 a = 0, b = 0, exp_a = 0, exp_b = 0;
+			float rv[ROW_PLANES_TOTAL], st[3];
 			if (slot < NS && R.contact[slot] != NB_NONE) {
 				pending = true;
 				a = R.a[slot]; b = R.b[slot];
-				u32 wa = R.wait[slot], wb = R.wait[S + slot];
-				token = w * NS + slot + 1;
-				// expected token on each body: predecessor in this sweep, or the body's last contact of the previous sweep
-				exp_a = (wa & NB_WAIT_PREV) ? (w ? (w - 1) * NS + (wa & ~NB_WAIT_PREV) + 1 : 0) : w * NS + wa + 1;
-				exp_b = (wb & NB_WAIT_PREV) ? (w ? (w - 1) * NS + (wb & ~NB_WAIT_PREV) + 1 : 0) : w * NS + wb + 1;
+				uint2 wa = R.wait[slot], wb = R.wait[S + slot];
+				exp_a = w * wa.y + wa.x; exp_b = w * wb.y + wb.x;
+				if (mode) {
+					const float* c = R.plane + slot;
+					#pragma unroll
+					for (int k = 0; k < ROW_PLANES_TOTAL; ++k) rv[k] = c[(size_t)k * S];
+					st[0] = R.state[0*S + slot]; st[1] = R.state[1*S + slot]; st[2] = R.state[2*S + slot];
+				}
 			}
 			while (__any_sync(0xffffffffu, pending)) {
+				u32 want = 0xffffffffu;
 				if (pending) {
-					float4 al = ld128(mw + 2*a), aw = ld128(mw + 2*a + 1), bl = ld128(mw + 2*b), bw = ld128(mw + 2*b + 1);  // one round trip
-					{
-						bool ready = (!a || (asu(al.w) == exp_a && asu(aw.w) == exp_a)) && (!b || (asu(bl.w) == exp_b && asu(bw.w) == exp_b));
-						if (ready) {
-							if (mode) solve_contact(R, slot, al, aw, bl, bw, s_rcp, s_rsqrt);
-							else warm_start_contact(R, slot, impulses, al, aw, bl, bw, s_rsqrt);
-							float tk = asf(token);
-							if (a) { al.w = tk; aw.w = tk; st128(mw + 2*a, al); st128(mw + 2*a + 1, aw); }  // body 0 is static: never written
-							if (b) { bl.w = tk; bw.w = tk; st128(mw + 2*b, bl); st128(mw + 2*b + 1, bw); }
-							pending = false;
-						}
-						else if (backoff_ns) __nanosleep(backoff_ns);
+					float4 al = ld128(mw + 2*a), bl = ld128(mw + 2*b), aw, bw;
+					if (near) { aw = ld128(mw + 2*a + 1); bw = ld128(mw + 2*b + 1); }
+					u32 ra = a ? exp_a - asu(al.w) : 0, rb = b ? exp_b - asu(bl.w) : 0;
+					u32 r = max(ra, rb);
+					if (r == 0 && near && (!a || asu(aw.w) == exp_a) && (!b || asu(bw.w) == exp_b)) {
+						if (mode) solve_contact(R, slot, rv, st, al, aw, bl, bw, s_rcp, s_rsqrt);
+						else warm_start_contact(R, slot, impulses, al, aw, bl, bw, s_rsqrt);
+						if (a) { float tk = asf(exp_a + 1); al.w = tk; aw.w = tk; st128(mw + 2*a, al); st128(mw + 2*a + 1, aw); }  // body 0 is static: never written
+						if (b) { float tk = asf(exp_b + 1); bl.w = tk; bw.w = tk; st128(mw + 2*b, bl); st128(mw + 2*b + 1, bw); }
+						pending = false;
+					}
+					else {
+						near = r <= 1;
+						want = r >= 2 ? (r - 1) * hop_ns : 0;
 					}
 				}
+				want = __reduce_min_sync(0xffffffffu, want);
+				if (want != 0xffffffffu && want) __nanosleep(min(want, 20000u));
 			}
 		}
 }
