@@ -82,6 +82,7 @@ __global__ void k_reset_collide(u32* counts, u32 K) {
 	if (threadIdx.x == 0) {
 		counts[CNT_SCRATCH1] = K;  // key count of the Morton sort
 		counts[CNT_PAIRS] = 0; counts[CNT_OVERFLOW] = 0; counts[CNT_EXT_SUM] = 0;
+		for (int k = 0; k < 18; ++k) counts[CNT_EXT_HIST + k] = 0;
 		for (int k = 0; k < 4; ++k) { counts[CNT_BMIN0 + k] = 0xffffffffu; counts[CNT_BMAX0 + k] = 0; }
 	}
 }
@@ -344,7 +345,7 @@ int nb_collide(nb_context* ctx, void* stream) {
 	if (K == 0 || B == 0) return NB_OK;
 	k_collider_world<<<GRID(K), NB_BLOCK, 0, st>>>(ctx->nboxes, ctx->nspheres, ctx->xf, ctx->box_xf, ctx->box_data, ctx->box_tags,
 		ctx->sph_xf, ctx->sph_data, ctx->sph_tags, ctx->world_xf, ctx->aabb_min, ctx->aabb_max, ctx->col_tag, ctx->col_body, counts);
-	k_morton<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->aabb_min, counts, ctx->sb.keys[0], ctx->sb.vals[0]);
+	k_morton<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->aabb_min, ctx->aabb_max, counts, ctx->sb.keys[0], ctx->sb.vals[0]);
 	ctx->launches += 2;
 	// radix sort on the 48-bit code; ties keep index order like the stable sort of nudge.cpp:3165
 	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_SCRATCH1, 0, 48, true, 0);

@@ -18,7 +18,8 @@ enum {  // device counters (u32 each)
 	CNT_FACE, CNT_EDGE, CNT_OTHER, CNT_STAGED, CNT_CONTACTS, CNT_SLEEP_FINE, CNT_SLEEPING, CNT_ACTIVE,
 	CNT_CACHE, CNT_CULLED, CNT_FULL_BATCHES, CNT_BATCHES, CNT_LEVELS, CNT_ENTRIES, CNT_OVERFLOW, CNT_LVCH0, CNT_LVCH1, CNT_LVCH2,
 	CNT_BMIN0, CNT_BMIN1, CNT_BMIN2, CNT_BMIN3, CNT_BMAX0, CNT_BMAX1, CNT_BMAX2, CNT_BMAX3,
-	CNT_BAR0, CNT_BAR1, CNT_SCRATCH0, CNT_SCRATCH1, CNT_EXT_SUM, CNT_GRID_LEVEL, CNT_LARGE, CNT__COUNT = 64
+	CNT_BAR0, CNT_BAR1, CNT_SCRATCH0, CNT_SCRATCH1, CNT_EXT_SUM, CNT_GRID_LEVEL, CNT_LARGE, CNT_SURV, CNT_TMP,
+	CNT_EXT_HIST = 64 /* 18 bins */, CNT__COUNT = 96
 };
 enum { OVF_PAIRS = 1, OVF_CONTACTS = 2, OVF_SCHED = 4, OVF_LEVELS = 8 };
 
@@ -113,7 +114,17 @@ NB_DEV void morton_quantise(const MortonFrame& f, float4 p, u32 i, u32& x, u32& 
 	x = (u32)nb_toint(nb_msub(p.x, s, f.ms[0])); y = (u32)nb_toint(nb_msub(p.y, s, f.ms[1])); z = (u32)nb_toint(nb_msub(p.z, s, f.ms[2]));
 }
 
-__global__ void __launch_bounds__(NB_BLOCK) k_morton(u32 K, const float4* aabb_min, const u32* counts, u64* keys, u32* vals) {
+// Also bins the colliders by the grid level they need (smallest l with quantised extent + 2 <= 2^l; 17 = never) for k_grid_setup.
+NB_DEV u32 grid_level_needed(float4 lo, float4 hi, float scale) {
+	float ext = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z)) * scale + 2.0f;
+	u32 l = 1;
+	while (l <= 16 && !(ext <= (float)(1u << l))) ++l;  // NaN never fits
+	return l;
+}
+__global__ void __launch_bounds__(NB_BLOCK) k_morton(u32 K, const float4* aabb_min, const float4* aabb_max, u32* counts, u64* keys, u32* vals) {
+	__shared__ u32 s_hist[18];
+	if (threadIdx.x < 18) s_hist[threadIdx.x] = 0;
+	__syncthreads();
 	float smin[4], smax[4], sc[4];
 	#pragma unroll
 	for (int k = 0; k < 3; ++k) { smin[k] = ord2f(counts[CNT_BMIN0 + k]); smax[k] = ord2f(counts[CNT_BMAX0 + k]); }
@@ -133,7 +144,10 @@ __global__ void __launch_bounds__(NB_BLOCK) k_morton(u32 K, const float4* aabb_m
 		dilate3(x, 2, lx, hx); dilate3(y, 1, ly, hy); dilate3(z, 0, lz, hz);
 		keys[i] = (u64)(lx | ly | lz) | ((u64)(hx | hy | hz) << 32);
 		vals[i] = i;
+		atomicAdd(&s_hist[grid_level_needed(p, aabb_max[i], L[0])], 1u);
 	}
+	__syncthreads();
+	if (threadIdx.x < 18 && s_hist[threadIdx.x]) atomicAdd(&counts[CNT_EXT_HIST + threadIdx.x], s_hist[threadIdx.x]);
 }
 
 // ---------------- K3/K4: Morton-ordered leaves and the implicit 8-ary AABB tree ----------------
@@ -306,13 +320,15 @@ NB_DEV u64 morton48_of(u32 x, u32 y, u32 z) {
 }
 NB_DEV u32 grid_hash(u64 prefix, u32 mask) { return (u32)((prefix * 0x9E3779B97F4A7C15ull) >> 32) & mask; }
 
+// Cell edge 2^j: the finest level that leaves at most NB_GRID_MAX_LARGE colliders too big for a cell (those go through the
+// brute-force kernel, K tests each), read off the histogram k_morton made.
+#define NB_GRID_MAX_LARGE 64u
 __global__ void k_grid_setup(u32 K, u32* counts) {
-	MortonFrame f = morton_frame(counts);
-	float mean = asf(counts[CNT_EXT_SUM]) / (float)K;
-	float need = 2.0f * mean * f.L[0] + 2.0f;  // cell edge in quantised units
-	u32 j = 1;
-	while (j < 16 && (float)(1u << j) < need) ++j;
-	if (!(need == need)) j = 16;
+	u32 j = 16, above = counts[CNT_EXT_HIST + 17];
+	for (u32 l = 16; l >= 1; --l) {  // above = colliders needing a level > l
+		if (above <= NB_GRID_MAX_LARGE) j = l;
+		above += counts[CNT_EXT_HIST + l];
+	}
 	counts[CNT_GRID_LEVEL] = j; counts[CNT_LARGE] = 0;
 }
 
@@ -320,12 +336,10 @@ __global__ void __launch_bounds__(NB_BLOCK) k_grid_build(u32 K, const u32* order
 		uint8_t* smallf, u32* large_list, u64* table_keys, u64* table_vals, u32 table_mask, u32* counts) {
 	const MortonFrame f = morton_frame(counts);
 	const u32 j = counts[CNT_GRID_LEVEL];
-	const float cell = (float)(1u << j);
 	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < K; p += gridDim.x * blockDim.x) {
 		float4 lo = leaf_min[p], hi = leaf_max[p];
 		u32 qx, qy, qz; morton_quantise(f, lo, order[p], qx, qy, qz);
-		float ext = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z)) * f.L[0] + 2.0f;
-		bool small = ext <= cell && qx < 65536u && qy < 65536u && qz < 65536u;  // NaN extents are "large" too
+		bool small = grid_level_needed(lo, hi, f.L[0]) <= j && qx < 65536u && qy < 65536u && qz < 65536u;  // NaN extents are "large" too
 		smallf[p] = small ? 1 : 0;
 		if (!small) large_list[atomicAdd(&counts[CNT_LARGE], 1u)] = p;
 		const u64 prefix = mkeys[p] >> (3 * j);
@@ -352,32 +366,83 @@ NB_DEV void emit_pair(u32 p, u32 q, const u32* order, u32 kbits, u64* pair_keys,
 	else atomicOr(&counts[CNT_OVERFLOW], OVF_PAIRS);
 }
 
-// One warp per small collider, one lane per neighbouring cell: 27 short independent probes instead of one long serial walk.
-// Cells whose Morton prefix is below the collider's own hold only earlier positions and are skipped outright.
+// One warp per small collider.  Lanes 0..26 each look up one neighbouring cell (cells whose Morton prefix is below the
+// collider's own hold only earlier positions and are skipped); the candidate ranges are then flattened with a warp scan and
+// dealt round-robin to all 32 lanes, so the walk takes ceil(candidates / 32) steps however unevenly the cells are filled.
+// Hits go to a per-warp shared buffer (shared-memory atomic for the slot) that is flushed to the pair list with one global
+// atomic per ~64 pairs: one global atomic per pair would serialise on the counter.
+#define NB_GP_BUF 128
 __global__ void __launch_bounds__(NB_BLOCK) k_grid_pairs(u32 K, const u32* order, const float4* leaf_min, const float4* leaf_max, const uint8_t* smallf, const u64* mkeys,
 		const u64* table_keys, const u64* table_vals, u32 table_mask, u32 kbits, u64* pair_keys, u32 max_pairs, u32* counts) {
+	__shared__ u64 buf[NB_WARPS][NB_GP_BUF];
+	__shared__ u32 fill[NB_WARPS];
 	const MortonFrame f = morton_frame(counts);
 	const u32 j = counts[CNT_GRID_LEVEL];
 	const int ncell = 1 << (16 - j);
-	const u32 lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+	const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	const int dx = (int)(lane % 3) - 1, dy = (int)((lane / 3) % 3) - 1, dz = (int)(lane / 9) - 1;
-	for (u32 p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < K; p += nwarps) {
-		if (lane >= 27 || !smallf[p]) continue;
+	if (lane == 0) fill[wid] = 0;
+	__syncwarp();
+	auto flush = [&]() {  // warp-converged
+		u32 cnt = min(fill[wid], (u32)NB_GP_BUF), base = 0;
+		if (lane == 0) base = atomicAdd(&counts[CNT_PAIRS], cnt);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		for (u32 i = lane; i < cnt; i += 32) {
+			if (base + i < max_pairs) pair_keys[base + i] = buf[wid][i];
+			else atomicOr(&counts[CNT_OVERFLOW], OVF_PAIRS);
+		}
+		__syncwarp();
+		if (lane == 0) fill[wid] = 0;
+		__syncwarp();
+	};
+	for (u32 p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < K; p += nwarps) {  // p is warp-uniform
+		if (!smallf[p]) continue;
 		const float4 lo = leaf_min[p], hi = leaf_max[p];
-		u32 qx, qy, qz; morton_quantise(f, lo, order[p], qx, qy, qz);
-		const int nx = (int)(qx >> j) + dx, ny = (int)(qy >> j) + dy, nz = (int)(qz >> j) + dz;
-		if (nx < 0 || ny < 0 || nz < 0 || nx >= ncell || ny >= ncell || nz >= ncell) continue;
-		const u64 prefix = morton48_of((u32)nx << j, (u32)ny << j, (u32)nz << j) >> (3 * j);
-		if (prefix < (mkeys[p] >> (3 * j))) continue;
-		u32 slot = grid_hash(prefix, table_mask);
-		u64 k;
-		while ((k = table_keys[slot]) != prefix && k != NB_GRID_EMPTY) slot = (slot + 1) & table_mask;
-		if (k == NB_GRID_EMPTY) continue;
-		const u64 range = table_vals[slot];
-		const u32 e = (u32)(range >> 32);
-		for (u32 q = max((u32)range, p + 1); q < e; ++q)  // each pair once: from its earlier Morton position
-			if (smallf[q] && boxes_overlap(lo, hi, leaf_min[q], leaf_max[q])) emit_pair(p, q, order, kbits, pair_keys, max_pairs, counts);
+		u32 qb = 0, len = 0;
+		if (lane < 27) {
+			u32 qx, qy, qz; morton_quantise(f, lo, order[p], qx, qy, qz);
+			const int nx = (int)(qx >> j) + dx, ny = (int)(qy >> j) + dy, nz = (int)(qz >> j) + dz;
+			if (nx >= 0 && ny >= 0 && nz >= 0 && nx < ncell && ny < ncell && nz < ncell) {
+				const u64 prefix = morton48_of((u32)nx << j, (u32)ny << j, (u32)nz << j) >> (3 * j);
+				if (prefix >= (mkeys[p] >> (3 * j))) {
+					u32 slot = grid_hash(prefix, table_mask);
+					u64 k;
+					while ((k = table_keys[slot]) != prefix && k != NB_GRID_EMPTY) slot = (slot + 1) & table_mask;
+					if (k != NB_GRID_EMPTY) {
+						const u64 range = table_vals[slot];
+						qb = max((u32)range, p + 1);  // each pair once: from its earlier Morton position
+						const u32 qe = (u32)(range >> 32);
+						len = qe > qb ? qe - qb : 0;
+					}
+				}
+			}
+		}
+		const u32 incl = warp_incl_scan(len), off = incl - len, total = __shfl_sync(0xffffffffu, incl, 31);
+		const u64 hi_key = (u64)order[p] << kbits;  // hi = earlier, lo = later (nudge.cpp:3495)
+		for (u32 t0 = 0; t0 < total; t0 += 32) {
+			const u32 t = t0 + lane;
+			// cell of candidate t: the last lane whose offset is <= t (offsets are non-decreasing)
+			u32 c = 0;
+			#pragma unroll
+			for (int step = 16; step; step >>= 1) {
+				u32 probe = __shfl_sync(0xffffffffu, off, (c + step) & 31);
+				if (c + step < 32 && probe <= t) c += step;
+			}
+			const u32 q = __shfl_sync(0xffffffffu, qb, c) + (t - __shfl_sync(0xffffffffu, off, c));
+			if (t < total && smallf[q] && boxes_overlap(lo, hi, leaf_min[q], leaf_max[q])) {
+				u32 slot = atomicAdd(&fill[wid], 1u);
+				if (slot < NB_GP_BUF) buf[wid][slot] = hi_key | (u64)order[q];
+				else {  // more than a buffer of hits from one step: straight to the list
+					u32 g = atomicAdd(&counts[CNT_PAIRS], 1u);
+					if (g < max_pairs) pair_keys[g] = hi_key | (u64)order[q];
+					else atomicOr(&counts[CNT_OVERFLOW], OVF_PAIRS);
+				}
+			}
+			__syncwarp();
+			if (fill[wid] > NB_GP_BUF - 32) flush();
+		}
 	}
+	if (fill[wid]) flush();
 }
 
 __global__ void __launch_bounds__(NB_BLOCK) k_large_pairs(u32 K, const u32* order, const float4* leaf_min, const float4* leaf_max, const uint8_t* smallf,
@@ -580,7 +645,7 @@ NB_DEV u32 warp_reserve(u32* counter, u32 n) {
 // `reserve` (optional, EMIT only): the contacts go to slots reserved from this counter once their number is known; `at` returns the first slot.
 template<bool EMIT>
 NB_DEV int bb_face_or_edge(const BoxIn& A, const BoxIn& B, float face_penetration, u32 a_face, const ContactOut& out, u32& at_io, u32 limit,
-						   u32& n_out, float& edge_pen, u32& edge_feature, bool& edge_swap, u32* reserve = nullptr) {
+						   u32& n_out, float& edge_pen, u32& edge_feature, bool& edge_swap, const u32* s_rsqrt, u32* reserve = nullptr) {
 	u32 at = at_io;
 	float a_to_b[9]; rel_rotation(A.t.q, B.t.q, a_to_b);
 	float3 sa = A.s, sb = B.s;
@@ -603,8 +668,8 @@ NB_DEV int bb_face_or_edge(const BoxIn& A, const BoxIn& B, float face_penetratio
 		float rb[3] = { bc2y + bc2z, bc2z + bc2x, bc2x + bc2y };
 		#pragma unroll
 		for (int k = 0; k < 3; ++k) {  // rsqrt | cmp_le -> NaN for degenerate axes (nudge.cpp:1611-1619)
-			ra[k] = asf(asu(nb_rsqrt(ra[k])) | (ra[k] <= 1e-3f ? 0xffffffffu : 0u));
-			rb[k] = asf(asu(nb_rsqrt(rb[k])) | (rb[k] <= 1e-3f ? 0xffffffffu : 0u));
+			ra[k] = asf(asu(nb_rsqrt_t(ra[k], s_rsqrt)) | (ra[k] <= 1e-3f ? 0xffffffffu : 0u));
+			rb[k] = asf(asu(nb_rsqrt_t(rb[k], s_rsqrt)) | (rb[k] <= 1e-3f ? 0xffffffffu : 0u));
 		}
 		float pa0 = aacy*sa.z + aacz*sa.y, pa1 = aacz*sa.x + aacx*sa.z, pa2 = aacx*sa.y + aacy*sa.x;
 		float pb0 = abcy*sb.z + abcz*sb.y, pb1 = abcz*sb.x + abcx*sb.z, pb2 = abcx*sb.y + abcy*sb.x;
@@ -806,7 +871,7 @@ NB_DEV int bb_face_or_edge(const BoxIn& A, const BoxIn& B, float face_penetratio
 }
 
 // Pass 3: edge-edge closest points, nudge.cpp:2157-2479.
-NB_DEV void bb_edge(const BoxIn& A, const BoxIn& B, float pen, u32 edge, const ContactOut& out, u32 at) {
+NB_DEV void bb_edge(const BoxIn& A, const BoxIn& B, float pen, u32 edge, const ContactOut& out, u32 at, const u32* s_rsqrt) {
 	float ab[3][3], bb[3][3];
 	#pragma unroll
 	for (int w = 0; w < 2; ++w) {
@@ -866,7 +931,7 @@ NB_DEV void bb_edge(const BoxIn& A, const BoxIn& B, float pen, u32 edge, const C
 	float px = (ca[0] - cb[0])*0.5f + u.x*s_a + v.x*s_b;
 	float py = (ca[1] - cb[1])*0.5f + u.y*s_a + v.y*s_b;
 	float pz = (ca[2] - cb[2])*0.5f + u.z*s_a + v.z*s_b;
-	float fn = nb_rsqrt(n.x*n.x + n.y*n.y + n.z*n.z);  // nudge.cpp:842-847, 2453
+	float fn = nb_rsqrt_t(n.x*n.x + n.y*n.y + n.z*n.z, s_rsqrt);  // nudge.cpp:842-847, 2453
 	put_contact(out, at, px, py, pz, pen, n.x*fn, n.y*fn, n.z*fn, asu(A.t.p.w), asu(B.t.p.w), (u64)A.tag | ((u64)B.tag << 32), tag);
 }
 
@@ -931,7 +996,6 @@ NB_DEV BoxIn load_box(const nb_transform* world_xf, const nb_box_collider* box_d
 //   k_np_clip   surviving box-box pairs (compacted): pass 2 (+ pass 3 for edge contacts) -> contacts in a scratch buffer + counts
 //   k_np_emit   moves the scratch contacts (and computes the sphere contacts) to the scanned offsets, in the reference's contact order
 //               (box-box face contacts, box-box edge contacts, box-sphere, sphere-sphere: nudge.cpp:3753-3786)
-enum { CNT_SURV = CNT_LARGE + 1, CNT_TMP };
 
 __global__ void __launch_bounds__(NB_BLOCK) k_np_faces(const uint2* live, u32 nboxes, const nb_transform* world_xf, const nb_box_collider* box_data,
 		const nb_sphere_collider* sph_data, const u32* col_tag, u32* cnt /*[4][stride]: face, edge, other, survivor*/, u32 stride, float* np_pen, u32* np_info, u32* counts) {
@@ -969,6 +1033,10 @@ __global__ void __launch_bounds__(NB_BLOCK) k_np_list(const u32* cnt, const u32*
 // and k_np_emit moves them to their final, pair-ordered place after the scan.
 __global__ void __launch_bounds__(NB_BLOCK) k_np_clip(const uint2* live, const u32* np_list, const float* np_pen, const u32* np_info, const nb_transform* world_xf,
 		const nb_box_collider* box_data, const u32* col_tag, u32* cnt, u32 stride, ContactOut tmp, u32* np_start, u32 max_contacts, u32* counts) {
+	// the rsqrtps table goes to shared memory: 32 different indices per warp would serialise on the constant cache
+	__shared__ u32 s_rsqrt[2048];
+	for (u32 i = threadIdx.x; i < 2048; i += blockDim.x) s_rsqrt[i] = g_rsqrt_lut[i];
+	__syncthreads();
 	u32 n = counts[CNT_SURV];
 	for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
 		u32 j = np_list[k];
@@ -976,11 +1044,11 @@ __global__ void __launch_bounds__(NB_BLOCK) k_np_clip(const uint2* live, const u
 		u32 info = np_info[j];
 		BoxIn A = load_box(world_xf, box_data, col_tag, (info & 4) ? pr.y : pr.x), B = load_box(world_xf, box_data, col_tag, (info & 4) ? pr.x : pr.y);  // a owns the best face (nudge.cpp:1381-1387)
 		float epen; u32 efeat; bool eswap; u32 nface = 0, at = 0;
-		int kind = bb_face_or_edge<true>(A, B, np_pen[j], info & 3, tmp, at, max_contacts, nface, epen, efeat, eswap, &counts[CNT_TMP]);
+		int kind = bb_face_or_edge<true>(A, B, np_pen[j], info & 3, tmp, at, max_contacts, nface, epen, efeat, eswap, s_rsqrt, &counts[CNT_TMP]);
 		if (kind == 2) {
 			at = warp_reserve(&counts[CNT_TMP], 1);
 			if (eswap) { BoxIn t = A; A = B; B = t; }
-			if (at < max_contacts) bb_edge(A, B, epen, efeat, tmp, at);
+			if (at < max_contacts) bb_edge(A, B, epen, efeat, tmp, at, s_rsqrt);
 		}
 		np_start[j] = at;
 		cnt[0*stride + j] = kind == 1 ? nface : 0;

@@ -301,11 +301,15 @@ __global__ void __launch_bounds__(NB_CS_THREADS) k_sort_coop(u64* k0, u64* k1, u
 			for (u32 w = tid; w < NB_CS_WARPS * 256; w += NB_CS_THREADS) (&wc[0][0])[w] = 0;
 			__syncthreads();
 			#pragma unroll
+			for (int r = 0; r < NB_CS_ITEMS; ++r) {  // all loads first: the warp barriers below would serialise them
+				u32 i = base + wid * (32 * NB_CS_ITEMS) + r * 32 + lane;
+				key[r] = i < end ? __ldcg(kin + i) : 0;
+				if (HAS_VALS) val[r] = i < end ? __ldcg(vin + i) : 0;
+			}
+			#pragma unroll
 			for (int r = 0; r < NB_CS_ITEMS; ++r) {
 				u32 i = base + wid * (32 * NB_CS_ITEMS) + r * 32 + lane;
 				bool valid = i < end;
-				key[r] = valid ? __ldcg(kin + i) : 0;
-				if (HAS_VALS) val[r] = valid ? __ldcg(vin + i) : 0;
 				u32 d = valid ? ((u32)(key[r] >> shift) & 0xff) : 0xffffffffu;
 				u32 peers = __match_any_sync(0xffffffffu, d);
 				u32 leader = __ffs(peers) - 1, old = 0;
@@ -348,7 +352,13 @@ __global__ void __launch_bounds__(NB_CS_THREADS) k_sort_coop(u64* k0, u64* k1, u
 			if (tid < 256) hist[b * 256 + tid] = h[tid];
 			grid_barrier(bar, G);
 			u32 d = tid & 255, q = tid >> 8, bl = 0, tt = 0;
-			for (u32 r = q; r < G; r += 4) { u32 v = __ldcg(&hist[r * 256 + d]); tt += v; if (r < b) bl += v; }
+			for (u32 r0 = q; r0 < G; r0 += 32) {  // eight independent loads in flight per round trip
+				u32 v[8];
+				#pragma unroll
+				for (int u = 0; u < 8; ++u) { u32 r = r0 + 4 * u; v[u] = r < G ? __ldcg(&hist[r * 256 + d]) : 0; }
+				#pragma unroll
+				for (int u = 0; u < 8; ++u) { tt += v[u]; if (r0 + 4 * u < b) bl += v[u]; }
+			}
 			below[q][d] = bl; total[q][d] = tt;
 			__syncthreads();
 			if (tid < 256) { h[tid] = total[0][tid] + total[1][tid] + total[2][tid] + total[3][tid]; mine = below[0][tid] + below[1][tid] + below[2][tid] + below[3][tid]; }
