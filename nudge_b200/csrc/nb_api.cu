@@ -3,6 +3,7 @@
 // here the context plays both roles for device memory: every buffer is carved once from cudaMalloc at
 // nb_create and reused every step, nothing is allocated or synchronised inside the step.
 #include "nb_solver.cuh"
+#define NB_DEFAULT_COOP_LAUNCH 1
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -25,7 +26,8 @@ struct nb_context {
 	u32 stride;    // scratch stride
 	u32 cstride;   // row plane stride
 	u32 slots_per_bucket;
-	int coop_blocks_solve;
+	int coop_blocks_solve; int coop_launch;
+	u64* keybits;  // OR, AND of the Morton codes of the current collide
 	u32* chain_start; u32* chain_len;  // per body: first entry / number of entries in the (body, batch) chain sort
 	bool contacts_internal;  // the current contact set came from nb_collide (not nb_upload_contacts)
 	u32 solve_backoff_ns;
@@ -78,8 +80,9 @@ static u32 bits_for(u64 n) { u32 b = 1; while (((u64)1 << b) < n) ++b; return b;
 static Launch mk_launch(nb_context* ctx, void* stream) { Launch L = { (cudaStream_t)stream, &ctx->launches, ctx->sms }; return L; }
 #define GRID(n) nb_grid_for((unsigned)(n), ctx->sms)
 
-__global__ void k_reset_collide(u32* counts, u32 K) {
+__global__ void k_reset_collide(u32* counts, u32 K, u64* keybits) {
 	if (threadIdx.x == 0) {
+		keybits[0] = 0; keybits[1] = ~(u64)0;
 		counts[CNT_SCRATCH1] = K;  // key count of the Morton sort
 		counts[CNT_PAIRS] = 0; counts[CNT_OVERFLOW] = 0; counts[CNT_EXT_SUM] = 0;
 		for (int k = 0; k < 18; ++k) counts[CNT_EXT_HIST + k] = 0;
@@ -154,7 +157,7 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ALLOC(ctx->box_tags, c.max_boxes); ALLOC(ctx->box_data, c.max_boxes); ALLOC(ctx->box_xf, c.max_boxes);
 	ALLOC(ctx->sph_tags, c.max_spheres); ALLOC(ctx->sph_data, c.max_spheres); ALLOC(ctx->sph_xf, c.max_spheres);
 	ALLOC(ctx->conn, c.max_connections);
-	ALLOC(ctx->counts, CNT__COUNT);
+	ALLOC(ctx->counts, CNT__COUNT); ALLOC(ctx->keybits, 2);
 	ALLOC(ctx->world_xf, K); ALLOC(ctx->aabb_min, K); ALLOC(ctx->aabb_max, K); ALLOC(ctx->col_tag, K); ALLOC(ctx->col_body, K);
 	ALLOC(ctx->order, K); ALLOC(ctx->rank, K);
 	size_t tree_nodes = 0; { u32 n = K ? K : 1; tree_nodes = n; while (n > 8) { n = (n + 7) / 8; tree_nodes += n; } }
@@ -170,7 +173,13 @@ int nb_create(const nb_config* config, nb_context** out) {
 	for (int i = 0; i < 2; ++i) { ALLOC(ctx->sb.keys[i], ctx->sort_cap); ALLOC(ctx->sb.vals[i], ctx->sort_cap); }
 	ALLOC(ctx->sb.hist, 256 * NB_SORT_GRID);
 	ctx->sb.bar = ctx->counts + CNT_BAR0;
-	{ const char* e = getenv("NB_SORT"); ctx->sb.coop_blocks = (e && !strcmp(e, "legacy")) ? 0 : ctx->sms; } ALLOC(ctx->sb.block_sums, 8 * NB_SCAN_GRID);
+	{ const char* e = getenv("NB_SORT"); ctx->sb.coop_blocks = (e && !strcmp(e, "legacy")) ? 0 : ctx->sms; }
+	// Grid-synchronising kernels (one block per SM for the sort, the occupancy-derived grid for the solver) are launched as
+	// ordinary kernels unless NB_COOP_LAUNCH=1: the grid fits the idle device by construction, and a cooperative launch costs
+	// several microseconds more per launch.
+	{ const char* e = getenv("NB_COOP_LAUNCH"); ctx->coop_launch = e ? atoi(e) != 0 : NB_DEFAULT_COOP_LAUNCH; ctx->sb.coop_launch = ctx->coop_launch; }
+	CK(cudaFuncSetAttribute(k_sort_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopSortSmem)));
+	CK(cudaFuncSetAttribute(k_sort_coop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopSortSmem))); ALLOC(ctx->sb.block_sums, 8 * NB_SCAN_GRID);
 	ALLOC(ctx->flags, 5 * (size_t)ctx->stride); ALLOC(ctx->offs, 5 * (size_t)ctx->stride); ALLOC(ctx->block_sums, 8 * NB_SCAN_GRID);
 	ALLOC(ctx->live, P); ALLOC(ctx->np_pen, P); ALLOC(ctx->np_info, P); ALLOC(ctx->np_list, P); ALLOC(ctx->np_start, P);
 	ALLOC(ctx->staged.data, 2 * (size_t)C); ALLOC(ctx->staged.bodies, C); ALLOC(ctx->staged.tags, C); ALLOC(ctx->staged.features, C);
@@ -341,14 +350,14 @@ int nb_collide(nb_context* ctx, void* stream) {
 	cudaStream_t st = L.stream;
 	const u32 K = ctx->nboxes + ctx->nspheres, B = ctx->B, nboxes = ctx->nboxes;
 	u32* counts = ctx->counts;
-	k_reset_collide<<<1, 32, 0, st>>>(counts, K); ++ctx->launches;
+	k_reset_collide<<<1, 32, 0, st>>>(counts, K, ctx->keybits); ++ctx->launches;
 	if (K == 0 || B == 0) return NB_OK;
 	k_collider_world<<<GRID(K), NB_BLOCK, 0, st>>>(ctx->nboxes, ctx->nspheres, ctx->xf, ctx->box_xf, ctx->box_data, ctx->box_tags,
 		ctx->sph_xf, ctx->sph_data, ctx->sph_tags, ctx->world_xf, ctx->aabb_min, ctx->aabb_max, ctx->col_tag, ctx->col_body, counts);
-	k_morton<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->aabb_min, ctx->aabb_max, counts, ctx->sb.keys[0], ctx->sb.vals[0]);
+	k_morton<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->aabb_min, ctx->aabb_max, counts, ctx->sb.keys[0], ctx->sb.vals[0], ctx->keybits);
 	ctx->launches += 2;
 	// radix sort on the 48-bit code; ties keep index order like the stable sort of nudge.cpp:3165
-	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_SCRATCH1, 0, 48, true, 0);
+	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_SCRATCH1, 0, 48, true, 0, 0, 0, ctx->keybits);
 	Tree T;
 	{
 		size_t off = 0; u32 n = K; int l = 0;
@@ -485,7 +494,8 @@ static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) 
 	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw);
 	u32 backoff = ctx->solve_backoff_ns;
 	void* args[] = { &R, &impulses, &mw, &mode, &sweeps, &backoff, &counts };
-	CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
+	if (ctx->coop_launch) CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
+	else k_solve<<<ctx->coop_blocks_solve, NB_BLOCK, 0, st>>>(R, impulses, mw, mode, sweeps, backoff, counts);
 	k_mw_out<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw, mode);
 	ctx->launches += 3;
 	return NB_OK;

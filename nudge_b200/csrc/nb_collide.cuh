@@ -121,8 +121,9 @@ NB_DEV u32 grid_level_needed(float4 lo, float4 hi, float scale) {
 	while (l <= 16 && !(ext <= (float)(1u << l))) ++l;  // NaN never fits
 	return l;
 }
-__global__ void __launch_bounds__(NB_BLOCK) k_morton(u32 K, const float4* aabb_min, const float4* aabb_max, u32* counts, u64* keys, u32* vals) {
+__global__ void __launch_bounds__(NB_BLOCK) k_morton(u32 K, const float4* aabb_min, const float4* aabb_max, u32* counts, u64* keys, u32* vals, u64* keybits /* OR, AND of all codes: steers the sort's bucket digit */) {
 	__shared__ u32 s_hist[18];
+	u64 k_or = 0, k_and = ~(u64)0;
 	if (threadIdx.x < 18) s_hist[threadIdx.x] = 0;
 	__syncthreads();
 	float smin[4], smax[4], sc[4];
@@ -142,10 +143,15 @@ __global__ void __launch_bounds__(NB_BLOCK) k_morton(u32 K, const float4* aabb_m
 		u32 z = (u32)nb_toint(nb_msub(p.z, s, ms[2]));
 		u32 lx, hx, ly, hy, lz, hz;
 		dilate3(x, 2, lx, hx); dilate3(y, 1, ly, hy); dilate3(z, 0, lz, hz);
-		keys[i] = (u64)(lx | ly | lz) | ((u64)(hx | hy | hz) << 32);
+		const u64 code = (u64)(lx | ly | lz) | ((u64)(hx | hy | hz) << 32);
+		keys[i] = code;
 		vals[i] = i;
+		k_or |= code; k_and &= code;
 		atomicAdd(&s_hist[grid_level_needed(p, aabb_max[i], L[0])], 1u);
 	}
+	#pragma unroll
+	for (int d = 16; d; d >>= 1) { k_or |= __shfl_xor_sync(0xffffffffu, k_or, d); k_and &= __shfl_xor_sync(0xffffffffu, k_and, d); }
+	if ((threadIdx.x & 31) == 0) { atomicOr((unsigned long long*)&keybits[0], (unsigned long long)k_or); atomicAnd((unsigned long long*)&keybits[1], (unsigned long long)k_and); }
 	__syncthreads();
 	if (threadIdx.x < 18 && s_hist[threadIdx.x]) atomicAdd(&counts[CNT_EXT_HIST + threadIdx.x], s_hist[threadIdx.x]);
 }

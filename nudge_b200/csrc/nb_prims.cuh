@@ -261,96 +261,241 @@ NB_DEV void grid_barrier(u32* bar /* [0]=arrivals, [1]=generation */, u32 nblock
 }
 
 // ---------------- single-launch radix sort (cooperative) ----------------
-// All passes of one sort in ONE cooperative launch: one block of 1024 threads per SM, two grid barriers per pass.  A block owns a
-// contiguous range of 4096-key tiles.  Per pass: block digit histogram -> [block][digit] matrix (L2 resident) | barrier | every
-// block derives its own scatter offsets from the matrix, ranks its tiles (match_any per warp, 4 keys per thread) and scatters |
-// barrier.  When every block owns at most one tile (n <= 4096 * blocks) the keys stay in registers between the histogram and
-// the scatter.  Small inputs (n <= NB_CS_SMALL) are sorted by block 0 alone with block-level barriers; n == 0 costs one empty
-// launch.  Same stable LSD order as nb_radix_sort.
+// One cooperative launch per sort: one block of 1024 threads per SM.  The digits are 8 bits wide, top-aligned (the host picks
+// the shifts so that the last digit covers the highest populated bits).
+//   n <= NB_CS_CAP      block 0 sorts everything in registers / shared memory (all digits, LSD), no grid barrier.
+//   otherwise           MSD first: histogram of the TOP digit -> [block][digit] matrix | barrier | every block derives its
+//                       scatter offsets from the matrix and scatters its keys into 256 buckets | barrier | each bucket
+//                       is sorted on the remaining digits by one block and written back in place: in registers / shared
+//                       memory when it has <= NB_CS_CAP keys, tile by tile through global memory when it is larger (a hot
+//                       key).  Two grid barriers per SORT instead of two per digit.
+//   a bucket > 8 caps   (very skewed keys, or large n): plain LSD over all digits, two grid barriers per digit.
+// The result always lands in k1/v1.  Stable, same order as nb_radix_sort.  n == 0 costs one empty launch.
 #define NB_CS_THREADS 1024
 #define NB_CS_WARPS 32
-#define NB_CS_ITEMS 4
+#define NB_CS_ITEMS 4                       // keys per thread while scattering through global memory
 #define NB_CS_TILE (NB_CS_THREADS * NB_CS_ITEMS)
-#define NB_CS_SMALL (4 * NB_CS_TILE)
+#define NB_CS_LOCAL 8                       // keys per thread in the block-local sort
+#define NB_CS_CAP (NB_CS_THREADS * NB_CS_LOCAL)
 struct SortPasses { int n; int shift[12]; };
+struct CoopSortSmem {
+	u32 wc[NB_CS_WARPS][256];
+	u32 h[256], tot[256], running[256], below[4][256], total[4][256], sm[8];
+	u64 skeys[NB_CS_CAP];
+	u32 svals[NB_CS_CAP];
+};
 
-template<bool HAS_VALS>
-__global__ void __launch_bounds__(NB_CS_THREADS) k_sort_coop(u64* k0, u64* k1, u32* v0, u32* v1, const u32* n_ptr, u32* hist /*[gridDim][256]*/, u32* bar, SortPasses P) {
-	__shared__ u32 h[256];        // digit totals of this block's range, then of the whole input
-	__shared__ u32 tot[256];      // digit totals of the current tile
-	__shared__ u32 running[256];  // next free output slot per digit for this block
-	__shared__ u32 below[4][256], total[4][256];
-	__shared__ u32 wc[NB_CS_WARPS][256];
-	__shared__ u32 sm[8];
-	const u32 n = *n_ptr;
-	if (n == 0) return;
-	const bool small = n <= NB_CS_SMALL;
-	if (small && blockIdx.x != 0) return;
-	const u32 G = small ? 1u : gridDim.x, b = blockIdx.x;
+// A digit is either 8 contiguous bits (np == 0) or up to 8 single bits gathered from the positions packed in `pos` (most
+// significant first): the top digit of a sort whose producer recorded which key bits vary at all (OR and AND of the keys) is
+// made of the 8 highest VARYING bits, which spreads e.g. Morton codes of a flat scene over all 256 buckets.
+struct CsDigit { u32 shift; u32 np; u64 pos; };
+NB_DEV u32 cs_digit(const CsDigit& D, u64 key) {
+	if (!D.np) return (u32)(key >> D.shift) & 0xff;
+	u32 d = 0; u64 pp = D.pos;
+	for (u32 i = 0; i < D.np; ++i) { d = (d << 1) | ((u32)(key >> (pp & 63)) & 1u); pp >>= 8; }
+	return d;
+}
+NB_DEV CsDigit cs_plain(int shift) { CsDigit D; D.shift = (u32)shift; D.np = 0; D.pos = 0; return D; }
+
+// Ranks ITEMS keys per thread (item r of a thread sits at tile position wid*32*ITEMS + r*32 + lane, so position order = rank
+// order).  Out: dg/rk per item, S.wc[w][d] = keys of digit d in warps before w, S.tot[d] = tile total.  Ends with a barrier.
+template<int ITEMS>
+NB_DEV void cs_rank(CoopSortSmem& S, const u64 (&key)[ITEMS], u32 nvalid, const CsDigit& D, u32 (&dg)[ITEMS], u32 (&rk)[ITEMS]) {
 	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lt = (1u << lane) - 1u;
-	const u32 tiles = (n + NB_CS_TILE - 1) / NB_CS_TILE, per = (tiles + G - 1) / G;
-	const u32 begin = min(n, b * per * NB_CS_TILE), end = min(n, begin + per * NB_CS_TILE);
-	const bool fused = per == 1;
-	u64* kin = k0; u64* kout = k1; u32* vin = v0; u32* vout = v1;
-	u64 key[NB_CS_ITEMS]; u32 val[NB_CS_ITEMS], dg[NB_CS_ITEMS], rk[NB_CS_ITEMS];
+	for (u32 w = tid; w < NB_CS_WARPS * 256; w += NB_CS_THREADS) (&S.wc[0][0])[w] = 0;
+	__syncthreads();
+	#pragma unroll
+	for (int r = 0; r < ITEMS; ++r) {
+		bool valid = wid * (32 * ITEMS) + r * 32 + lane < nvalid;
+		u32 d = valid ? cs_digit(D, key[r]) : 0xffffffffu;
+		u32 peers = __match_any_sync(0xffffffffu, d);
+		u32 leader = __ffs(peers) - 1, old = 0;
+		if (valid && lane == leader) { old = S.wc[wid][d]; S.wc[wid][d] = old + __popc(peers); }
+		old = __shfl_sync(0xffffffffu, old, leader);
+		dg[r] = d; rk[r] = old + __popc(peers & lt);
+		__syncwarp();
+	}
+	__syncthreads();
+	if (tid < 256) {
+		u32 sum = 0;
+		#pragma unroll 8
+		for (int w = 0; w < NB_CS_WARPS; ++w) { u32 c = S.wc[w][tid]; S.wc[w][tid] = sum; sum += c; }
+		S.tot[tid] = sum;
+	}
+	__syncthreads();
+}
 
-	for (int p = 0; p < P.n; ++p) {
-		const u32 shift = (u32)P.shift[p];
-		// ranks one tile: key/val/dg/rk in registers, wc[w][d] = keys of digit d in warps before w, tot[d] = tile total
-		auto rank_tile = [&](u32 base) {
-			for (u32 w = tid; w < NB_CS_WARPS * 256; w += NB_CS_THREADS) (&wc[0][0])[w] = 0;
-			__syncthreads();
-			#pragma unroll
-			for (int r = 0; r < NB_CS_ITEMS; ++r) {  // all loads first: the warp barriers below would serialise them
-				u32 i = base + wid * (32 * NB_CS_ITEMS) + r * 32 + lane;
-				key[r] = i < end ? __ldcg(kin + i) : 0;
-				if (HAS_VALS) val[r] = i < end ? __ldcg(vin + i) : 0;
+// S.running[d] = add[d] + exclusive prefix of src[d] over the 256 digits (threads 0..255 hold add).  Ends with a barrier.
+NB_DEV void cs_scan_digits(CoopSortSmem& S, const u32* src, u32 add) {
+	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	u32 t = tid < 256 ? src[tid] : 0;
+	u32 incl = warp_incl_scan(t);
+	if (tid < 256 && lane == 31) S.sm[wid] = incl;
+	__syncthreads();
+	if (wid == 0) { u32 w = lane < 8 ? S.sm[lane] : 0; u32 wi = warp_incl_scan(w); if (lane < 8) S.sm[lane] = wi - w; }
+	__syncthreads();
+	if (tid < 256) S.running[tid] = incl - t + S.sm[wid] + add;
+	__syncthreads();
+}
+
+// Sorts m <= NB_CS_CAP keys at src[0..m) on digits P.shift[0..npass) entirely inside the block; result to dst[0..m).
+template<bool HAS_VALS>
+NB_DEV void cs_local_sort(CoopSortSmem& S, const u64* ksrc, const u32* vsrc, u64* kdst, u32* vdst, u32 m, const SortPasses& P, int npass) {
+	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	u64 key[NB_CS_LOCAL]; u32 val[NB_CS_LOCAL], dg[NB_CS_LOCAL], rk[NB_CS_LOCAL];
+	#pragma unroll
+	for (int r = 0; r < NB_CS_LOCAL; ++r) {
+		u32 i = wid * (32 * NB_CS_LOCAL) + r * 32 + lane;
+		key[r] = i < m ? __ldcg(ksrc + i) : 0;
+		if (HAS_VALS) val[r] = i < m ? __ldcg(vsrc + i) : 0;
+	}
+	if (npass == 0) {  // nothing left to sort on: plain copy
+		#pragma unroll
+		for (int r = 0; r < NB_CS_LOCAL; ++r) {
+			u32 i = wid * (32 * NB_CS_LOCAL) + r * 32 + lane;
+			if (i < m) { kdst[i] = key[r]; if (HAS_VALS) vdst[i] = val[r]; }
+		}
+		return;
+	}
+	__syncthreads();  // every key of the bucket is in registers before anything is written back
+	for (int p = 0; p < npass; ++p) {
+		cs_rank<NB_CS_LOCAL>(S, key, m, cs_plain(P.shift[p]), dg, rk);
+		cs_scan_digits(S, S.tot, 0);
+		const bool last = p == npass - 1;
+		#pragma unroll
+		for (int r = 0; r < NB_CS_LOCAL; ++r)
+			if (dg[r] != 0xffffffffu) {
+				u32 pos = S.running[dg[r]] + S.wc[wid][dg[r]] + rk[r];
+				if (last) { kdst[pos] = key[r]; if (HAS_VALS) vdst[pos] = val[r]; }
+				else { S.skeys[pos] = key[r]; if (HAS_VALS) S.svals[pos] = val[r]; }
 			}
+		__syncthreads();
+		if (!last) {
+			#pragma unroll
+			for (int r = 0; r < NB_CS_LOCAL; ++r) {
+				u32 i = wid * (32 * NB_CS_LOCAL) + r * 32 + lane;
+				if (i < m) { key[r] = S.skeys[i]; if (HAS_VALS) val[r] = S.svals[i]; }
+			}
+		}
+	}
+}
+
+// A bucket that does not fit the registers of one block (m > NB_CS_CAP: a hot key value such as the ground's tag) is still sorted
+// by ONE block: plain LSD over the remaining digits, tile by tile through global memory, ping-ponging between the bucket's own
+// region (ka/va, holds the input and receives the result) and the same region of the other buffer (kb/vb, free scratch).
+template<bool HAS_VALS>
+NB_DEV void cs_block_lsd(CoopSortSmem& S, u64* ka, u32* va, u64* kb, u32* vb, u32 m, const SortPasses& P, int npass) {
+	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	u64 key[NB_CS_ITEMS]; u32 val[NB_CS_ITEMS], dg[NB_CS_ITEMS], rk[NB_CS_ITEMS];
+	u64* kin = ka; u64* kout = kb; u32* vin = va; u32* vout = vb;
+	for (int p = 0; p < npass; ++p) {
+		const u32 shift = (u32)P.shift[p];
+		if (tid < 256) S.h[tid] = 0;
+		__syncthreads();
+		for (u32 i = tid; i < m; i += NB_CS_THREADS) atomicAdd(&S.h[(u32)(__ldcg(kin + i) >> shift) & 0xff], 1u);
+		__syncthreads();
+		cs_scan_digits(S, S.h, 0);
+		for (u32 base = 0; base < m; base += NB_CS_TILE) {
 			#pragma unroll
 			for (int r = 0; r < NB_CS_ITEMS; ++r) {
 				u32 i = base + wid * (32 * NB_CS_ITEMS) + r * 32 + lane;
-				bool valid = i < end;
-				u32 d = valid ? ((u32)(key[r] >> shift) & 0xff) : 0xffffffffu;
-				u32 peers = __match_any_sync(0xffffffffu, d);
-				u32 leader = __ffs(peers) - 1, old = 0;
-				if (valid && lane == leader) { old = wc[wid][d]; wc[wid][d] = old + __popc(peers); }
-				old = __shfl_sync(0xffffffffu, old, leader);
-				dg[r] = d; rk[r] = old + __popc(peers & lt);
-				__syncwarp();
+				key[r] = i < m ? __ldcg(kin + i) : 0;
+				if (HAS_VALS) val[r] = i < m ? __ldcg(vin + i) : 0;
 			}
-			__syncthreads();
-			if (tid < 256) {
-				u32 sum = 0;
-				#pragma unroll 8
-				for (int w = 0; w < NB_CS_WARPS; ++w) { u32 c = wc[w][tid]; wc[w][tid] = sum; sum += c; }
-				tot[tid] = sum;
-			}
-			__syncthreads();
-		};
-		auto scatter_tile = [&]() {
+			cs_rank<NB_CS_ITEMS>(S, key, m - base, cs_plain((int)shift), dg, rk);
 			#pragma unroll
 			for (int r = 0; r < NB_CS_ITEMS; ++r)
 				if (dg[r] != 0xffffffffu) {
-					u32 pos = running[dg[r]] + wc[wid][dg[r]] + rk[r];
+					u32 pos = S.running[dg[r]] + S.wc[wid][dg[r]] + rk[r];
 					kout[pos] = key[r];
 					if (HAS_VALS) vout[pos] = val[r];
 				}
-		};
-
-		if (fused) {
-			rank_tile(begin);
-			if (tid < 256) h[tid] = tot[tid];
-		}
-		else {
-			if (tid < 256) h[tid] = 0;
 			__syncthreads();
-			for (u32 i = begin + tid; i < end; i += NB_CS_THREADS) atomicAdd(&h[(u32)(__ldcg(kin + i) >> shift) & 0xff], 1u);
+			if (tid < 256) S.running[tid] += S.tot[tid];
+			__syncthreads();
 		}
+		{ u64* t = kin; kin = kout; kout = t; u32* tv = vin; vin = vout; vout = tv; }
+	}
+	if (kin != ka)
+		for (u32 i = tid; i < m; i += NB_CS_THREADS) { ka[i] = __ldcg(kb + i); if (HAS_VALS) va[i] = __ldcg(vb + i); }
+}
+
+// A bucket of m > NB_CS_CAP keys (a hot key value such as the ground's tag; region ka/va in the result buffer, kb/vb = the same
+// region of the other buffer, free scratch) is split once more by ONE block on the next digit `level` (counting sort ka -> kb,
+// tile by tile); consecutive sub-buckets are then grouped into chunks of <= NB_CS_CAP keys, each sorted in registers on digits
+// 0..level (kb -> ka).  A single sub-bucket that is still too large goes through cs_block_lsd.
+template<bool HAS_VALS>
+NB_DEV void cs_bucket_split(CoopSortSmem& S, u64* ka, u32* va, u64* kb, u32* vb, u32 m, const SortPasses& P, int level) {
+	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (level < 0) return;  // no digits left: the bucket is already in order
+	{
+		u64 key[NB_CS_ITEMS]; u32 val[NB_CS_ITEMS], dg[NB_CS_ITEMS], rk[NB_CS_ITEMS];
+		const u32 shift = (u32)P.shift[level];
+		if (tid < 256) S.h[tid] = 0;
 		__syncthreads();
-		u32 mine = 0;  // keys of digit tid in blocks before this one
-		if (!small) {
-			if (tid < 256) hist[b * 256 + tid] = h[tid];
-			grid_barrier(bar, G);
+		for (u32 i = tid; i < m; i += NB_CS_THREADS) atomicAdd(&S.h[(u32)(__ldcg(ka + i) >> shift) & 0xff], 1u);
+		__syncthreads();
+		cs_scan_digits(S, S.h, 0);
+		if (tid < 256) { S.total[0][tid] = S.h[tid]; S.total[1][tid] = S.running[tid]; }  // sub-bucket sizes and starts
+		for (u32 base = 0; base < m; base += NB_CS_TILE) {
+			#pragma unroll
+			for (int r = 0; r < NB_CS_ITEMS; ++r) {
+				u32 i = base + wid * (32 * NB_CS_ITEMS) + r * 32 + lane;
+				key[r] = i < m ? __ldcg(ka + i) : 0;
+				if (HAS_VALS) val[r] = i < m ? __ldcg(va + i) : 0;
+			}
+			cs_rank<NB_CS_ITEMS>(S, key, m - base, cs_plain((int)shift), dg, rk);
+			#pragma unroll
+			for (int r = 0; r < NB_CS_ITEMS; ++r)
+				if (dg[r] != 0xffffffffu) {
+					u32 pos = S.running[dg[r]] + S.wc[wid][dg[r]] + rk[r];
+					kb[pos] = key[r];
+					if (HAS_VALS) vb[pos] = val[r];
+				}
+			__syncthreads();
+			if (tid < 256) S.running[tid] += S.tot[tid];
+			__syncthreads();
+		}
+	}
+	for (u32 d = 0; d < 256; ) {  // uniform across the block: everybody reads the same table
+		u32 gs = S.total[1][d], gm = S.total[0][d], e = d + 1;
+		if (gm <= NB_CS_CAP) while (e < 256 && gm + S.total[0][e] <= NB_CS_CAP) { gm += S.total[0][e]; ++e; }
+		if (gm > NB_CS_CAP) {  // one value of this digit alone overflows the registers: LSD on the digits below, then move over
+			cs_block_lsd<HAS_VALS>(S, kb + gs, vb + gs, ka + gs, va + gs, gm, P, level);
+			__syncthreads();
+			for (u32 i = tid; i < gm; i += NB_CS_THREADS) { ka[gs + i] = __ldcg(kb + gs + i); if (HAS_VALS) va[gs + i] = __ldcg(vb + gs + i); }
+		}
+		else if (gm) cs_local_sort<HAS_VALS>(S, kb + gs, vb + gs, ka + gs, va + gs, gm, P, level + 1);
+		__syncthreads();
+		d = e;
+	}
+}
+
+template<bool HAS_VALS>
+__global__ void __launch_bounds__(NB_CS_THREADS) k_sort_coop(u64* k0, u64* k1, u32* v0, u32* v1, const u32* n_ptr, u32* hist /*[gridDim][256]*/, u32* bar, SortPasses P, const u64* keybits /* OR, AND of the keys, or null */) {
+	extern __shared__ __align__(16) unsigned char cs_smem_raw[];
+	CoopSortSmem& S = *reinterpret_cast<CoopSortSmem*>(cs_smem_raw);
+	const u32 n = *n_ptr;
+	if (n == 0) return;
+	if (n <= NB_CS_CAP) {
+		if (blockIdx.x == 0) cs_local_sort<HAS_VALS>(S, k0, v0, k1, v1, n, P, P.n);
+		return;
+	}
+	const u32 G = gridDim.x, b = blockIdx.x;
+	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const u32 tiles = (n + NB_CS_TILE - 1) / NB_CS_TILE, per = (tiles + G - 1) / G;
+	const u32 begin = min(n, b * per * NB_CS_TILE), end = min(n, begin + per * NB_CS_TILE);
+	u64 key[NB_CS_ITEMS]; u32 val[NB_CS_ITEMS], dg[NB_CS_ITEMS], rk[NB_CS_ITEMS];
+
+	// one global counting-sort pass on digit `shift` from (kin, vin) to (kout, vout); leaves S.h = digit totals of the whole input
+	auto global_pass = [&](const u64* kin, const u32* vin, u64* kout, u32* vout, const CsDigit& D) {
+		if (tid < 256) S.h[tid] = 0;
+		__syncthreads();
+		for (u32 i = begin + tid; i < end; i += NB_CS_THREADS) atomicAdd(&S.h[cs_digit(D, __ldcg(kin + i))], 1u);
+		__syncthreads();
+		if (tid < 256) hist[b * 256 + tid] = S.h[tid];
+		grid_barrier(bar, G);
+		{
 			u32 d = tid & 255, q = tid >> 8, bl = 0, tt = 0;
 			for (u32 r0 = q; r0 < G; r0 += 32) {  // eight independent loads in flight per round trip
 				u32 v[8];
@@ -359,47 +504,101 @@ __global__ void __launch_bounds__(NB_CS_THREADS) k_sort_coop(u64* k0, u64* k1, u
 				#pragma unroll
 				for (int u = 0; u < 8; ++u) { tt += v[u]; if (r0 + 4 * u < b) bl += v[u]; }
 			}
-			below[q][d] = bl; total[q][d] = tt;
-			__syncthreads();
-			if (tid < 256) { h[tid] = total[0][tid] + total[1][tid] + total[2][tid] + total[3][tid]; mine = below[0][tid] + below[1][tid] + below[2][tid] + below[3][tid]; }
+			S.below[q][d] = bl; S.total[q][d] = tt;
 		}
-		{	// exclusive scan of the 256 digit totals (threads 0..255 = warps 0..7)
-			u32 t = tid < 256 ? h[tid] : 0;
-			u32 incl = warp_incl_scan(t);
-			if (tid < 256 && lane == 31) sm[wid] = incl;
-			__syncthreads();
-			if (wid == 0) { u32 w = lane < 8 ? sm[lane] : 0; u32 wi = warp_incl_scan(w); if (lane < 8) sm[lane] = wi - w; }
-			__syncthreads();
-			if (tid < 256) running[tid] = incl - t + sm[wid] + mine;
-			__syncthreads();
-		}
-		if (fused) scatter_tile();
-		else
-			for (u32 base = begin; base < end; base += NB_CS_TILE) {
-				rank_tile(base);
-				scatter_tile();
-				__syncthreads();
-				if (tid < 256) running[tid] += tot[tid];
+		__syncthreads();
+		u32 mine = 0;  // keys of digit tid in blocks before this one
+		if (tid < 256) { S.h[tid] = S.total[0][tid] + S.total[1][tid] + S.total[2][tid] + S.total[3][tid]; mine = S.below[0][tid] + S.below[1][tid] + S.below[2][tid] + S.below[3][tid]; }
+		__syncthreads();
+	};
+	auto global_scatter = [&](const u64* kin, const u32* vin, u64* kout, u32* vout, const CsDigit& D, u32 mine) {
+		cs_scan_digits(S, S.h, mine);
+		for (u32 base = begin; base < end; base += NB_CS_TILE) {
+			#pragma unroll
+			for (int r = 0; r < NB_CS_ITEMS; ++r) {
+				u32 i = base + wid * (32 * NB_CS_ITEMS) + r * 32 + lane;
+				key[r] = i < end ? __ldcg(kin + i) : 0;
+				if (HAS_VALS) val[r] = i < end ? __ldcg(vin + i) : 0;
 			}
-		if (!small) grid_barrier(bar, G);
-		else { __threadfence(); __syncthreads(); }
+			cs_rank<NB_CS_ITEMS>(S, key, end - base, D, dg, rk);
+			#pragma unroll
+			for (int r = 0; r < NB_CS_ITEMS; ++r)
+				if (dg[r] != 0xffffffffu) {
+					u32 pos = S.running[dg[r]] + S.wc[wid][dg[r]] + rk[r];
+					kout[pos] = key[r];
+					if (HAS_VALS) vout[pos] = val[r];
+				}
+			__syncthreads();
+			if (tid < 256) S.running[tid] += S.tot[tid];
+			__syncthreads();
+		}
+	};
+	// `mine` has to survive between the two lambdas: recompute it from S.below (still intact)
+	auto mine_of = [&]() { return tid < 256 ? S.below[0][tid] + S.below[1][tid] + S.below[2][tid] + S.below[3][tid] : 0u; };
+
+	// ---- top digit first ----
+	CsDigit top = cs_plain(P.shift[P.n - 1]);
+	int nlocal = P.n - 1;  // digits left for the buckets
+	if (keybits) {
+		u64 varying = keybits[0] ^ keybits[1];
+		top.np = 0; top.pos = 0;
+		while (varying && top.np < 8) { u32 bit = 63 - __clzll((long long)varying); top.pos |= (u64)bit << (8 * top.np); ++top.np; varying &= ~((u64)1 << bit); }
+		if (top.np) nlocal = P.n; else top = cs_plain(P.shift[P.n - 1]);  // (all keys equal: any digit will do)
+	}
+	global_pass(k0, v0, k1, v1, top);
+	const int oversize = __syncthreads_or(tid < 256 && S.h[tid] > 8 * NB_CS_CAP);  // same answer in every block
+	if (!oversize) {
+		global_scatter(k0, v0, k1, v1, top, mine_of());
+		__syncthreads();
+		if (tid < 256) S.below[0][tid] = S.h[tid];  // bucket sizes; bucket starts = their exclusive scan
+		__syncthreads();
+		cs_scan_digits(S, S.below[0], 0);
+		if (tid < 256) S.below[1][tid] = S.running[tid];
+		grid_barrier(bar, G);
+		for (u32 d = b; d < 256; d += G) {
+			const u32 m = S.below[0][d], s = S.below[1][d];
+			if (m > NB_CS_CAP) cs_bucket_split<HAS_VALS>(S, k1 + s, v1 + s, k0 + s, v0 + s, m, P, nlocal - 1);
+			else if (m) cs_local_sort<HAS_VALS>(S, k1 + s, v1 + s, k1 + s, v1 + s, m, P, nlocal);
+			__syncthreads();
+		}
+		return;
+	}
+	// ---- skewed keys: LSD over all digits ----
+	grid_barrier(bar, G);  // every block is done with the top-digit matrix before it is reused
+	u64* kin = k0; u64* kout = k1; u32* vin = v0; u32* vout = v1;
+	for (int p = 0; p < P.n; ++p) {
+		if (p || top.np || P.n > 1) global_pass(kin, vin, kout, vout, cs_plain(P.shift[p]));
+		// (one plain digit: its histogram is already in place)
+		global_scatter(kin, vin, kout, vout, cs_plain(P.shift[p]), mine_of());
+		grid_barrier(bar, G);
 		{ u64* t = kin; kin = kout; kout = t; u32* tv = vin; vin = vout; vout = tv; }
 	}
+	if (kin != k1)  // an even number of digits ended in k0/v0: the result belongs in k1/v1
+		for (u32 i = blockIdx.x * NB_CS_THREADS + tid; i < n; i += G * NB_CS_THREADS) { k1[i] = __ldcg(k0 + i); if (HAS_VALS) v1[i] = __ldcg(v0 + i); }
 }
 
-struct SortBuffers { u64* keys[2]; u32* vals[2]; u32* hist; u32* block_sums; u32* bar; int coop_blocks; /* 0 = three launches per pass */ };
+struct SortBuffers { u64* keys[2]; u32* vals[2]; u32* hist; u32* block_sums; u32* bar; int coop_blocks; /* 0 = three launches per pass */ int coop_launch; };
 
 // Sorts bits [begin_bit, end_bit) of keys[cur] (+vals[cur]); returns which buffer (0/1) holds the result.
-static int nb_radix_sort(const Launch& L, const SortBuffers& B, const u32* n_ptr, int begin_bit, int end_bit, bool has_vals, int cur, int begin_bit2 = 0, int end_bit2 = 0) {
+static int nb_radix_sort(const Launch& L, const SortBuffers& B, const u32* n_ptr, int begin_bit, int end_bit, bool has_vals, int cur, int begin_bit2 = 0, int end_bit2 = 0, const u64* keybits = nullptr) {
 	if (B.coop_blocks) {
+		// 8-bit digits, top-aligned per bit range; the lowest digit of a range may overlap the next one (harmless for LSD order)
 		SortPasses P; P.n = 0;
-		for (int shift = begin_bit; shift < end_bit; shift += 8) P.shift[P.n++] = shift;
-		for (int shift = begin_bit2; shift < end_bit2; shift += 8) P.shift[P.n++] = shift;
+		auto add_range = [&](int lo, int hi) {
+			int first = P.n;
+			for (int shift = hi - 8; shift > lo; shift -= 8) P.shift[P.n++] = shift;
+			if (hi > lo) P.shift[P.n++] = lo;
+			for (int i = first, j = P.n - 1; i < j; ++i, --j) { int t = P.shift[i]; P.shift[i] = P.shift[j]; P.shift[j] = t; }  // ascending
+		};
+		add_range(begin_bit, end_bit);
+		add_range(begin_bit2, end_bit2);
 		u64* k0 = B.keys[cur]; u64* k1 = B.keys[cur ^ 1]; u32* v0 = B.vals[cur]; u32* v1 = B.vals[cur ^ 1]; u32* hist = B.hist; u32* bar = B.bar;
-		void* args[] = { &k0, &k1, &v0, &v1, &n_ptr, &hist, &bar, &P };
-		cudaLaunchCooperativeKernel(has_vals ? (void*)k_sort_coop<true> : (void*)k_sort_coop<false>, dim3(B.coop_blocks), dim3(NB_CS_THREADS), args, 0, L.stream);
+		void* args[] = { &k0, &k1, &v0, &v1, &n_ptr, &hist, &bar, &P, &keybits };
+		if (B.coop_launch) cudaLaunchCooperativeKernel(has_vals ? (void*)k_sort_coop<true> : (void*)k_sort_coop<false>, dim3(B.coop_blocks), dim3(NB_CS_THREADS), args, sizeof(CoopSortSmem), L.stream);
+		else if (has_vals) k_sort_coop<true><<<B.coop_blocks, NB_CS_THREADS, sizeof(CoopSortSmem), L.stream>>>(k0, k1, v0, v1, n_ptr, hist, bar, P, keybits);
+		else k_sort_coop<false><<<B.coop_blocks, NB_CS_THREADS, sizeof(CoopSortSmem), L.stream>>>(k0, k1, v0, v1, n_ptr, hist, bar, P, keybits);
 		*L.counter += 1;
-		return cur ^ (P.n & 1);
+		return cur ^ 1;
 	}
 	if (end_bit2 > begin_bit2) { cur = nb_radix_sort(L, B, n_ptr, begin_bit, end_bit, has_vals, cur); begin_bit = begin_bit2; end_bit = end_bit2; }
 	for (int shift = begin_bit; shift < end_bit; shift += 8) {
