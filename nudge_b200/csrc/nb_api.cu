@@ -177,10 +177,12 @@ int nb_create(const nb_config* config, nb_context** out) {
 	// Grid-synchronising kernels (one block per SM for the sort, the occupancy-derived grid for the solver) are launched as
 	// ordinary kernels unless NB_COOP_LAUNCH=1: the grid fits the idle device by construction, and a cooperative launch costs
 	// several microseconds more per launch.
+	if (const char* e = getenv("NB_PREFER_SHARED")) { if (atoi(e)) CK(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared)); }
 	{ const char* e = getenv("NB_COOP_LAUNCH"); ctx->coop_launch = e ? atoi(e) != 0 : NB_DEFAULT_COOP_LAUNCH; ctx->sb.coop_launch = ctx->coop_launch; }
 	CK(cudaFuncSetAttribute(k_sort_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopSortSmem)));
 	CK(cudaFuncSetAttribute(k_sort_coop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopSortSmem))); ALLOC(ctx->sb.block_sums, 8 * NB_SCAN_GRID);
-	ALLOC(ctx->flags, 5 * (size_t)ctx->stride); ALLOC(ctx->offs, 5 * (size_t)ctx->stride); ALLOC(ctx->block_sums, 8 * NB_SCAN_GRID);
+	ALLOC(ctx->flags, 5 * (size_t)ctx->stride); ALLOC(ctx->offs, 5 * (size_t)ctx->stride); ALLOC(ctx->block_sums, 16 * NB_SCAN_GRID);
+	{ const char* e = getenv("NB_SCAN"); g_nb_scan_three_kernels = !(e && !strcmp(e, "single")); }  // the single-launch variant measured slower (profiles/)
 	ALLOC(ctx->live, P); ALLOC(ctx->np_pen, P); ALLOC(ctx->np_info, P); ALLOC(ctx->np_list, P); ALLOC(ctx->np_start, P);
 	ALLOC(ctx->staged.data, 2 * (size_t)C); ALLOC(ctx->staged.bodies, C); ALLOC(ctx->staged.tags, C); ALLOC(ctx->staged.features, C);
 	ALLOC(ctx->fin.data, 2 * (size_t)C); ALLOC(ctx->fin.bodies, C); ALLOC(ctx->fin.tags, C); ALLOC(ctx->fin.features, C);
@@ -377,7 +379,7 @@ int nb_collide(nb_context* ctx, void* stream) {
 	else {
 		CK(cudaMemsetAsync(ctx->table_keys, 0xff, sizeof(u64) * ((size_t)ctx->table_mask + 1), st));
 		k_grid_setup<<<1, 1, 0, st>>>(K, counts);
-		k_grid_build<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->order, T.mn[0], T.mx[0], ctx->mkeys, ctx->smallf, ctx->large_list, ctx->table_keys, ctx->table_vals, ctx->table_mask, counts);
+		k_grid_build<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->order, (float4*)T.mn[0], T.mx[0], ctx->mkeys, ctx->smallf, ctx->large_list, ctx->table_keys, ctx->table_vals, ctx->table_mask, counts);
 		k_grid_pairs<<<GRID((size_t)K * 32), NB_BLOCK, 0, st>>>(K, ctx->order, T.mn[0], T.mx[0], ctx->smallf, ctx->mkeys, ctx->table_keys, ctx->table_vals, ctx->table_mask, ctx->kbits, ctx->sb.keys[0], ctx->cfg.max_pairs, counts);
 		k_large_pairs<<<GRID(K), NB_BLOCK, 0, st>>>(K, ctx->order, T.mn[0], T.mx[0], ctx->smallf, ctx->large_list, ctx->kbits, ctx->sb.keys[0], ctx->cfg.max_pairs, counts);
 		ctx->launches += 4;

@@ -338,7 +338,7 @@ __global__ void k_grid_setup(u32 K, u32* counts) {
 	counts[CNT_GRID_LEVEL] = j; counts[CNT_LARGE] = 0;
 }
 
-__global__ void __launch_bounds__(NB_BLOCK) k_grid_build(u32 K, const u32* order, const float4* leaf_min, const float4* leaf_max, const u64* mkeys,
+__global__ void __launch_bounds__(NB_BLOCK) k_grid_build(u32 K, const u32* order, float4* leaf_min, const float4* leaf_max, const u64* mkeys,
 		uint8_t* smallf, u32* large_list, u64* table_keys, u64* table_vals, u32 table_mask, u32* counts) {
 	const MortonFrame f = morton_frame(counts);
 	const u32 j = counts[CNT_GRID_LEVEL];
@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(NB_BLOCK) k_grid_build(u32 K, const u32* order
 		u32 qx, qy, qz; morton_quantise(f, lo, order[p], qx, qy, qz);
 		bool small = grid_level_needed(lo, hi, f.L[0]) <= j && qx < 65536u && qy < 65536u && qz < 65536u;  // NaN extents are "large" too
 		smallf[p] = small ? 1 : 0;
+		lo.w = small ? -INFINITY : INFINITY; leaf_min[p] = lo;  // k_grid_pairs reads the class with the box: 0 > lo.w <=> small
 		if (!small) large_list[atomicAdd(&counts[CNT_LARGE], 1u)] = p;
 		const u64 prefix = mkeys[p] >> (3 * j);
 		if (p == 0 || (mkeys[p - 1] >> (3 * j)) != prefix) {  // first collider of its cell: publish the cell's range
@@ -407,8 +408,12 @@ __global__ void __launch_bounds__(NB_BLOCK) k_grid_pairs(u32 K, const u32* order
 		u32 qb = 0, len = 0;
 		if (lane < 27) {
 			u32 qx, qy, qz; morton_quantise(f, lo, order[p], qx, qy, qz);
-			const int nx = (int)(qx >> j) + dx, ny = (int)(qy >> j) + dy, nz = (int)(qz >> j) + dz;
-			if (nx >= 0 && ny >= 0 && nz >= 0 && nx < ncell && ny < ncell && nz < ncell) {
+			// a cell on the + side only matters if this box reaches into it (max corner quantised like the min corner, +1 for rounding)
+			u32 hx, hy, hz; morton_quantise(f, hi, order[p], hx, hy, hz);
+			const int cx = (int)(qx >> j), cy = (int)(qy >> j), cz = (int)(qz >> j);
+			const bool reach = (dx <= 0 || ((hx + 1) >> j) > (u32)cx) && (dy <= 0 || ((hy + 1) >> j) > (u32)cy) && (dz <= 0 || ((hz + 1) >> j) > (u32)cz);
+			const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+			if (reach && nx >= 0 && ny >= 0 && nz >= 0 && nx < ncell && ny < ncell && nz < ncell) {
 				const u64 prefix = morton48_of((u32)nx << j, (u32)ny << j, (u32)nz << j) >> (3 * j);
 				if (prefix >= (mkeys[p] >> (3 * j))) {
 					u32 slot = grid_hash(prefix, table_mask);
@@ -435,7 +440,12 @@ __global__ void __launch_bounds__(NB_BLOCK) k_grid_pairs(u32 K, const u32* order
 				if (c + step < 32 && probe <= t) c += step;
 			}
 			const u32 q = __shfl_sync(0xffffffffu, qb, c) + (t - __shfl_sync(0xffffffffu, off, c));
-			if (t < total && smallf[q] && boxes_overlap(lo, hi, leaf_min[q], leaf_max[q])) {
+			bool hit = false;
+			if (t < total) {
+				const float4 a = __ldg(leaf_min + q), bq = __ldg(leaf_max + q);  // two 128-bit loads; a.w carries the class
+				hit = (bq.x > lo.x) & (hi.x > a.x) & (bq.y > lo.y) & (hi.y > a.y) & (bq.z > lo.z) & (hi.z > a.z) & (0.0f > a.w);  // strict, nudge.cpp:3306-3310
+			}
+			if (hit) {
 				u32 slot = atomicAdd(&fill[wid], 1u);
 				if (slot < NB_GP_BUF) buf[wid][slot] = hi_key | (u64)order[q];
 				else {  // more than a buffer of hits from one step: straight to the list

@@ -127,8 +127,103 @@ __global__ void __launch_bounds__(NB_BLOCK) k_scan_down(const u32* in, u32* out,
 	}
 }
 
+// The same scan in ONE launch (decoupled look-back): every block sums its range and publishes (flag | sum) per counter, the
+// first warp looks back over its predecessors' words 32 at a time until it meets an inclusive prefix, publishes its own, and the
+// block writes its outputs.  status: u64[N][grid] + one u32 completion counter behind it, all zero between launches (the last
+// block to finish its look-back clears them, so a launch needs no host-side epoch and replays from a CUDA graph).
+#define NB_SCAN_AGG  ((u64)1 << 32)
+#define NB_SCAN_INCL ((u64)2 << 32)
 template<int N>
-static void nb_scan(const Launch& L, const u32* in, u32* out, u32 stride, const u32* n_ptr, u32 n_host, u32* block_sums /*N*NB_SCAN_GRID*/, u32* totals) {
+__global__ void __launch_bounds__(NB_BLOCK) k_scan_single(const u32* in, u32* out, u32 stride, const u32* n_ptr, u32 n_host, u64* status, u32* totals) {
+	__shared__ u32 sm[NB_WARPS + 1];
+	__shared__ u32 s_excl[N];
+	const u32 G = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31;
+	u32* done = reinterpret_cast<u32*>(status + (size_t)N * G);
+	u32 n = n_ptr ? *n_ptr : n_host;
+	u32 begin, end; scan_tile_range(n, begin, end);
+	u32 acc[N];
+	#pragma unroll
+	for (int c = 0; c < N; ++c) acc[c] = 0;
+	for (u32 i = begin + threadIdx.x; i < end; i += NB_BLOCK)
+		#pragma unroll
+		for (int c = 0; c < N; ++c) acc[c] += in[c*stride + i];
+	u32 sum[N];
+	#pragma unroll
+	for (int c = 0; c < N; ++c) { block_excl_scan(acc[c], &sum[c], sm); }
+	if (threadIdx.x < 32) {
+		volatile u64* st = status;
+		if (lane == 0) {
+			#pragma unroll
+			for (int c = 0; c < N; ++c) st[(size_t)c * G + b] = (b ? NB_SCAN_AGG : NB_SCAN_INCL) | sum[c];
+		}
+		u32 excl[N];
+		#pragma unroll
+		for (int c = 0; c < N; ++c) excl[c] = 0;
+		u32 open_mask = (1u << N) - 1u;  // counters whose look-back has not met an inclusive prefix yet
+		for (int j = (int)b - 1; j >= 0 && open_mask; j -= 32) {  // window j, j-1, ..., j-31; all counters in one round trip
+			int idx = j - (int)lane;
+			u64 w[N];
+			#pragma unroll
+			for (int c = 0; c < N; ++c) {
+				w[c] = NB_SCAN_INCL;  // lanes before block 0 read as "inclusive prefix 0"
+				if (idx >= 0 && ((open_mask >> c) & 1)) w[c] = st[(size_t)c * G + idx];
+			}
+			#pragma unroll
+			for (int c = 0; c < N; ++c) {
+				if (!((open_mask >> c) & 1)) continue;
+				if (idx >= 0) while ((w[c] >> 32) == 0) w[c] = st[(size_t)c * G + idx];
+				u32 incl_mask = __ballot_sync(0xffffffffu, (w[c] >> 32) == 2);
+				u32 upto = incl_mask ? (u32)__ffs(incl_mask) - 1 : 31;  // nearest inclusive prefix in the window, if any
+				u32 v = lane <= upto ? (u32)w[c] : 0;
+				#pragma unroll
+				for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+				excl[c] += v;
+				if (incl_mask) open_mask &= ~(1u << c);
+			}
+		}
+		if (lane == 0) {
+			#pragma unroll
+			for (int c = 0; c < N; ++c) {
+				if (b) st[(size_t)c * G + b] = NB_SCAN_INCL | (u32)(excl[c] + sum[c]);
+				s_excl[c] = excl[c];
+				if (b == G - 1 && totals) totals[c] = excl[c] + sum[c];
+			}
+		}
+		__syncwarp();
+		u32 last = 0;
+		if (lane == 0) { __threadfence(); last = atomicAdd(done, 1u) == G - 1; }
+		if (__shfl_sync(0xffffffffu, last, 0)) {  // every look-back is over: clear the words for the next launch
+			for (u32 i = lane; i < (u32)N * G; i += 32) status[i] = 0;
+			if (lane == 0) *done = 0;
+		}
+	}
+	__syncthreads();
+	u32 run[N];
+	#pragma unroll
+	for (int c = 0; c < N; ++c) run[c] = s_excl[c];
+	for (u32 base = begin; base < end; base += NB_BLOCK * NB_SCAN_ITEMS) {
+		u32 i0 = base + threadIdx.x * NB_SCAN_ITEMS;
+		#pragma unroll
+		for (int c = 0; c < N; ++c) {
+			u32 v[NB_SCAN_ITEMS]; u32 s = 0;
+			#pragma unroll
+			for (int k = 0; k < NB_SCAN_ITEMS; ++k) { v[k] = (i0 + k < end) ? in[c*stride + i0 + k] : 0; s += v[k]; }
+			u32 total; u32 ex = block_excl_scan(s, &total, sm) + run[c];
+			#pragma unroll
+			for (int k = 0; k < NB_SCAN_ITEMS; ++k) { if (i0 + k < end) out[c*stride + i0 + k] = ex; ex += v[k]; }
+			run[c] += total;
+		}
+	}
+}
+
+static bool g_nb_scan_three_kernels = true;  // NB_SCAN=single selects k_scan_single (measured slower on B200 at these sizes)
+template<int N>
+static void nb_scan(const Launch& L, const u32* in, u32* out, u32 stride, const u32* n_ptr, u32 n_host, u32* block_sums /*16*NB_SCAN_GRID, zero*/, u32* totals) {
+	if (!g_nb_scan_three_kernels) {
+		k_scan_single<N><<<L.sms, NB_BLOCK, 0, L.stream>>>(in, out, stride, n_ptr, n_host, reinterpret_cast<u64*>(block_sums), totals);
+		*L.counter += 1;
+		return;
+	}
 	k_scan_reduce<N><<<NB_SCAN_GRID, NB_BLOCK, 0, L.stream>>>(in, stride, n_ptr, n_host, block_sums);
 	k_scan_spine<N><<<1, 1024, 0, L.stream>>>(block_sums, totals);
 	k_scan_down<N><<<NB_SCAN_GRID, NB_BLOCK, 0, L.stream>>>(in, out, stride, n_ptr, n_host, block_sums);
@@ -302,24 +397,30 @@ NB_DEV CsDigit cs_plain(int shift) { CsDigit D; D.shift = (u32)shift; D.np = 0; 
 template<int ITEMS>
 NB_DEV void cs_rank(CoopSortSmem& S, const u64 (&key)[ITEMS], u32 nvalid, const CsDigit& D, u32 (&dg)[ITEMS], u32 (&rk)[ITEMS]) {
 	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lt = (1u << lane) - 1u;
-	for (u32 w = tid; w < NB_CS_WARPS * 256; w += NB_CS_THREADS) (&S.wc[0][0])[w] = 0;
+	const u32 nw = min((u32)NB_CS_WARPS, (nvalid + 32 * ITEMS - 1) / (32 * ITEMS));  // warps that hold keys
+	for (u32 w = tid; w < nw * 256; w += NB_CS_THREADS) (&S.wc[0][0])[w] = 0;
 	__syncthreads();
-	#pragma unroll
-	for (int r = 0; r < ITEMS; ++r) {
-		bool valid = wid * (32 * ITEMS) + r * 32 + lane < nvalid;
-		u32 d = valid ? cs_digit(D, key[r]) : 0xffffffffu;
-		u32 peers = __match_any_sync(0xffffffffu, d);
-		u32 leader = __ffs(peers) - 1, old = 0;
-		if (valid && lane == leader) { old = S.wc[wid][d]; S.wc[wid][d] = old + __popc(peers); }
-		old = __shfl_sync(0xffffffffu, old, leader);
-		dg[r] = d; rk[r] = old + __popc(peers & lt);
-		__syncwarp();
+	if (wid < nw) {
+		#pragma unroll
+		for (int r = 0; r < ITEMS; ++r) {
+			bool valid = wid * (32 * ITEMS) + r * 32 + lane < nvalid;
+			u32 d = valid ? cs_digit(D, key[r]) : 0xffffffffu;
+			u32 peers = __match_any_sync(0xffffffffu, d);
+			u32 leader = __ffs(peers) - 1, old = 0;
+			if (valid && lane == leader) { old = S.wc[wid][d]; S.wc[wid][d] = old + __popc(peers); }
+			old = __shfl_sync(0xffffffffu, old, leader);
+			dg[r] = d; rk[r] = old + __popc(peers & lt);
+			__syncwarp();
+		}
+	}
+	else {
+		#pragma unroll
+		for (int r = 0; r < ITEMS; ++r) { dg[r] = 0xffffffffu; rk[r] = 0; }
 	}
 	__syncthreads();
 	if (tid < 256) {
 		u32 sum = 0;
-		#pragma unroll 8
-		for (int w = 0; w < NB_CS_WARPS; ++w) { u32 c = S.wc[w][tid]; S.wc[w][tid] = sum; sum += c; }
+		for (u32 w = 0; w < nw; ++w) { u32 c = S.wc[w][tid]; S.wc[w][tid] = sum; sum += c; }
 		S.tot[tid] = sum;
 	}
 	__syncthreads();
@@ -339,31 +440,31 @@ NB_DEV void cs_scan_digits(CoopSortSmem& S, const u32* src, u32 add) {
 }
 
 // Sorts m <= NB_CS_CAP keys at src[0..m) on digits P.shift[0..npass) entirely inside the block; result to dst[0..m).
-template<bool HAS_VALS>
-NB_DEV void cs_local_sort(CoopSortSmem& S, const u64* ksrc, const u32* vsrc, u64* kdst, u32* vdst, u32 m, const SortPasses& P, int npass) {
+template<bool HAS_VALS, int LOCAL>
+NB_DEV void cs_local_sort_n(CoopSortSmem& S, const u64* ksrc, const u32* vsrc, u64* kdst, u32* vdst, u32 m, const SortPasses& P, int npass) {
 	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	u64 key[NB_CS_LOCAL]; u32 val[NB_CS_LOCAL], dg[NB_CS_LOCAL], rk[NB_CS_LOCAL];
+	u64 key[LOCAL]; u32 val[LOCAL], dg[LOCAL], rk[LOCAL];
 	#pragma unroll
-	for (int r = 0; r < NB_CS_LOCAL; ++r) {
-		u32 i = wid * (32 * NB_CS_LOCAL) + r * 32 + lane;
+	for (int r = 0; r < LOCAL; ++r) {
+		u32 i = wid * (32 * LOCAL) + r * 32 + lane;
 		key[r] = i < m ? __ldcg(ksrc + i) : 0;
 		if (HAS_VALS) val[r] = i < m ? __ldcg(vsrc + i) : 0;
 	}
 	if (npass == 0) {  // nothing left to sort on: plain copy
 		#pragma unroll
-		for (int r = 0; r < NB_CS_LOCAL; ++r) {
-			u32 i = wid * (32 * NB_CS_LOCAL) + r * 32 + lane;
+		for (int r = 0; r < LOCAL; ++r) {
+			u32 i = wid * (32 * LOCAL) + r * 32 + lane;
 			if (i < m) { kdst[i] = key[r]; if (HAS_VALS) vdst[i] = val[r]; }
 		}
 		return;
 	}
 	__syncthreads();  // every key of the bucket is in registers before anything is written back
 	for (int p = 0; p < npass; ++p) {
-		cs_rank<NB_CS_LOCAL>(S, key, m, cs_plain(P.shift[p]), dg, rk);
+		cs_rank<LOCAL>(S, key, m, cs_plain(P.shift[p]), dg, rk);
 		cs_scan_digits(S, S.tot, 0);
 		const bool last = p == npass - 1;
 		#pragma unroll
-		for (int r = 0; r < NB_CS_LOCAL; ++r)
+		for (int r = 0; r < LOCAL; ++r)
 			if (dg[r] != 0xffffffffu) {
 				u32 pos = S.running[dg[r]] + S.wc[wid][dg[r]] + rk[r];
 				if (last) { kdst[pos] = key[r]; if (HAS_VALS) vdst[pos] = val[r]; }
@@ -372,12 +473,21 @@ NB_DEV void cs_local_sort(CoopSortSmem& S, const u64* ksrc, const u32* vsrc, u64
 		__syncthreads();
 		if (!last) {
 			#pragma unroll
-			for (int r = 0; r < NB_CS_LOCAL; ++r) {
-				u32 i = wid * (32 * NB_CS_LOCAL) + r * 32 + lane;
+			for (int r = 0; r < LOCAL; ++r) {
+				u32 i = wid * (32 * LOCAL) + r * 32 + lane;
 				if (i < m) { key[r] = S.skeys[i]; if (HAS_VALS) val[r] = S.svals[i]; }
 			}
 		}
 	}
+}
+
+template<bool HAS_VALS>
+NB_DEV void cs_local_sort(CoopSortSmem& S, const u64* ksrc, const u32* vsrc, u64* kdst, u32* vdst, u32 m, const SortPasses& P, int npass) {
+	// fewer keys per thread for small buckets: the ranking cost grows with the keys a thread holds, not with m
+	if (m <= NB_CS_THREADS) cs_local_sort_n<HAS_VALS, 1>(S, ksrc, vsrc, kdst, vdst, m, P, npass);
+	else if (m <= 2 * NB_CS_THREADS) cs_local_sort_n<HAS_VALS, 2>(S, ksrc, vsrc, kdst, vdst, m, P, npass);
+	else if (m <= 4 * NB_CS_THREADS) cs_local_sort_n<HAS_VALS, 4>(S, ksrc, vsrc, kdst, vdst, m, P, npass);
+	else cs_local_sort_n<HAS_VALS, NB_CS_LOCAL>(S, ksrc, vsrc, kdst, vdst, m, P, npass);
 }
 
 // A bucket that does not fit the registers of one block (m > NB_CS_CAP: a hot key value such as the ground's tag) is still sorted
