@@ -183,6 +183,11 @@ class Sim(abi.HostState):
         s = self.scene
         self._ck(self.lib.nb_step(self.ctx, float(s.time_step), int(s.iterations), float(s.gravity), float(s.damping), self.stream), "nb_step")
 
+    def step_staged(self):
+        """The same sub-step through the seven stage calls (example/main.cpp:274-328)."""
+        self.collide(); self.apply_gravity_damping(); self.read_cached_impulses(); self.setup_contact_constraints()
+        self.apply_impulses(int(self.scene.iterations)); self.update_cached_impulses(); self.write_cached_impulses(); self.advance()
+
     def launch_count(self):
         return int(self.lib.nb_launch_count(self.ctx))
 

@@ -28,6 +28,10 @@ struct nb_context {
 	u32 slots_per_bucket;
 	int coop_blocks_solve; int coop_launch;
 	u64* keybits;  // OR, AND of the Morton codes of the current collide
+	bool defer_warm_start;  // nb_step: the warm start runs inside the first solver launch
+	// nb_step as a CUDA graph: captured once per (stream, parameters, scene shape), replayed afterwards
+	struct StepKey { cudaStream_t stream; float ts, gravity, damping; u32 iterations, B, nboxes, nspheres, nconn, tagbits, kbits; int debug; } graph_key;
+	cudaGraphExec_t graph_exec; unsigned long long graph_launches; int graph_enabled; bool capturing;
 	u32* chain_start; u32* chain_len;  // per body: first entry / number of entries in the (body, batch) chain sort
 	bool contacts_internal;  // the current contact set came from nb_collide (not nb_upload_contacts)
 	u32 solve_backoff_ns;
@@ -177,7 +181,7 @@ int nb_create(const nb_config* config, nb_context** out) {
 	// Grid-synchronising kernels (one block per SM for the sort, the occupancy-derived grid for the solver) are launched as
 	// ordinary kernels unless NB_COOP_LAUNCH=1: the grid fits the idle device by construction, and a cooperative launch costs
 	// several microseconds more per launch.
-	if (const char* e = getenv("NB_PREFER_SHARED")) { if (atoi(e)) CK(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared)); }
+	{ const char* e = getenv("NB_GRAPH"); ctx->graph_enabled = e ? atoi(e) != 0 : 1; }
 	{ const char* e = getenv("NB_COOP_LAUNCH"); ctx->coop_launch = e ? atoi(e) != 0 : NB_DEFAULT_COOP_LAUNCH; ctx->sb.coop_launch = ctx->coop_launch; }
 	CK(cudaFuncSetAttribute(k_sort_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopSortSmem)));
 	CK(cudaFuncSetAttribute(k_sort_coop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopSortSmem))); ALLOC(ctx->sb.block_sums, 8 * NB_SCAN_GRID);
@@ -223,6 +227,7 @@ int nb_create(const nb_config* config, nb_context** out) {
 void nb_destroy(nb_context* ctx) {
 	if (!ctx) return;
 	cudaDeviceSynchronize();
+	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	for (size_t i = 0; i < ctx->allocs.size(); ++i) cudaFree(ctx->allocs[i]);
 	delete ctx;
 }
@@ -496,9 +501,9 @@ static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) 
 	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw);
 	u32 backoff = ctx->solve_backoff_ns;
 	void* args[] = { &R, &impulses, &mw, &mode, &sweeps, &backoff, &counts };
-	if (ctx->coop_launch) CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
+	if (ctx->coop_launch && !ctx->capturing) CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
 	else k_solve<<<ctx->coop_blocks_solve, NB_BLOCK, 0, st>>>(R, impulses, mw, mode, sweeps, backoff, counts);
-	k_mw_out<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw, mode);
+	k_mw_out<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw, mode ? 1 : 0);
 	ctx->launches += 3;
 	return NB_OK;
 }
@@ -523,14 +528,15 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, ctx->slot_idx, ctx->chain_start, ctx->chain_len, ctx->rows.wait, ctx->cstride, counts);
 	k_build_rows<<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts);
 	ctx->launches += 2;
-	int r = launch_solve(ctx, 0, 1, st); if (r) return r;  // warm start (nudge.cpp:4563-4632)
+	if (!ctx->defer_warm_start) { int r = launch_solve(ctx, 0, 1, st); if (r) return r; }  // warm start (nudge.cpp:4563-4632)
 	CK(cudaGetLastError());
 	return NB_OK;
 }
 
 int nb_apply_impulses(nb_context* ctx, uint32_t sweeps, void* stream) {
 	if (!sweeps) return NB_OK;
-	int r = launch_solve(ctx, 1, sweeps, (cudaStream_t)stream); if (r) return r;
+	int r = launch_solve(ctx, ctx->defer_warm_start ? 2 : 1, sweeps, (cudaStream_t)stream); if (r) return r;
+	ctx->defer_warm_start = false;
 	CK(cudaGetLastError());
 	return NB_OK;
 }
@@ -549,16 +555,56 @@ int nb_advance(nb_context* ctx, float time_step, void* stream) {
 	return NB_OK;
 }
 
-int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity, float damping, void* stream) {
+static int step_body(nb_context* ctx, float time_step, uint32_t iterations, float gravity, float damping, void* stream) {
 	int r;
 	if ((r = nb_collide(ctx, stream))) return r;
 	if ((r = nb_apply_gravity_damping(ctx, time_step, gravity, damping, stream))) return r;
 	if ((r = nb_read_cached_impulses(ctx, stream))) return r;
-	if ((r = nb_setup_contact_constraints(ctx, stream))) return r;
-	if ((r = nb_apply_impulses(ctx, iterations, stream))) return r;
+	ctx->defer_warm_start = iterations > 0;  // warm start + sweeps in one solver launch (same arithmetic, same order)
+	r = nb_setup_contact_constraints(ctx, stream);
+	if (!r) r = nb_apply_impulses(ctx, iterations, stream);
+	ctx->defer_warm_start = false;
+	if (r) return r;
 	if ((r = nb_update_cached_impulses(ctx, stream))) return r;
 	if ((r = nb_write_cached_impulses(ctx, stream))) return r;
 	return nb_advance(ctx, time_step, stream);
+}
+
+// One sub-step (example/main.cpp:274-328).  On a capturable stream the ~75 launches are recorded once into a CUDA graph and
+// replayed; every count the kernels need lives in device memory, so the graph only depends on the parameters and the scene
+// shape held in StepKey.  NB_GRAPH=0, the legacy default stream or debug mode use plain launches.
+int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity, float damping, void* stream) {
+	cudaStream_t st = (cudaStream_t)stream;
+	if (!ctx->graph_enabled || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread || ctx->debug)
+		return step_body(ctx, time_step, iterations, gravity, damping, stream);
+	nb_context::StepKey key;
+	memset(&key, 0, sizeof(key));  // padding bytes included: the key is compared with memcmp
+	key.stream = st; key.ts = time_step; key.gravity = gravity; key.damping = damping; key.iterations = iterations;
+	key.B = ctx->B; key.nboxes = ctx->nboxes; key.nspheres = ctx->nspheres; key.nconn = ctx->nconn; key.tagbits = ctx->tagbits; key.kbits = ctx->kbits; key.debug = ctx->debug;
+	if (!ctx->graph_exec || memcmp(&key, &ctx->graph_key, sizeof(key)) != 0) {
+		if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+		const unsigned long long before = ctx->launches;
+		const int coop = ctx->sb.coop_launch;
+		if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); ctx->graph_enabled = 0; return step_body(ctx, time_step, iterations, gravity, damping, stream); }
+		ctx->capturing = true; ctx->sb.coop_launch = 0;  // grid-synchronising kernels go in as ordinary kernel nodes
+		int r = step_body(ctx, time_step, iterations, gravity, damping, stream);
+		ctx->capturing = false; ctx->sb.coop_launch = coop;
+		cudaGraph_t graph = nullptr;
+		cudaError_t e = cudaStreamEndCapture(st, &graph);
+		if (r == NB_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+		if (graph) cudaGraphDestroy(graph);
+		ctx->graph_launches = ctx->launches - before;
+		ctx->launches = before;
+		if (r != NB_OK || e != cudaSuccess || !ctx->graph_exec) {  // capture refused: stay on plain launches
+			cudaGetLastError(); ctx->graph_exec = nullptr; ctx->graph_enabled = 0;
+			return step_body(ctx, time_step, iterations, gravity, damping, stream);
+		}
+		ctx->graph_key = key;
+	}
+	CK(cudaGraphLaunch(ctx->graph_exec, st));
+	ctx->launches += ctx->graph_launches;
+	ctx->contacts_internal = true;
+	return NB_OK;
 }
 
 // ---------------- parity-test introspection ----------------

@@ -673,7 +673,8 @@ NB_DEV void solve_contact(const Rows& R, u32 j, const float (&rv)[ROW_PLANES_TOT
 	bw.z = nb_madd(rv[VB_Z], friction_impulse_y, b_angular_velocity_z);
 }
 
-// mode 0: warm start (one pass); mode 1: `sweeps` PGS sweeps.  Co-resident grid, no barrier.  Thread t owns slots t, t+T, ...
+// mode 0: warm start (one pass); mode 1: `sweeps` PGS sweeps; mode 2: the warm start followed by `sweeps` sweeps in the same
+// launch (nb_step: nothing happens between setup and the first sweep, so the two pipelines can overlap).  Co-resident grid, no barrier.  Thread t owns slots t, t+T, ...
 // (so the per-contact solver state stays private to one thread) and walks them sweep by sweep; within and across threads the
 // items are visited in increasing (sweep, slot), which is a topological order of the dependency graph, so the lowest
 // unfinished item is always runnable.  Inside a warp the lanes poll instead of blocking, so a lane may depend on another
@@ -689,9 +690,10 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve(Rows R, const float4* imp
 	__syncthreads();
 	const u32 NS = 8 * counts[CNT_BATCHES];
 	const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-	const u32 passes = mode ? sweeps : 1;
+	const u32 passes = mode == 0 ? 1 : (mode == 1 ? sweeps : sweeps + 1);
 	const u32 S = R.stride;
-	for (u32 w = 0; w < passes; ++w)
+	for (u32 w = 0; w < passes; ++w) {
+		const bool sweep = mode == 1 || (mode == 2 && w > 0);  // this pass is a PGS sweep (else: the warm start)
 		for (u32 s0 = 0; s0 < NS; s0 += nth) {  // uniform trip count for the whole grid
 			u32 slot = s0 + tid;
 			bool pending = false, near = false;
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve(Rows R, const float4* imp
 				a = R.a[slot]; b = R.b[slot];
 				uint2 wa = R.wait[slot], wb = R.wait[S + slot];
 				exp_a = w * wa.y + wa.x; exp_b = w * wb.y + wb.x;
-				if (mode) {
+				if (sweep) {
 					const float* c = R.plane + slot;
 					#pragma unroll
 					for (int k = 0; k < ROW_PLANES_TOTAL; ++k) rv[k] = c[(size_t)k * S];
@@ -717,7 +719,7 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve(Rows R, const float4* imp
 					u32 ra = a ? exp_a - asu(al.w) : 0, rb = b ? exp_b - asu(bl.w) : 0;
 					u32 r = max(ra, rb);
 					if (r == 0 && near && (!a || asu(aw.w) == exp_a) && (!b || asu(bw.w) == exp_b)) {
-						if (mode) solve_contact(R, slot, rv, st, al, aw, bl, bw, s_rcp, s_rsqrt);
+						if (sweep) solve_contact(R, slot, rv, st, al, aw, bl, bw, s_rcp, s_rsqrt);
 						else warm_start_contact(R, slot, impulses, al, aw, bl, bw, s_rsqrt);
 						if (a) { float tk = asf(exp_a + 1); al.w = tk; aw.w = tk; st128(mw + 2*a, al); st128(mw + 2*a + 1, aw); }  // body 0 is static: never written
 						if (b) { float tk = asf(exp_b + 1); bl.w = tk; bw.w = tk; st128(mw + 2*b, bl); st128(mw + 2*b + 1, bw); }
@@ -732,6 +734,7 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve(Rows R, const float4* imp
 				if (want != 0xffffffffu && want) __nanosleep(min(want, 20000u));
 			}
 		}
+	}
 }
 
 // ---------------- update_cached_impulses (nudge.cpp:4857-4884) ----------------

@@ -288,3 +288,25 @@ def test_config3_one_million_boxes_runs_and_keeps_invariants():
     assert np.isin(pk, allp).all()
     g.download_bodies()
     assert np.isfinite(g.transforms["position"]).all() and g.transforms["position"][1:, 1].min() > -1.0
+
+
+def test_nb_step_graph_replay_equals_staged_calls_and_oracle():
+    """nb_step on a capturable stream (CUDA graph replay, warm start fused into the first solver launch) against the seven stage
+    calls on the default stream and against the oracle: same bits after 25 steps."""
+    import torch
+    from oracle import pyoracle
+    scene = scenes.demo_scene(600, 600)
+    side = torch.cuda.Stream()
+    a = nudge_b200.Sim(scene)                                 # stage calls, default stream
+    b = nudge_b200.Sim(scene, stream=side.cuda_stream)        # nb_step -> graph
+    o = pyoracle.OracleSim(scene, contact_capacity=a.cap)
+    for _ in range(25):
+        a.step_staged(); b.step(); o.step()
+    a.download_bodies(); b.download_bodies()
+    launches_per_step = b.launch_count() / 25.0
+    assert launches_per_step > 10
+    for name in ("transforms", "momentum", "idle"):
+        x, y, z = getattr(a, name), getattr(b, name), getattr(o, name)
+        assert x.tobytes() == y.tobytes(), name
+        assert x.tobytes() == z.tobytes(), name
+    assert b.counts().overflow == 0 and a.counts().contacts == b.counts().contacts > 0
