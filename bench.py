@@ -7,7 +7,26 @@
 Workload (BASELINE.json configs[1]): 65,536 random boxes dropped onto a ground plane, 8 solver iterations, measured on the
 settled pile.  One "step" = one sub-step of example/main.cpp:274-328.  Prints ONE JSON line (see README / DESIGN.md §5)."""
 import argparse, json, os, subprocess, sys, threading, time
-os.environ["NCCL_DEBUG"] = "WARN"  # NCCL otherwise prints its version banner on stdout, which must carry exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+
+# stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version banner through C stdio).
+# File descriptor 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _own_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -28,31 +47,60 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML in-process (a query takes
+    microseconds, so a 40 ms region still gets dozens of samples); `nvidia-smi` once per 0.2 s if pynvml is unavailable."""
+    REASONS = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index = index; self.rows = []; self.stop_flag = False
+        self.index = index; self.rows = []; self.stop_flag = False; self.max_mhz = None; self.nvml = None; self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.handle = pynvml, h
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            n, h = self.nvml, self.handle
+            while not self.stop_flag:
+                try:
+                    mhz = int(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    self.rows.append((mhz, mask))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.rows.append(f)
+                if len(f) >= 6 and f[0].isdigit():
+                    mask = sum(bit for k, (bit, _) in enumerate(self.REASONS) if f[2 + k].lower().startswith("active"))
+                    self.rows.append((int(f[0]), mask))
+                    if f[1].isdigit(): self.max_mhz = int(f[1])
             except Exception:
                 pass
             time.sleep(0.2)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [name for bit, name in self.REASONS if any(r[1] & bit for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def settle_gpu(sim, steps):
@@ -135,7 +183,7 @@ def run_sharded(args, rank, world, local):
             "roofline": {"bound": "hbm", "kernel": "k_solve", "achieved": None, "peak": peaks()[0], "unit": "GB/s", "frac": None, "traffic": None,
                          "note": "per-sweep launches interleaved with the all-gather; see the N=1 line for the solver roofline"},
         }
-        print(json.dumps(line))
+        emit(line)
     dist.destroy_process_group()
 
 
@@ -182,7 +230,8 @@ def run_ours(args):
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
     launches0 = sim.launch_count()
-    if os.environ.get("NB_CUDA_PROFILER"):
+    prof = os.environ.get("NB_CUDA_PROFILER")     # "1": the timed nb_step loop; "staged": the stage-call loop below
+    if prof and prof != "staged":
         torch.cuda.profiler.start()           # ncu --profile-from-start off: capture the timed region only
     wall0 = time.perf_counter()
     for k in range(K):
@@ -192,7 +241,7 @@ def run_ours(args):
         step_ev[k][1].record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
-    if os.environ.get("NB_CUDA_PROFILER"):
+    if prof and prof != "staged":
         torch.cuda.profiler.stop()
     launches = sim.launch_count() - launches0
     if world > 1: dist.barrier()
@@ -203,12 +252,16 @@ def run_ours(args):
     # ---- stage breakdown and the solver's launch time: the same step through the seven stage calls (untimed for `value`) ----
     KS = min(K, 10)
     sstep_ev = [(E(), E()) for _ in range(KS)]; solve_ev = [(E(), E()) for _ in range(KS)]; stage_ev = [(E(), E()) for _ in range(KS)]
+    if prof == "staged":
+        torch.cuda.profiler.start()
     for k in range(KS):
         flush.fill_(k & 255)
         sstep_ev[k][0].record()
         staged_step(solve_ev[k], stage_ev[k])
         sstep_ev[k][1].record()
     torch.cuda.synchronize()
+    if prof == "staged":
+        torch.cuda.profiler.stop()
     solve_ms = [a.elapsed_time(b) for a, b in solve_ev]
     staged_ms = [a.elapsed_time(b) for a, b in sstep_ev]
     stage_ms = {"collide": float(np.mean([sstep_ev[k][0].elapsed_time(stage_ev[k][0]) for k in range(KS)])),
@@ -289,7 +342,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(args)
-    print(json.dumps(line))
+    emit(line)
     if world > 1: dist.destroy_process_group()
 
 
@@ -364,10 +417,11 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "reference",
                              "sample": "8 x 8191-box piles per step; unmodified nudge.cpp, g++ -O3 -mavx2 -mfma, FTZ/DAZ on"},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
+    _own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
