@@ -116,7 +116,11 @@ def run_sharded(args, rank, world, local):
     import torch.distributed as dist
     import nudge_b200
     from nudge_b200 import shard
-    stream = torch.cuda.current_stream().cuda_stream
+    # one non-default stream for everything, so that a whole step (kernels + NCCL all-gathers) can be recorded into a CUDA graph
+    os.environ.setdefault("NB_COOP_LAUNCH", "0")   # grid-synchronising kernels as ordinary launches: capturable, same speed
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
     g = scenes.box_drop(args.boxes * world, iterations=args.iterations, seed=2)
 
     def make_sim(scene, max_bodies):
@@ -128,6 +132,9 @@ def run_sharded(args, rank, world, local):
             sim.reshard()
         sim.step()
     sim.reshard()
+    for _ in range(2):
+        sim.step()
+    graphed = os.environ.get("NB_GRAPH", "1") != "0" and sim.capture(side)
     for _ in range(max(args.warmup, 3)):
         sim.step()
     K = args.steps
@@ -136,14 +143,14 @@ def run_sharded(args, rank, world, local):
     step_ev = [(E(), E()) for _ in range(K)]
     sampler = ClockSampler(local); sampler.start()
     dist.barrier(); torch.cuda.synchronize()
-    launches0 = sim.sim.launch_count()
+    launches0 = sim.launch_count()
     for k in range(K):
         flush.fill_(k & 255)
         step_ev[k][0].record()
         sim.step()
         step_ev[k][1].record()
     torch.cuda.synchronize()
-    launches = sim.sim.launch_count() - launches0
+    launches = sim.launch_count() - launches0
     dist.barrier()
     sampler.stop_flag = True
     total_ms = float(sum(a.elapsed_time(b) for a, b in step_ev))
@@ -173,6 +180,7 @@ def run_sharded(args, rank, world, local):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "bodies_total": int(g.n_bodies), "bodies_per_gpu_owned": int(ssum[1] / world), "ghost_bodies_per_gpu": int(ssum[2] / world),
                        "exchanged_rows_per_gpu_per_sweep": int(ssum[3] / world), "solver_iterations": int(g.iterations), "contacts_incl_ghost_copies": int(ssum[0]),
+                       "step_call": ("CUDA graph replay of one sharded step (kernels + 9 NCCL all-gathers)" if graphed else "plain launches" + (": " + getattr(sim, "capture_error", "") if getattr(sim, "capture_error", None) else "")),
                        "presim_steps": args.presim, "parallelism": "one scene of %d x 65,536 boxes sharded into %d x-slabs; ghost momentum exchanged by one NCCL all-gather after the warm start and after each sweep (9 per step)" % (world, world),
                        "value_definition": "scene steps/s x (total bodies / 65,536): 65,536-box-equivalent steps per second of the whole job",
                        "scene_steps_per_s": rate, "l2": "flushed between timed steps (256 MiB write), flush excluded", "timing": "CUDA events per step, summed; max over ranks",

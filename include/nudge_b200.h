@@ -109,6 +109,8 @@ int nb_apply_impulses(nb_context*, uint32_t sweeps, void* stream);  /* `sweeps` 
 int nb_update_cached_impulses(nb_context*, void* stream);
 int nb_write_cached_impulses(nb_context*, void* stream);
 int nb_advance(nb_context*, float time_step, void* stream);
+/* One sub-step = the eight calls above in order.  On a stream the caller created (not the legacy default stream) the launches
+ * are recorded once into a CUDA graph and replayed; NB_GRAPH=0 in the environment keeps plain launches. */
 int nb_step(nb_context*, float time_step, uint32_t iterations, float gravity, float damping, void* stream);
 
 /* Kernel-launch counter (every kernel this library launches increments it) and named device buffers for parity tests. */

@@ -129,6 +129,42 @@ class ShardedSim:
 
     # ---- one simulation step (example/main.cpp:274-328) with the exchanges ----
     def step(self):
+        if getattr(self, "graph", None) is not None:
+            self.graph.replay()
+            self.replayed_launches = getattr(self, "replayed_launches", 0) + self.graph_launches
+            return
+        self._step_launches()
+
+    def launch_count(self):
+        """Kernels the library launched for this rank, including the ones replayed from a recorded step."""
+        return self.sim.launch_count() + getattr(self, "replayed_launches", 0)
+
+    def capture(self, torch_stream):
+        """Records one step (the library's launches on `torch_stream` - the stream the Sim was created with - and the NCCL
+        all-gathers) into a CUDA graph; step() replays it until the next reshard().  Returns False (and keeps plain launches) if
+        the capture is refused."""
+        import torch
+        self.graph = None
+        if self.world > 1 and not self.device_exchange:
+            return False
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            before = self.sim.launch_count()
+            with torch.cuda.graph(g, stream=torch_stream):
+                self._step_launches()
+            torch.cuda.synchronize()
+            self.graph_launches = self.sim.launch_count() - before
+            self.graph = g
+            return True
+        except Exception as e:  # noqa: BLE001 - any capture failure means: stay on plain launches
+            self.graph = None
+            self.capture_error = repr(e)
+            try: torch.cuda.synchronize()
+            except Exception: pass
+            return False
+
+    def _step_launches(self):
         sim = self.sim
         sim.collide(); sim.apply_gravity_damping(); sim.read_cached_impulses(); sim.setup_contact_constraints()
         self.exchange()
@@ -156,6 +192,7 @@ class ShardedSim:
         return g
 
     def reshard(self):
+        self.graph = None  # the partition (sizes, export plan) changes: a recorded step is stale
         self.gather_global()
         self._partition()
 
