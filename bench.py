@@ -130,7 +130,8 @@ def run_sharded(args, rank, world, local):
     def make_sim(scene, max_bodies):
         return nudge_b200.Sim(scene, device=local, stream=stream, max_bodies=max_bodies, max_boxes=max_bodies, contact_capacity=30 * max_bodies)
 
-    sim = shard.ShardedSim(g, rank, world, make_sim, halo=8.0, device_exchange=True)
+    dataflow = os.environ.get("NB_SHARD_DATAFLOW", "0") == "1"   # experimental: ghost hand-over inside the solver, peer memory
+    sim = shard.ShardedSim(g, rank, world, make_sim, halo=8.0, device_exchange=True, dataflow=dataflow)
     for k in range(args.presim):
         if k and k % 25 == 0:
             sim.reshard()
@@ -184,6 +185,7 @@ def run_sharded(args, rank, world, local):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "bodies_total": int(g.n_bodies), "bodies_per_gpu_owned": int(ssum[1] / world), "ghost_bodies_per_gpu": int(ssum[2] / world),
                        "exchanged_rows_per_gpu_per_sweep": int(ssum[3] / world), "solver_iterations": int(g.iterations), "contacts_incl_ghost_copies": int(ssum[0]),
+                       "exchange": "solver dataflow over peer-memory inboxes (experimental)" if dataflow else "pack -> ncclAllGather -> unpack after the warm start and after every sweep",
                        "step_call": ("CUDA graph replay of one sharded step (kernels + 9 NCCL all-gathers)" if graphed else "plain launches" + (": " + getattr(sim, "capture_error", "") if getattr(sim, "capture_error", None) else "")),
                        "presim_steps": args.presim, "parallelism": "one scene of %d x 65,536 boxes sharded into %d x-slabs; ghost momentum exchanged by one NCCL all-gather after the warm start and after each sweep (9 per step)" % (world, world),
                        "value_definition": "scene steps/s x (total bodies / 65,536): 65,536-box-equivalent steps per second of the whole job",

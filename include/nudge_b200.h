@@ -100,6 +100,18 @@ int nb_download_transforms(nb_context*, nb_transform* host, uint32_t count, void
 int nb_pack_momentum(nb_context*, const uint32_t* dev_indices, uint32_t n, void* dev_out, void* stream);
 int nb_unpack_momentum(nb_context*, const uint32_t* dev_indices, const uint32_t* dev_sources, uint32_t n, const void* dev_in, void* stream);
 
+/* EXPERIMENTAL (opt-in, not yet validated on hardware): the same ghost exchange carried by the solver's dataflow
+ * over peer memory instead of collectives between launches.  nb_exchange_create allocates this rank's inbox and returns its CUDA IPC
+ * handle (64 bytes); the ranks swap handles out of band and map each other's inbox with nb_exchange_open; nb_exchange_plan uploads, per
+ * local body, its subscribers (CSR exp_off[B+1] over (exp_rank, exp_slot)) and, per ghost body, its inbox slot (0xffffffff otherwise).
+ * A step then calls nb_setup_contact_constraints_deferred (setup without the warm-start launch) and nb_solve_exchange (warm start and
+ * all sweeps in one launch, ghosts fed by their owners' GPUs) in place of nb_setup_contact_constraints + nb_apply_impulses. */
+int nb_exchange_create(nb_context*, uint32_t rank, uint32_t world, uint32_t ghost_capacity, uint32_t max_passes, void* ipc_handle_out);
+int nb_exchange_open(nb_context*, uint32_t peer, const void* ipc_handle);
+int nb_exchange_plan(nb_context*, const uint32_t* exp_off, const uint32_t* exp_rank, const uint32_t* exp_slot, uint32_t n_targets, const uint32_t* ghost_slot, void* stream);
+int nb_setup_contact_constraints_deferred(nb_context*, void* stream);
+int nb_solve_exchange(nb_context*, uint32_t sweeps, void* stream);
+
 /* The simulation step, device resident.  Same order of calls as example/main.cpp:274-328. */
 int nb_collide(nb_context*, void* stream);
 int nb_apply_gravity_damping(nb_context*, float time_step, float gravity, float damping, void* stream);

@@ -16,7 +16,8 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_upload_contacts", "nb_download_bodies", "nb_download_contacts", "nb_download_cache", "nb_download_counts", "nb_upload_momentum", "nb_upload_transforms",
            "nb_download_momentum", "nb_download_transforms", "nb_collide", "nb_apply_gravity_damping", "nb_read_cached_impulses",
            "nb_setup_contact_constraints", "nb_apply_impulses", "nb_update_cached_impulses", "nb_write_cached_impulses", "nb_advance", "nb_step",
-           "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact", "nb_debug_sort", "nb_debug_scan", "nb_debug_enable", "nb_pack_momentum", "nb_unpack_momentum"]
+           "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact", "nb_debug_sort", "nb_debug_scan", "nb_debug_enable", "nb_pack_momentum", "nb_unpack_momentum",
+           "nb_exchange_create", "nb_exchange_open", "nb_exchange_plan", "nb_setup_contact_constraints_deferred", "nb_solve_exchange"]
 
 
 class Config(C.Structure):
@@ -63,6 +64,11 @@ def load_library():
         lib.nb_debug_enable.argtypes = [V, C.c_int]
         lib.nb_pack_momentum.argtypes = [V, V, C.c_uint32, V, V]
         lib.nb_unpack_momentum.argtypes = [V, V, V, C.c_uint32, V, V]
+        lib.nb_exchange_create.argtypes = [V, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, V]
+        lib.nb_exchange_open.argtypes = [V, C.c_uint32, V]
+        lib.nb_exchange_plan.argtypes = [V, V, V, V, C.c_uint32, V, V]
+        lib.nb_setup_contact_constraints_deferred.argtypes = [V, V]
+        lib.nb_solve_exchange.argtypes = [V, C.c_uint32, V]
         _lib = lib
     return _lib
 
@@ -124,6 +130,27 @@ class Sim(abi.HostState):
         self._ck(self.lib.nb_unpack_momentum(self.ctx, C.c_void_p(dev_indices_ptr), C.c_void_p(dev_sources_ptr), int(n), C.c_void_p(dev_in_ptr), self.stream), "nb_unpack_momentum")
 
     # ---- host <-> HBM ----
+    # ---- experimental cross-GPU dataflow exchange (include/nudge_b200.h) ----
+    def exchange_create(self, rank, world, ghost_capacity, max_passes):
+        handle = (C.c_ubyte * 64)()
+        self._ck(self.lib.nb_exchange_create(self.ctx, int(rank), int(world), int(ghost_capacity), int(max_passes), handle), "nb_exchange_create")
+        return bytes(handle)
+
+    def exchange_open(self, peer, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._ck(self.lib.nb_exchange_open(self.ctx, int(peer), buf), "nb_exchange_open")
+
+    def exchange_plan(self, exp_off, exp_rank, exp_slot, ghost_slot):
+        exp_off = np.ascontiguousarray(exp_off, np.uint32); exp_rank = np.ascontiguousarray(exp_rank, np.uint32)
+        exp_slot = np.ascontiguousarray(exp_slot, np.uint32); ghost_slot = np.ascontiguousarray(ghost_slot, np.uint32)
+        self._ck(self.lib.nb_exchange_plan(self.ctx, abi.ptr(exp_off), abi.ptr(exp_rank), abi.ptr(exp_slot), len(exp_rank), abi.ptr(ghost_slot), self.stream), "nb_exchange_plan")
+
+    def setup_contact_constraints_deferred(self):
+        self._ck(self.lib.nb_setup_contact_constraints_deferred(self.ctx, self.stream), "nb_setup_contact_constraints_deferred")
+
+    def solve_exchange(self, sweeps):
+        self._ck(self.lib.nb_solve_exchange(self.ctx, int(sweeps), self.stream), "nb_solve_exchange")
+
     def upload(self):
         self._ck(self.lib.nb_upload_bodies(self.ctx, C.byref(self.bodies), self.stream), "nb_upload_bodies")
         self._ck(self.lib.nb_upload_colliders(self.ctx, C.byref(self.colliders), self.stream), "nb_upload_colliders")

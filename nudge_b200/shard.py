@@ -58,12 +58,39 @@ def local_scene(g, owned, ghosts):
     return s, gids
 
 
+def dataflow_plan(part, rank):
+    """Plan of the experimental peer-memory exchange (include/nudge_b200.h, nb_exchange_*) for one rank, from the partition every
+    rank computes identically.  Local body order is [world, owned..., ghosts...]; ghost j of a rank uses inbox slot j on that rank.
+    Returns exp_off (CSR over local bodies), exp_rank, exp_slot (the subscribers of each owned body) and ghost_slot per local body."""
+    world = len(part["owned"])
+    owned, ghosts = part["owned"][rank], part["ghosts"][rank]
+    n_local = 1 + len(owned) + len(ghosts)
+    local_of = {int(g): 1 + k for k, g in enumerate(owned)}
+    targets = [[] for _ in range(n_local)]
+    for p in range(world):
+        if p == rank:
+            continue
+        for j, g in enumerate(part["ghosts"][p]):
+            k = local_of.get(int(g))
+            if k is not None:               # I own this body: rank p wants it in its inbox slot j
+                targets[k].append((p, j))
+    exp_off = np.zeros(n_local + 1, np.uint32)
+    exp_off[1:] = np.cumsum([len(t) for t in targets])
+    flat = [t for ts in targets for t in ts]
+    exp_rank = np.array([t[0] for t in flat], np.uint32); exp_slot = np.array([t[1] for t in flat], np.uint32)
+    ghost_slot = np.full(n_local, 0xffffffff, np.uint32)
+    ghost_slot[1 + len(owned):] = np.arange(len(ghosts), dtype=np.uint32)
+    return dict(exp_off=exp_off, exp_rank=exp_rank, exp_slot=exp_slot, ghost_slot=ghost_slot)
+
+
 class ShardedSim:
     """One rank of a sharded simulation.  `make_sim(scene, max_bodies)` builds the per-rank simulator (nudge_b200.Sim on the GPU box;
     the CPU oracle in the gloo tests); `comm` is a torch.distributed process group wrapper or None for world_size 1."""
 
-    def __init__(self, global_scene, rank, world, make_sim, halo=8.0, device_exchange=False):
+    def __init__(self, global_scene, rank, world, make_sim, halo=8.0, device_exchange=False, dataflow=False):
         self.g = global_scene.copy()
+        self.dataflow = bool(dataflow) and world > 1   # experimental: ghosts fed through peer-memory inboxes by the solver itself
+        self.dataflow_ready = False
         self.rank, self.world, self.halo = rank, world, float(halo)
         self.make_sim = make_sim
         self.device_exchange = device_exchange
@@ -97,6 +124,22 @@ class ShardedSim:
         self.ghost_source = (owner_of[ghosts] * self.max_export + pos_in_export[ghosts]).astype(np.uint32)
         self.exchange_rows = len(exp[self.rank])
         self._setup_buffers()
+        if self.dataflow:
+            self._setup_dataflow()
+
+    def _setup_dataflow(self):
+        import torch.distributed as dist
+        sim = self.sim
+        if not self.dataflow_ready:   # one inbox per rank for the lifetime of the simulator; handles swapped once
+            cap = int(self.sim.cfg_max_bodies) if hasattr(self.sim, "cfg_max_bodies") else int(1.5 * (self.g.n_bodies / self.world + 2 * 4096) + 64)
+            handle = sim.exchange_create(self.rank, self.world, cap, int(self.g.iterations) + 1)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle)
+            for p in range(self.world):
+                sim.exchange_open(p, handles[p])
+            self.dataflow_ready = True
+        plan = dataflow_plan(self.part, self.rank)
+        sim.exchange_plan(plan["exp_off"], plan["exp_rank"], plan["exp_slot"], plan["ghost_slot"])
 
     def _setup_buffers(self):
         import torch
@@ -166,6 +209,11 @@ class ShardedSim:
 
     def _step_launches(self):
         sim = self.sim
+        if self.dataflow:
+            sim.collide(); sim.apply_gravity_damping(); sim.read_cached_impulses(); sim.setup_contact_constraints_deferred()
+            sim.solve_exchange(int(self.g.iterations))   # warm start + all sweeps, ghost hand-over inside the kernel
+            sim.update_cached_impulses(); sim.write_cached_impulses(); sim.advance()
+            return
         sim.collide(); sim.apply_gravity_damping(); sim.read_cached_impulses(); sim.setup_contact_constraints()
         self.exchange()
         for _ in range(int(self.g.iterations)):

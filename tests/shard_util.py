@@ -46,7 +46,7 @@ def _worker(rank, world, port, kind, steps, reshard_every, out_dir, n_boxes):
     from nudge_b200 import scenes, shard
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = scenes.box_drop(n_boxes, iterations=4, seed=5, spacing=(2.4, 2.2, 2.4))
-    sim = shard.ShardedSim(g, rank, world, make_gpu_sim if kind == "gpu" else make_oracle_sim, halo=6.0)
+    sim = shard.ShardedSim(g, rank, world, make_oracle_sim if kind == "oracle" else make_gpu_sim, halo=6.0, dataflow=(kind == "gpu_dataflow"))
     log = []
     for k in range(steps):
         if reshard_every and k and k % reshard_every == 0:

@@ -233,6 +233,19 @@ def test_sharded_scene_two_ranks_gpu_equals_oracle_ranks():
         assert np.array_equal(a[r]["counts"], b[r]["counts"])
 
 
+@pytest.mark.skipif(os.environ.get("NB_TEST_DATAFLOW") != "1", reason="experimental peer-memory exchange: opt-in until validated on hardware (NB_TEST_DATAFLOW=1)")
+def test_sharded_dataflow_exchange_equals_collective_exchange():
+    """The ghost hand-over carried by the solver's dataflow (nb_exchange_*, inboxes in peer memory) is the same block-Jacobi coupling as
+    the per-sweep collective: identical transforms and velocities on every rank.  (Two ranks on ONE GPU time-slice each other while
+    they wait on each other's kernels, so this is slow there; it is meant for a multi-GPU box.)"""
+    from tests import shard_util
+    a = shard_util.run_ranks(2, "gpu_dataflow", steps=6, reshard_every=4, n_boxes=400)
+    b = shard_util.run_ranks(2, "gpu", steps=6, reshard_every=4, n_boxes=400)
+    for r in range(2):
+        assert np.array_equal(a[r]["transforms"].view(np.uint8), b[r]["transforms"].view(np.uint8))
+        assert np.array_equal(a[r]["momentum"]["velocity"], b[r]["momentum"]["velocity"])
+
+
 def test_body_connections_join_islands():
     """BodyConnections only feed the island passes (nudge.cpp:3511-3575, 3799-3863): a sleeping body connected to an awake one stays active."""
     s = scenes.demo_scene(60, 0, iterations=4, spread=40.0, height=2.0, seed=9)   # far apart: no contacts between boxes

@@ -67,3 +67,30 @@ def test_world2_gloo_ranks_agree_and_are_deterministic():
     # the scene stayed physical: nothing fell through the ground (top at y = 0) and nothing exploded
     y = a[0]["transforms"]["position"][1:, 1]
     assert np.isfinite(a[0]["transforms"]["position"]).all() and y.min() > -0.5 and y.max() < 400.0
+
+
+def test_dataflow_plan_is_consistent_across_ranks():
+    """Host logic of the experimental peer-memory exchange: every ghost slot of every rank is fed by exactly one owner."""
+    import numpy as np
+    from nudge_b200 import shard
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-60, 60, 5000)
+    for world in (2, 3, 5):
+        part = shard.partition(x, world, 8.0)
+        plans = [shard.dataflow_plan(part, r) for r in range(world)]
+        fed = [np.zeros(len(part["ghosts"][p]), np.int64) for p in range(world)]
+        for r in range(world):
+            pl = plans[r]
+            n_owned, n_ghost = len(part["owned"][r]), len(part["ghosts"][r])
+            assert len(pl["exp_off"]) == 1 + n_owned + n_ghost + 1 and pl["exp_off"][-1] == len(pl["exp_rank"])
+            assert pl["exp_off"][1] == 0                                  # the static world body is never exported
+            assert np.all(np.diff(pl["exp_off"].astype(np.int64))[1 + n_owned:] == 0)   # ghosts are never exported
+            assert np.array_equal(pl["ghost_slot"][1 + n_owned:], np.arange(n_ghost)) and np.all(pl["ghost_slot"][:1 + n_owned] == 0xffffffff)
+            for k in range(1, 1 + n_owned):
+                gid = part["owned"][r][k - 1]
+                for t in range(pl["exp_off"][k], pl["exp_off"][k + 1]):
+                    p, j = int(pl["exp_rank"][t]), int(pl["exp_slot"][t])
+                    assert p != r and part["ghosts"][p][j] == gid
+                    fed[p][j] += 1
+        for p in range(world):
+            assert np.all(fed[p] == 1)
