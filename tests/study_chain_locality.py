@@ -1,11 +1,12 @@
 """CPU study for DESIGN.md §7(1): how many hand-offs of the solver's dependency chains would stay inside one thread block
-if contacts were assigned to blocks by spatial cluster?  Uses the CPU oracle (test infrastructure) on a settled pile; no GPU.
+if contacts were assigned to blocks by spatial cluster?  Uses the CPU oracle (test infrastructure, hence under tests/) on a settled
+pile; no GPU.  Not a pytest module: run it by hand.
 
 For every contact (in schedule order) the predecessor on each of its two bodies is an edge of the dependency graph.  A contact is
 owned by the cluster of one of its bodies; an edge is "local" when both contacts have the same owner.  The script reports the
 share of local edges and the length of the critical path when a local hand-off costs `t_local` and a remote one `t_remote`."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import numpy as np
 from nudge_b200 import scenes
 from oracle import pyoracle
