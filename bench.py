@@ -33,7 +33,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from nudge_b200 import scenes  # noqa: E402
 
-WORKLOAD = "64k boxes random drop onto ground plane, 8 solver iters (BASELINE.json configs[1]), settled pile"
+# BASELINE.json configs[0..4] as --config c1..c5.  c2 is the configuration the metric is quoted on (the default; N > 1 scales it weakly:
+# one scene of N x 65,536 boxes).  c3/c4/c5 are fixed-size scenes: on N > 1 GPUs they are sharded (strong scaling).
+CONFIGS = {
+    "c1": dict(workload="reference example scene: 1024 boxes + 1024 spheres falling onto ground, 8 solver iters (BASELINE.json configs[0]), settled",
+               scene=lambda a, w: scenes.demo_scene(1024, 1024, iterations=a.iterations or 8), small=lambda a, seed: scenes.demo_scene(1024, 1024, iterations=a.iterations or 8, seed=seed),
+               presim=700, scaling="weak"),
+    "c2": dict(workload="64k boxes random drop onto ground plane, 8 solver iters (BASELINE.json configs[1]), settled pile",
+               scene=lambda a, w: scenes.box_drop(a.boxes * w, iterations=a.iterations or 8, seed=2), small=lambda a, seed: scenes.box_drop(8191, iterations=a.iterations or 8, seed=seed),
+               presim=900, scaling="weak"),
+    "c3": dict(workload="256k mixed box/sphere stack (50/50), 16 solver iters (BASELINE.json configs[2]), settled",
+               scene=lambda a, w: scenes.mixed_stack(262144, iterations=a.iterations or 16), small=lambda a, seed: scenes.mixed_stack(8190, iterations=a.iterations or 16, seed=seed),
+               presim=500, scaling="strong"),
+    "c4": dict(workload="1M boxes random drop, 8 solver iters (BASELINE.json configs[3]), settled pile",
+               scene=lambda a, w: scenes.box_drop(1 << 20, iterations=a.iterations or 8, seed=2), small=lambda a, seed: scenes.box_drop(8191, iterations=a.iterations or 8, seed=seed),
+               presim=900, scaling="strong"),
+    "c5": dict(workload="256k-box brick wall (running bond, deep stacking), 20 solver iters (BASELINE.json configs[4])",
+               scene=lambda a, w: scenes.brick_wall(262144, iterations=a.iterations or 20), small=lambda a, seed: scenes.brick_wall(8191, iterations=a.iterations or 20),
+               presim=300, scaling="strong"),
+}
 
 
 def peaks():
@@ -125,10 +143,13 @@ def run_sharded(args, rank, world, local):
         side = torch.cuda.Stream()
         torch.cuda.set_stream(side)
     stream = torch.cuda.current_stream().cuda_stream
-    g = scenes.box_drop(args.boxes * world, iterations=args.iterations, seed=2)
+    cfg = CONFIGS[args.config]
+    g = cfg["scene"](args, world)
+    strong = cfg["scaling"] == "strong"
+    unit_bodies = 65536.0 if not strong else float(g.n_bodies - 1)     # `value` counts steps of a scene of this many bodies
 
     def make_sim(scene, max_bodies):
-        return nudge_b200.Sim(scene, device=local, stream=stream, max_bodies=max_bodies, max_boxes=max_bodies, contact_capacity=30 * max_bodies)
+        return nudge_b200.Sim(scene, device=local, stream=stream, max_bodies=max_bodies, max_boxes=max_bodies, max_spheres=(max_bodies if g.n_spheres else 0), contact_capacity=30 * max_bodies)
 
     dataflow = os.environ.get("NB_SHARD_DATAFLOW", "0") == "1"   # experimental: ghost hand-over inside the solver, peer memory
     sim = shard.ShardedSim(g, rank, world, make_sim, halo=8.0, device_exchange=True, dataflow=dataflow)
@@ -181,17 +202,17 @@ def run_sharded(args, rank, world, local):
         total_ms, e2e_ms = float(tmax[0]), float(tmax[1])
         rate = K / (total_ms * 1e-3)
         line = {
-            "metric": "simulation steps/s", "value": rate * world, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bodies_total": int(g.n_bodies), "bodies_per_gpu_owned": int(ssum[1] / world), "ghost_bodies_per_gpu": int(ssum[2] / world),
+            "metric": "simulation steps/s", "value": rate * (g.n_bodies - 1) / unit_bodies, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "config": args.config, "bodies_total": int(g.n_bodies), "bodies_per_gpu_owned": int(ssum[1] / world), "ghost_bodies_per_gpu": int(ssum[2] / world),
                        "exchanged_rows_per_gpu_per_sweep": int(ssum[3] / world), "solver_iterations": int(g.iterations), "contacts_incl_ghost_copies": int(ssum[0]),
                        "exchange": "solver dataflow over peer-memory inboxes (experimental)" if dataflow else "pack -> ncclAllGather -> unpack after the warm start and after every sweep",
                        "step_call": ("CUDA graph replay of one sharded step (kernels + 9 NCCL all-gathers)" if graphed else "plain launches" + (": " + getattr(sim, "capture_error", "") if getattr(sim, "capture_error", None) else "")),
-                       "presim_steps": args.presim, "parallelism": "one scene of %d x 65,536 boxes sharded into %d x-slabs; ghost momentum exchanged by one NCCL all-gather after the warm start and after each sweep (9 per step)" % (world, world),
-                       "value_definition": "scene steps/s x (total bodies / 65,536): 65,536-box-equivalent steps per second of the whole job",
+                       "presim_steps": args.presim, "parallelism": "one scene of %d bodies sharded into %d x-slabs; ghost momentum exchanged by one NCCL all-gather after the warm start and after each sweep" % (g.n_bodies - 1, world),
+                       "value_definition": ("scene steps/s of the fixed-size scene" if strong else "scene steps/s x (total bodies / 65,536): 65,536-box-equivalent steps per second of the whole job"),
                        "scene_steps_per_s": rate, "l2": "flushed between timed steps (256 MiB write), flush excluded", "timing": "CUDA events per step, summed; max over ranks",
                        "solver_mode": "exact reference Gauss-Seidel order inside a rank, block-Jacobi across ranks"},
-            "e2e": {"value": world * K / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(ssum[4]), "d2h_bytes_per_step": int(ssum[5]),
+            "e2e": {"value": ((g.n_bodies - 1) / unit_bodies) * K / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(ssum[4]), "d2h_bytes_per_step": int(ssum[5]),
                     "what": "per rank: nb_upload_bodies (host) + sharded step + nb_download_bodies, every step"},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_solve", "achieved": None, "peak": peaks()[0], "unit": "GB/s", "frac": None, "traffic": None,
@@ -217,7 +238,11 @@ def run_ours(args):
     side = torch.cuda.Stream()
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
-    scene = scenes.box_drop(args.boxes, iterations=args.iterations, seed=2 + rank)
+    cfg = CONFIGS[args.config]
+    if args.config == "c2":
+        scene = scenes.box_drop(args.boxes, iterations=args.iterations or 8, seed=2 + rank)
+    else:
+        scene = cfg["scene"](args, 1)
     sim = nudge_b200.Sim(scene, device=local, stream=stream)
     c = settle_gpu(sim, args.presim)
     if c.overflow:
@@ -339,7 +364,7 @@ def run_ours(args):
     line = {
         "metric": "simulation steps/s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "bodies_per_gpu": scene.n_bodies, "colliders_per_gpu": scene.n_colliders, "solver_iterations": sweeps,
+        "config": {"workload": cfg["workload"], "config": args.config, "bodies_per_gpu": scene.n_bodies, "colliders_per_gpu": scene.n_colliders, "solver_iterations": sweeps,
                    "contacts": int(C), "broadphase_pairs": int(cnt.pairs), "batches": int(cnt.batches),
                    "presim_steps": args.presim, "solver_mode": "exact reference Gauss-Seidel order (per-body dataflow)",
                    "parallelism": "1 GPU" if world == 1 else "%d independent replicas of the workload, one per GPU (no cross-GPU contacts)" % world,
@@ -366,7 +391,7 @@ def cpu_baseline_sample(args):
     8191-box pile of the same generator (the reference's 2^13 collider limit, nudge.cpp:3010), settled on the GPU, then timed."""
     import nudge_b200
     from oracle import pyref
-    s = scenes.box_drop(8191, iterations=args.iterations, seed=77)
+    s = CONFIGS[args.config]["small"](args, 77)
     g = nudge_b200.Sim(s)
     settle_gpu(g, args.presim)
     g.download_bodies(); g.download_cache()
@@ -383,7 +408,7 @@ def cpu_baseline_sample(args):
         r.step(); k += 1
     dt = time.perf_counter() - t0
     return {"value": k / dt, "unit": "steps/s", "cores": 1, "kind": "reference",
-            "sample": "one 8191-box settled pile (%d contacts) of the same generator, %d steps in %.1f s; the reference cannot run 65,536 boxes (nudge.cpp:3010)" % (r.contacts.count, k, dt),
+            "sample": "one %d-body settled scene (%d contacts) of the same generator (%s), %d steps in %.1f s; the reference cannot run more than 8192 colliders (nudge.cpp:3010)" % (s.n_bodies - 1, r.contacts.count, s.name, k, dt),
             "host_cpus": os.cpu_count()}
 
 
@@ -406,7 +431,7 @@ def run_reference(args):
             for th in ths[b:b + threads]: th.join()
 
     def make(t):
-        s = scenes.box_drop(8191, iterations=args.iterations, seed=100 + t)
+        s = CONFIGS[args.config]["small"](args, 100 + t)
         sims[t] = pyref.RefSim(s, fast=True, ftz=True)
         for _ in range(args.ref_presim):
             sims[t].step()
@@ -427,10 +452,11 @@ def run_reference(args):
     contacts = sum(s.contacts.count for s in sims)
     line = {"impl": "reference", "metric": "simulation steps/s", "value": value, "unit": "steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K,
             "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": "8 independent 8191-box piles (65,528 boxes, %d contacts) stepped together, one host thread each" % contacts,
-                       "solver_iterations": args.iterations, "presim_steps": args.ref_presim},
+            "config": {"workload": CONFIGS[args.config]["workload"], "config": args.config,
+                       "sample": "8 independent scenes of the same generator at the reference's size limit (%s: %d bodies each, %d contacts in all) stepped together, one host thread each" % (sims[0].scene.name, sims[0].scene.n_bodies - 1, contacts),
+                       "solver_iterations": int(sims[0].scene.iterations), "presim_steps": args.ref_presim},
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "reference",
-                             "sample": "8 x 8191-box piles per step; unmodified nudge.cpp, g++ -O3 -mavx2 -mfma, FTZ/DAZ on"},
+                             "sample": "8 scenes (%s) per step; unmodified nudge.cpp, g++ -O3 -mavx2 -mfma, FTZ/DAZ on" % sims[0].scene.name},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -443,13 +469,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--boxes", type=int, default=65536)
-    ap.add_argument("--iterations", type=int, default=8)
-    ap.add_argument("--presim", type=int, default=900, help="untimed settling steps before the measurement")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configs[0..4] = c1..c5 (default c2, the configuration the metric is quoted on)")
+    ap.add_argument("--iterations", type=int, default=0, help="solver sweeps per step (0 = the config's own)")
+    ap.add_argument("--presim", type=int, default=-1, help="untimed settling steps before the measurement (-1 = the config's own)")
     ap.add_argument("--ref-presim", type=int, default=700)
     ap.add_argument("--ref-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent copies of the workload instead of one sharded scene")
     args = ap.parse_args()
+    if args.presim < 0:
+        args.presim = CONFIGS[args.config]["presim"]
     if args.impl == "reference":
         run_reference(args)
     else:
@@ -458,7 +487,8 @@ def main():
 
 if __name__ == "__main__":
     main()
-    # the result line is out (os.write on the saved descriptor): leave without interpreter/NCCL/CUDA-graph teardown, which can
-    # block for minutes when a process group or recorded collectives are still alive
     sys.stdout.flush(); sys.stderr.flush()
-    os._exit(0)
+    if os.environ.get("NB_SHARD_GRAPH", "0") == "1" and int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        # opt-in mode only: with NCCL collectives recorded inside a live torch CUDA graph the interpreter teardown blocked once;
+        # every other run exits normally (atexit hooks run, teardown failures show in the exit code)
+        os._exit(0)

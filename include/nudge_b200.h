@@ -89,7 +89,7 @@ int nb_upload_contacts(nb_context*, const nb_contact_data* host /* may be null *
 int nb_download_bodies(nb_context*, nb_body_data* host, void* stream);
 int nb_download_contacts(nb_context*, nb_contact_data* host, nb_active_bodies* host_active, void* stream); /* synchronises */
 int nb_download_cache(nb_context*, nb_contact_cache* host, void* stream);                                  /* synchronises */
-int nb_download_counts(nb_context*, nb_counts* out, void* stream);                                         /* synchronises */
+int nb_download_counts(nb_context*, nb_counts* out, void* stream);   /* synchronises; fills *out and returns NB_ERR_OVERFLOW when out->overflow != 0 */
 int nb_upload_momentum(nb_context*, const nb_body_momentum* host, uint32_t count, void* stream);
 int nb_upload_transforms(nb_context*, const nb_transform* host, uint32_t count, void* stream);
 int nb_download_momentum(nb_context*, nb_body_momentum* host, uint32_t count, void* stream);

@@ -36,6 +36,8 @@ struct nb_context {
 	// nb_step as a CUDA graph: captured once per (stream, parameters, scene shape), replayed afterwards
 	struct StepKey { cudaStream_t stream; float ts, gravity, damping; u32 iterations, B, nboxes, nspheres, nconn, tagbits, kbits; int debug; } graph_key;
 	cudaGraphExec_t graph_exec; unsigned long long graph_launches; int graph_enabled; bool capturing;
+	int graph_is_coop;  // the recorded graph holds cooperative kernel nodes
+	int graph_coop;  // 1: grid-synchronising kernels keep the cooperative-launch attribute inside the captured graph (co-residency guaranteed by the driver)
 	u32* chain_start; u32* chain_len;  // per body: first entry / number of entries in the (body, batch) chain sort
 	bool contacts_internal;  // the current contact set came from nb_collide (not nb_upload_contacts)
 	u32 solve_backoff_ns;
@@ -186,6 +188,7 @@ int nb_create(const nb_config* config, nb_context** out) {
 	// ordinary kernels unless NB_COOP_LAUNCH=1: the grid fits the idle device by construction, and a cooperative launch costs
 	// several microseconds more per launch.
 	{ const char* e = getenv("NB_GRAPH"); ctx->graph_enabled = e ? atoi(e) != 0 : 1; }
+	{ const char* e = getenv("NB_GRAPH_COOP"); ctx->graph_coop = e ? atoi(e) != 0 : 1; }
 	{ const char* e = getenv("NB_COOP_LAUNCH"); ctx->coop_launch = e ? atoi(e) != 0 : NB_DEFAULT_COOP_LAUNCH; ctx->sb.coop_launch = ctx->coop_launch; }
 	CK(cudaFuncSetAttribute(k_sort_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopSortSmem)));
 	CK(cudaFuncSetAttribute(k_sort_coop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopSortSmem))); ALLOC(ctx->sb.block_sums, 8 * NB_SCAN_GRID);
@@ -251,10 +254,11 @@ int nb_upload_bodies(nb_context* ctx, const nb_body_data* h, void* stream) {
 	H2D(ctx->mom, h->momentum, h->count, nb_body_momentum); H2D(ctx->idle, h->idle_counters, h->count, uint8_t);
 	return NB_OK;
 }
-int nb_upload_momentum(nb_context* ctx, const nb_body_momentum* h, uint32_t count, void* stream) { H2D(ctx->mom, h, count, nb_body_momentum); return NB_OK; }
-int nb_upload_transforms(nb_context* ctx, const nb_transform* h, uint32_t count, void* stream) { H2D(ctx->xf, h, count, nb_transform); return NB_OK; }
-int nb_download_momentum(nb_context* ctx, nb_body_momentum* h, uint32_t count, void* stream) { D2H(h, ctx->mom, count, nb_body_momentum); return NB_OK; }
-int nb_download_transforms(nb_context* ctx, nb_transform* h, uint32_t count, void* stream) { D2H(h, ctx->xf, count, nb_transform); return NB_OK; }
+#define ROWS_OK(count) do { if ((count) > ctx->cfg.max_bodies) { ctx->error = "row count exceeds max_bodies"; return NB_ERR_CAPACITY; } } while (0)
+int nb_upload_momentum(nb_context* ctx, const nb_body_momentum* h, uint32_t count, void* stream) { ROWS_OK(count); H2D(ctx->mom, h, count, nb_body_momentum); return NB_OK; }
+int nb_upload_transforms(nb_context* ctx, const nb_transform* h, uint32_t count, void* stream) { ROWS_OK(count); H2D(ctx->xf, h, count, nb_transform); return NB_OK; }
+int nb_download_momentum(nb_context* ctx, nb_body_momentum* h, uint32_t count, void* stream) { ROWS_OK(count); D2H(h, ctx->mom, count, nb_body_momentum); return NB_OK; }
+int nb_download_transforms(nb_context* ctx, nb_transform* h, uint32_t count, void* stream) { ROWS_OK(count); D2H(h, ctx->xf, count, nb_transform); return NB_OK; }
 
 int nb_upload_colliders(nb_context* ctx, const nb_collider_data* h, void* stream) {
 	if (h->boxes.count > ctx->cfg.max_boxes || h->spheres.count > ctx->cfg.max_spheres) { ctx->error = "too many colliders"; return NB_ERR_CAPACITY; }
@@ -301,6 +305,7 @@ int nb_download_counts(nb_context* ctx, nb_counts* out, void* stream) {
 	out->pairs = h[CNT_PAIRS]; out->live_pairs = h[CNT_LIVE_TOTAL]; out->contacts = h[CNT_CONTACTS]; out->sleeping = h[CNT_SLEEPING];
 	out->active = h[CNT_ACTIVE]; out->cache = h[CNT_CACHE]; out->culled = h[CNT_CULLED]; out->batches = h[CNT_BATCHES]; out->levels = h[CNT_LEVELS];
 	out->overflow = h[CNT_OVERFLOW];
+	if (h[CNT_OVERFLOW]) { ctx->error = "capacity overflow during the last step (nb_counts.overflow: 1 pairs, 2 contacts, 4 batch scheduler)"; return NB_ERR_OVERFLOW; }
 	return NB_OK;
 }
 int nb_download_contacts(nb_context* ctx, nb_contact_data* h, nb_active_bodies* ha, void* stream) {
@@ -309,6 +314,8 @@ int nb_download_contacts(nb_context* ctx, nb_contact_data* h, nb_active_bodies* 
 	if (h) {
 		u32 n = c[CNT_CONTACTS], s = c[CNT_SLEEPING];
 		if (n > h->capacity) { ctx->error = "host contact buffer too small"; return NB_ERR_CAPACITY; }
+		// sleeping pairs can number up to the broadphase pairs; the reference sizes that buffer like the contact arrays (nudge.h:73-82)
+		if (h->sleeping_pairs && s > h->capacity) { ctx->error = "host sleeping-pair buffer too small (it is bounded by nb_contact_data.capacity)"; return NB_ERR_CAPACITY; }
 		h->count = n; h->sleeping_count = s;
 		D2H(h->data, ctx->fin.data, n, nb_contact); D2H(h->bodies, ctx->fin.bodies, n, nb_body_pair);
 		D2H(h->tags, ctx->fin.tags, n, u64); D2H(h->features, ctx->fin.features, n, u32);
@@ -506,7 +513,7 @@ static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) 
 	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw);
 	u32 backoff = ctx->solve_backoff_ns;
 	void* args[] = { &R, &impulses, &mw, &mode, &sweeps, &backoff, &counts };
-	if (ctx->coop_launch && !ctx->capturing) CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
+	if (ctx->coop_launch && (!ctx->capturing || ctx->graph_coop)) CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
 	else k_solve<<<ctx->coop_blocks_solve, NB_BLOCK, 0, st>>>(R, impulses, mw, mode, sweeps, backoff, counts);
 	k_mw_out<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw, mode ? 1 : 0);
 	ctx->launches += 3;
@@ -671,20 +678,29 @@ int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity
 	key.B = ctx->B; key.nboxes = ctx->nboxes; key.nspheres = ctx->nspheres; key.nconn = ctx->nconn; key.tagbits = ctx->tagbits; key.kbits = ctx->kbits; key.debug = ctx->debug;
 	if (!ctx->graph_exec || memcmp(&key, &ctx->graph_key, sizeof(key)) != 0) {
 		if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
-		const unsigned long long before = ctx->launches;
-		const int coop = ctx->sb.coop_launch;
-		if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); ctx->graph_enabled = 0; return step_body(ctx, time_step, iterations, gravity, damping, stream); }
-		ctx->capturing = true; ctx->sb.coop_launch = 0;  // grid-synchronising kernels go in as ordinary kernel nodes
-		int r = step_body(ctx, time_step, iterations, gravity, damping, stream);
-		ctx->capturing = false; ctx->sb.coop_launch = coop;
-		cudaGraph_t graph = nullptr;
-		cudaError_t e = cudaStreamEndCapture(st, &graph);
-		if (r == NB_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
-		if (graph) cudaGraphDestroy(graph);
-		ctx->graph_launches = ctx->launches - before;
-		ctx->launches = before;
-		if (r != NB_OK || e != cudaSuccess || !ctx->graph_exec) {  // capture refused: stay on plain launches
-			cudaGetLastError(); ctx->graph_exec = nullptr; ctx->graph_enabled = 0;
+		// Attempt 1 keeps the cooperative-launch attribute on the grid-synchronising kernel nodes (k_sort_coop's software grid barriers,
+		// k_solve's spin waits): the driver then guarantees co-residency at replay, also with other work on the device.  If this
+		// driver refuses cooperative nodes in a capture, attempt 2 records them as ordinary nodes (correct on an otherwise idle device:
+		// their grids are sized from the occupancy calculator), and if that fails too the step stays on plain launches.
+		for (int attempt = ctx->graph_coop ? 0 : 1; attempt < 2 && !ctx->graph_exec; ++attempt) {
+			const unsigned long long before = ctx->launches;
+			const int coop = ctx->sb.coop_launch, gcoop = ctx->graph_coop;
+			if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); break; }
+			ctx->capturing = true;
+			if (attempt == 1) { ctx->sb.coop_launch = 0; ctx->graph_coop = 0; }
+			int r = step_body(ctx, time_step, iterations, gravity, damping, stream);
+			ctx->capturing = false; ctx->sb.coop_launch = coop; ctx->graph_coop = gcoop;
+			cudaGraph_t graph = nullptr;
+			cudaError_t e = cudaStreamEndCapture(st, &graph);
+			if (r == NB_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+			if (graph) cudaGraphDestroy(graph);
+			ctx->graph_launches = ctx->launches - before;
+			ctx->launches = before;
+			if (r != NB_OK || e != cudaSuccess || !ctx->graph_exec) { cudaGetLastError(); ctx->graph_exec = nullptr; if (attempt == 0) ctx->graph_coop = 0; }
+			else ctx->graph_is_coop = attempt == 0;
+		}
+		if (!ctx->graph_exec) {  // capture refused: stay on plain launches
+			ctx->graph_enabled = 0;
 			return step_body(ctx, time_step, iterations, gravity, damping, stream);
 		}
 		ctx->graph_key = key;
@@ -725,6 +741,7 @@ int nb_debug_read(nb_context* ctx, const char* name, void* dst, size_t max_bytes
 		{ "inertia", ctx->inertia, sizeof(float4) * 2 * ctx->B },
 	};
 	if (!strcmp(name, "row_stride")) { if (max_bytes < 4) return NB_ERR_ARGUMENT; *(u32*)dst = ctx->cstride; if (bytes) *bytes = 4; return NB_OK; }
+	if (!strcmp(name, "graph_coop")) { if (max_bytes < 4) return NB_ERR_ARGUMENT; *(u32*)dst = ctx->graph_exec ? (ctx->graph_is_coop ? 2u : 1u) : 0u; if (bytes) *bytes = 4; return NB_OK; }
 	if (!strcmp(name, "kbits")) { if (max_bytes < 4) return NB_ERR_ARGUMENT; *(u32*)dst = ctx->kbits; if (bytes) *bytes = 4; return NB_OK; }
 	for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); ++i)
 		if (!strcmp(name, table[i].name)) {

@@ -377,11 +377,17 @@ __global__ void __launch_bounds__(NB_BLOCK) k_batch_index(const u32* sorted, con
 	u32 left_base[17]; left_base[0] = 0;
 	#pragma unroll
 	for (int k = 0; k < 16; ++k) left_base[k + 1] = left_base[k] + left_count[k];
+	// A schedule that overflowed (k_schedule's slot list, or more batches than the row planes hold) is partial: slot_of / slot_left /
+	// complete_flag are stale beyond the point of failure.  Publish an EMPTY schedule instead (no batches, no chain entries): the
+	// row builder, the solver (which would otherwise wait forever for tokens nobody writes) and update_cached_impulses then do
+	// nothing, and the host sees OVF_SCHED in nb_download_counts / nb_download_contacts (NB_ERR_OVERFLOW).
+	const bool sched_ovf = (counts[CNT_OVERFLOW] & OVF_SCHED) != 0 || 8 * (u64)(nfull + left_base[16]) > max_slots;
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		u32 nb = nfull + left_base[16];
-		if (8 * nb > max_slots) { atomicOr(&counts[CNT_OVERFLOW], OVF_SCHED); nb = max_slots / 8; }
-		counts[CNT_BATCHES] = nb; counts[CNT_ENTRIES] = 2 * n;
+		if (sched_ovf) { atomicOr(&counts[CNT_OVERFLOW], OVF_SCHED); nb = 0; }
+		counts[CNT_BATCHES] = nb; counts[CNT_ENTRIES] = sched_ovf ? 0 : 2 * n;
 	}
+	if (sched_ovf) return;
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		u32 bucket = i & 15, packed = slot_of[i], uid = packed >> 3, lane = packed & 7;
 		u32 t = slot_done[(size_t)bucket * slots_per_bucket + uid];

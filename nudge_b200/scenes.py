@@ -218,3 +218,20 @@ def two_boxes(pos_b=(0.0, 1.9, 0.0), rot_b=(0.0, 0.0, 0.0, 1.0), size_a=(1.0, 1.
     s.transforms["rotation"][1] = rot_b
     s.properties[1:] = _box_props(np.asarray([size_b], np.float32))
     return s
+
+
+def hub_platform(n_side=55, iterations=4):
+    """One DYNAMIC platform box carrying n_side^2 small boxes: every box-platform contact shares the platform's body, so the
+    reference's batch scheduler (nudge.cpp:4206-4340) can never put two of them into one 8-lane batch.  Exercises the scheduler's
+    open-slot list far beyond what a pile produces (the ADVICE.md hub-body case)."""
+    n = n_side * n_side
+    half = 0.6 * n_side + 2.0
+    sizes = np.full((n + 1, 3), 0.5, np.float32); sizes[0] = (half, 1.0, half)
+    pos = np.zeros((n + 1, 3), np.float32); pos[0] = (0.0, 5.0, 0.0)
+    k = np.arange(n)
+    pos[1:, 0] = (k % n_side - (n_side - 1) / 2.0) * 1.2
+    pos[1:, 2] = (k // n_side - (n_side - 1) / 2.0) * 1.2
+    pos[1:, 1] = 5.0 + 1.0 + 0.5 - 0.02
+    s = _assemble("hub_platform_%d" % n, sizes, pos, None, np.zeros(0, np.float32), np.zeros((0, 3), np.float32))
+    s.iterations = iterations
+    return s

@@ -5,6 +5,8 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o handoff_latency scripts/handoff_latency.cu && ./handoff_latency
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 __device__ __forceinline__ float4 ld128(const float4* p) {
 	float4 v;
@@ -48,6 +50,27 @@ __global__ void pingpong_shared(int rounds, long long* cycles) {
 	if (me == 0) *cycles = clock64() - t0;
 }
 
+// two CTAs of one thread-block cluster bounce the word through distributed shared memory: CTA 1 polls and writes CTA 0's word
+__global__ void __cluster_dims__(2, 1, 1) pingpong_dsmem(int rounds, long long* cycles) {
+	__shared__ float4 word;
+	cg::cluster_group cluster = cg::this_cluster();
+	if (threadIdx.x == 0) word = make_float4(0, 0, 0, __uint_as_float(0u));
+	cluster.sync();
+	const int me = cluster.block_rank();
+	volatile float4* w = (volatile float4*)cluster.map_shared_rank(&word, 0);   // both CTAs use CTA 0's copy
+	if (threadIdx.x == 0) {
+		long long t0 = clock64();
+		for (int r = 0; r < rounds; ++r) {
+			unsigned expect = 2u * r + me;
+			float x, tok;
+			do { x = w->x; tok = w->w; } while (__float_as_uint(tok) != expect);
+			w->x = x + 1.0f; __threadfence_block(); w->w = __uint_as_float(expect + 1);
+		}
+		if (me == 0) *cycles = clock64() - t0;
+	}
+	cluster.sync();
+}
+
 int main() {
 	cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
 	float4* word; long long* cyc; cudaMalloc(&word, 16); cudaMalloc(&cyc, 8);
@@ -65,5 +88,8 @@ int main() {
 	pingpong_shared<<<1, 64>>>(rounds, cyc);
 	long long c = 0; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
 	printf("shared-memory ping-pong, two warps of one block: %.0f cycles = %.0f ns per hand-off\n", c / (2.0 * rounds), c / (2.0 * rounds) * 1e6 / khz);
+	pingpong_dsmem<<<2, 32>>>(rounds, cyc);
+	c = 0; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+	printf("DSMEM ping-pong, two CTAs of one cluster (word in CTA 0): %.0f cycles = %.0f ns per hand-off (%s)\n", c / (2.0 * rounds), c / (2.0 * rounds) * 1e6 / khz, cudaGetErrorString(cudaGetLastError()));
 	return 0;
 }

@@ -31,7 +31,7 @@ def make_oracle_sim(scene, max_bodies):
 
 def make_gpu_sim(scene, max_bodies):
     import nudge_b200
-    return nudge_b200.Sim(scene, max_bodies=max_bodies, max_boxes=max_bodies, contact_capacity=max(4096, 40 * max_bodies))
+    return nudge_b200.Sim(scene, max_bodies=max_bodies, max_boxes=max_bodies, max_spheres=(max_bodies if scene.n_spheres else 0), contact_capacity=max(4096, 40 * max_bodies))
 
 
 def free_port():

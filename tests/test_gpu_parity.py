@@ -323,3 +323,37 @@ def test_nb_step_graph_replay_equals_staged_calls_and_oracle():
         assert x.tobytes() == y.tobytes(), name
         assert x.tobytes() == z.tobytes(), name
     assert b.counts().overflow == 0 and a.counts().contacts == b.counts().contacts > 0
+
+
+def test_hub_body_beyond_scheduler_capacity_reports_overflow_instead_of_hanging():
+    """one dynamic body with more contacts than the batch scheduler's open-slot list holds (16 buckets x 511 slots) used to
+    leave a partial schedule behind and the dataflow solver waited forever.  Now the schedule is published empty, the step finishes,
+    and the overflow is reported (nb_counts.overflow & 4, NB_ERR_OVERFLOW from nb_download_contacts)."""
+    s = scenes.hub_platform(55, iterations=4)      # 3025 boxes x 4 contacts on the platform's body
+    g = nudge_b200.Sim(s)
+    g.step_staged()
+    c = g.counts()
+    assert c.contacts > 8176 + 16, c.contacts
+    assert c.overflow & 4 and c.batches == 0
+    with pytest.raises(nudge_b200.NudgeError):
+        g.download_contacts()
+    # a hub below the limit runs normally and matches the oracle
+    o, g2 = _pair(scenes.hub_platform(30, iterations=4))     # 900 boxes, 3600 contacts on one body
+    _steps(o, g2, 3)
+
+
+def test_two_simulations_on_two_streams_step_concurrently():
+    """grid-synchronising kernels inside the replayed graph keep the cooperative attribute, so two contexts stepping on two
+    streams of one device cannot dead-lock each other; both must equal a lone simulation."""
+    import torch
+    scene = scenes.demo_scene(400, 400)
+    sa, sb, sc = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    a = nudge_b200.Sim(scene, stream=sa.cuda_stream); b = nudge_b200.Sim(scene, stream=sb.cuda_stream); c = nudge_b200.Sim(scene, stream=sc.cuda_stream)
+    for _ in range(20):
+        c.step()
+    for _ in range(20):
+        a.step(); b.step()          # asynchronous: the two graphs are in flight together
+    for x in (a, b, c):
+        x.download_bodies()
+    assert a.debug_scalar("graph_coop") in (1, 2)
+    assert a.transforms.tobytes() == c.transforms.tobytes() and b.transforms.tobytes() == c.transforms.tobytes()

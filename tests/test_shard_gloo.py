@@ -31,7 +31,15 @@ def test_local_scene_keeps_global_tags_and_static_body():
     p = shard.partition(g.transforms["position"][1:, 0], 2, halo=4.0)
     s, gids = shard.local_scene(g, p["owned"][0], p["ghosts"][0])
     assert gids[0] == 0 and s.box_tags[0] == 0 and s.properties["mass_inverse"][0] == 0
-    assert np.array_equal(s.box_tags, g.box_tags[gids]) and np.array_equal(s.box_transforms["body"], np.arange(len(gids)))
+    # every collider of a local body is present exactly once, in global collider order, still carrying its global tag
+    assert np.array_equal(s.box_tags, np.sort(g.box_tags[gids])) and np.array_equal(gids[s.box_transforms["body"]], g.box_transforms["body"][s.box_tags])
+    # mixed scenes: spheres travel with their bodies and keep their (box-count offset) tags
+    m = scenes.demo_scene(40, 30, spread=6.0, height=10.0)
+    pm = shard.partition(m.transforms["position"][1:, 0], 2, halo=1.0)
+    sm, gm = shard.local_scene(m, pm["owned"][1], pm["ghosts"][1])
+    assert sm.n_boxes + sm.n_spheres == len(gm) and sm.n_spheres > 0
+    assert np.array_equal(gm[sm.sphere_transforms["body"]], m.sphere_transforms["body"][sm.sphere_tags - m.n_boxes])
+    assert np.array_equal(sm.sphere_data, m.sphere_data[sm.sphere_tags - m.n_boxes])
 
 
 def test_world1_sharded_equals_plain_oracle():
