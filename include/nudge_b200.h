@@ -125,6 +125,19 @@ int nb_advance(nb_context*, float time_step, void* stream);
  * are recorded once into a CUDA graph and replayed; NB_GRAPH=0 in the environment keeps plain launches. */
 int nb_step(nb_context*, float time_step, uint32_t iterations, float gravity, float damping, void* stream);
 
+/* Solver mode.  NB_SOLVER_PARITY (default): the reference's exact Gauss-Seidel order (nudge.cpp:4206-4340 schedule, 4640-4855 sweeps),
+ * bit-identical impulses.  NB_SOLVER_THROUGHPUT: mass-splitting Jacobi over the same constraint rows (nudge_b200/csrc/nb_jacobi.cuh) -
+ * order independent, HBM-streaming, converges to the same contact problem but its impulses after N sweeps differ from the reference's
+ * (validated by invariants and against a CPU restatement within a tolerance, tests/test_gpu_throughput.py).  Takes effect from the
+ * next nb_setup_contact_constraints / nb_step.  The NB_SOLVER=throughput environment variable selects it at nb_create. */
+enum nb_solver_mode { NB_SOLVER_PARITY = 0, NB_SOLVER_THROUGHPUT = 1 };
+int nb_set_solver_mode(nb_context*, int mode);
+int nb_get_solver_mode(const nb_context*);
+
+/* CUDA-event timing of the dominant solver kernel across plain (non-graph) launches; see nb_api.cu. */
+int nb_debug_timing_enable(nb_context*, int on);
+int nb_debug_timing(nb_context*, uint32_t* launches, float* total_ms, void* stream);
+
 /* Kernel-launch counter (every kernel this library launches increments it) and named device buffers for parity tests. */
 uint64_t nb_launch_count(const nb_context*);
 int nb_debug_read(nb_context*, const char* name, void* dst, size_t max_bytes, size_t* bytes, void* stream); /* synchronises */

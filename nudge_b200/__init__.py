@@ -17,7 +17,8 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_download_momentum", "nb_download_transforms", "nb_collide", "nb_apply_gravity_damping", "nb_read_cached_impulses",
            "nb_setup_contact_constraints", "nb_apply_impulses", "nb_update_cached_impulses", "nb_write_cached_impulses", "nb_advance", "nb_step",
            "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact", "nb_debug_sort", "nb_debug_scan", "nb_debug_enable", "nb_pack_momentum", "nb_unpack_momentum",
-           "nb_exchange_create", "nb_exchange_open", "nb_exchange_plan", "nb_setup_contact_constraints_deferred", "nb_solve_exchange"]
+           "nb_exchange_create", "nb_exchange_open", "nb_exchange_plan", "nb_setup_contact_constraints_deferred", "nb_solve_exchange",
+           "nb_set_solver_mode", "nb_get_solver_mode", "nb_debug_timing_enable", "nb_debug_timing"]
 
 
 class Config(C.Structure):
@@ -69,6 +70,10 @@ def load_library():
         lib.nb_exchange_plan.argtypes = [V, V, V, V, C.c_uint32, V, V]
         lib.nb_setup_contact_constraints_deferred.argtypes = [V, V]
         lib.nb_solve_exchange.argtypes = [V, C.c_uint32, V]
+        lib.nb_set_solver_mode.argtypes = [V, C.c_int]
+        lib.nb_get_solver_mode.argtypes = [V]
+        lib.nb_debug_timing_enable.argtypes = [V, C.c_int]
+        lib.nb_debug_timing.argtypes = [V, V, V, V]
         _lib = lib
     return _lib
 
@@ -219,6 +224,22 @@ class Sim(abi.HostState):
 
     def launch_count(self):
         return int(self.lib.nb_launch_count(self.ctx))
+
+    # ---- solver mode (include/nudge_b200.h): "parity" = the reference's exact Gauss-Seidel order, "throughput" = mass-splitting Jacobi ----
+    def set_solver_mode(self, mode):
+        self._ck(self.lib.nb_set_solver_mode(self.ctx, {"parity": 0, "throughput": 1}[mode]), "nb_set_solver_mode")
+
+    def solver_mode(self):
+        return ["parity", "throughput"][int(self.lib.nb_get_solver_mode(self.ctx))]
+
+    def timing_enable(self, on=True):
+        self._ck(self.lib.nb_debug_timing_enable(self.ctx, 1 if on else 0), "nb_debug_timing_enable")
+
+    def timing(self):
+        """(launches, total milliseconds) of the dominant solver kernel since the last call (CUDA events inside the library)."""
+        n = C.c_uint32(0); ms = C.c_float(0.0)
+        self._ck(self.lib.nb_debug_timing(self.ctx, C.byref(n), C.byref(ms), self.stream), "nb_debug_timing")
+        return int(n.value), float(ms.value)
 
     def lut_model_exact(self):
         return bool(self.lib.nb_lut_model_exact(self.ctx))

@@ -2,7 +2,7 @@
 // The reference keeps all memory caller-owned and bump-allocates scratch from an Arena (nudge.cpp:990-1055);
 // here the context plays both roles for device memory: every buffer is carved once from cudaMalloc at
 // nb_create and reused every step, nothing is allocated or synchronised inside the step.
-#include "nb_solver.cuh"
+#include "nb_jacobi.cuh"
 #define NB_DEFAULT_COOP_LAUNCH 1
 #include <stdio.h>
 #include <stdlib.h>
@@ -34,13 +34,17 @@ struct nb_context {
 	float4** xch_peers_dev; std::vector<float4*> xch_peers; std::vector<void*> xch_opened;
 	u32* xch_exp_off; uint2* xch_exp_tgt; u32 xch_tgt_cap; u32* xch_ghost_slot; u32* xch_epoch;
 	// nb_step as a CUDA graph: captured once per (stream, parameters, scene shape), replayed afterwards
-	struct StepKey { cudaStream_t stream; float ts, gravity, damping; u32 iterations, B, nboxes, nspheres, nconn, tagbits, kbits; int debug; } graph_key;
+	struct StepKey { cudaStream_t stream; float ts, gravity, damping; u32 iterations, B, nboxes, nspheres, nconn, tagbits, kbits; int debug, solver_mode; } graph_key;
 	cudaGraphExec_t graph_exec; unsigned long long graph_launches; int graph_enabled; bool capturing;
 	int graph_is_coop;  // the recorded graph holds cooperative kernel nodes
 	int graph_coop;  // 1: grid-synchronising kernels keep the cooperative-launch attribute inside the captured graph (co-residency guaranteed by the driver)
 	u32* chain_start; u32* chain_len;  // per body: first entry / number of entries in the (body, batch) chain sort
 	bool contacts_internal;  // the current contact set came from nb_collide (not nb_upload_contacts)
 	u32 solve_backoff_ns;
+	// throughput mode (nb_set_solver_mode): mass-splitting Jacobi, nb_jacobi.cuh
+	int solver_mode; u32* jcnt; float4* jd; int jacobi_blocks;
+	// CUDA-event timing of the dominant solver kernel (nb_debug_timing): bench.py's roofline numerator is measured live
+	int timing; cudaEvent_t tev[2][64]; int tev_n; bool tev_made;
 
 	// scene
 	nb_transform* xf; nb_body_properties* props; nb_body_momentum* mom; uint8_t* idle;
@@ -208,6 +212,17 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ALLOC(ctx->rows.plane, (size_t)ROW_PLANES_TOTAL * ctx->cstride); ALLOC(ctx->rows.state, 3 * (size_t)ctx->cstride);
 	ALLOC(ctx->rows.a, ctx->cstride); ALLOC(ctx->rows.b, ctx->cstride); ALLOC(ctx->rows.contact, ctx->cstride); ALLOC(ctx->rows.wait, 2 * (size_t)ctx->cstride); ALLOC(ctx->chain_start, B); ALLOC(ctx->chain_len, B);
 	ctx->rows.stride = ctx->cstride;
+	ALLOC(ctx->jcnt, B); ALLOC(ctx->jd, 2 * (size_t)B);
+	ctx->solver_mode = NB_SOLVER_PARITY;
+	CK(cudaFuncSetAttribute(k_jacobi_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem)));
+	CK(cudaFuncSetAttribute(k_jacobi_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem)));
+	{
+		int per = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_jacobi_sweep<false>, NJ_TILE, sizeof(JacobiSmem)));
+		if (per < 1) { ctx->error = "k_jacobi_sweep does not fit on an SM"; return NB_ERR_CUDA; }
+		ctx->jacobi_blocks = ctx->sms * per;   // persistent: every CTA walks tiles blockIdx.x, + gridDim.x, ...
+		if (const char* e = getenv("NB_SOLVER")) ctx->solver_mode = !strcmp(e, "throughput") ? NB_SOLVER_THROUGHPUT : NB_SOLVER_PARITY;
+	}
 	ctx->pair_keys = ctx->sb.keys[0];
 	ctx->pair_keys_debug = nullptr; ctx->debug = 0;
 
@@ -504,7 +519,42 @@ int nb_write_cached_impulses(nb_context* ctx, void* stream) {
 }
 
 // ---------------- setup + solve ----------------
+static void timing_begin(nb_context* ctx, cudaStream_t st) {
+	if (!ctx->timing || ctx->capturing || ctx->tev_n >= 64) return;
+	if (!ctx->tev_made) { for (int i = 0; i < 64; ++i) { cudaEventCreate(&ctx->tev[0][i]); cudaEventCreate(&ctx->tev[1][i]); } ctx->tev_made = true; }
+	cudaEventRecord(ctx->tev[0][ctx->tev_n], st);
+}
+static void timing_end(nb_context* ctx, cudaStream_t st) {
+	if (!ctx->timing || ctx->capturing || ctx->tev_n >= 64) return;
+	cudaEventRecord(ctx->tev[1][ctx->tev_n++], st);
+}
+
+// throughput mode: warm start and sweeps as Jacobi passes (k_jacobi_sweep + k_jacobi_apply per pass), nb_jacobi.cuh
+static int launch_solve_jacobi(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) {
+	Rows R = ctx->rows;
+	const u32 B = ctx->B;
+	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw);
+	++ctx->launches;
+	if (mode == 0 || mode == 2) {
+		k_jacobi_sweep<true><<<ctx->jacobi_blocks, NJ_TILE, sizeof(JacobiSmem), st>>>(R, ctx->impulses, ctx->mw, ctx->jd, ctx->counts);
+		k_jacobi_apply<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mw, ctx->jd, ctx->jcnt);
+		ctx->launches += 2;
+	}
+	if (mode != 0)
+		for (u32 w = 0; w < sweeps; ++w) {
+			timing_begin(ctx, st);
+			k_jacobi_sweep<false><<<ctx->jacobi_blocks, NJ_TILE, sizeof(JacobiSmem), st>>>(R, ctx->impulses, ctx->mw, ctx->jd, ctx->counts);
+			timing_end(ctx, st);
+			k_jacobi_apply<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mw, ctx->jd, ctx->jcnt);
+			ctx->launches += 2;
+		}
+	k_mw_out<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw, mode ? 1 : 0);
+	++ctx->launches;
+	return NB_OK;
+}
+
 static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) {
+	if (ctx->solver_mode == NB_SOLVER_THROUGHPUT) return launch_solve_jacobi(ctx, mode, sweeps, st);
 	Rows R = ctx->rows;
 	const float4* impulses = ctx->impulses;
 	float4* mw = ctx->mw;
@@ -513,8 +563,10 @@ static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) 
 	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw);
 	u32 backoff = ctx->solve_backoff_ns;
 	void* args[] = { &R, &impulses, &mw, &mode, &sweeps, &backoff, &counts };
+	if (mode) timing_begin(ctx, st);
 	if (ctx->coop_launch && (!ctx->capturing || ctx->graph_coop)) CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
 	else k_solve<<<ctx->coop_blocks_solve, NB_BLOCK, 0, st>>>(R, impulses, mw, mode, sweeps, backoff, counts);
+	if (mode) timing_end(ctx, st);
 	k_mw_out<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw, mode ? 1 : 0);
 	ctx->launches += 3;
 	return NB_OK;
@@ -526,6 +578,17 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 	u32* counts = ctx->counts;
 	const u32 C = ctx->cfg.max_contacts, S = ctx->stride, B = ctx->B;
 	k_inertia<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->xf, ctx->props, ctx->inertia, ctx->mom);
+	if (ctx->solver_mode == NB_SOLVER_THROUGHPUT) {
+		// no batch schedule, no per-body chains: slots in tag order, per-body contact counts for the mass split, split rows
+		CK(cudaMemsetAsync(ctx->rows.contact, 0xff, sizeof(u32) * ctx->cstride, st));
+		CK(cudaMemsetAsync(ctx->jcnt, 0, sizeof(u32) * B, st));
+		k_jacobi_prepare<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->jcnt, ctx->rows, ctx->cstride, counts);
+		k_build_rows<true><<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts, ctx->jcnt);
+		ctx->launches += 3;
+		if (!ctx->defer_warm_start) { int r = launch_solve(ctx, 0, 1, st); if (r) return r; }
+		CK(cudaGetLastError());
+		return NB_OK;
+	}
 	k_sched_prep<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->cab, ctx->back, counts);
 	k_schedule<<<16, 32, 0, st>>>(ctx->cab, ctx->back, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,
 		ctx->flags, ctx->left_count, counts);
@@ -539,7 +602,7 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 	if (ctx->xch_enabled) CK(cudaMemsetAsync(ctx->chain_len, 0, sizeof(u32) * B, st));  // "no contacts on this rank" must read as length 0
 	k_chain_heads<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->batchbits, ctx->chain_start, ctx->chain_len, counts); ++ctx->launches;
 	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, ctx->slot_idx, ctx->chain_start, ctx->chain_len, ctx->rows.wait, ctx->cstride, counts);
-	k_build_rows<<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts);
+	k_build_rows<false><<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts, nullptr);
 	ctx->launches += 2;
 	if (!ctx->defer_warm_start) { int r = launch_solve(ctx, 0, 1, st); if (r) return r; }  // warm start (nudge.cpp:4563-4632)
 	CK(cudaGetLastError());
@@ -675,7 +738,7 @@ int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity
 	nb_context::StepKey key;
 	memset(&key, 0, sizeof(key));  // padding bytes included: the key is compared with memcmp
 	key.stream = st; key.ts = time_step; key.gravity = gravity; key.damping = damping; key.iterations = iterations;
-	key.B = ctx->B; key.nboxes = ctx->nboxes; key.nspheres = ctx->nspheres; key.nconn = ctx->nconn; key.tagbits = ctx->tagbits; key.kbits = ctx->kbits; key.debug = ctx->debug;
+	key.B = ctx->B; key.nboxes = ctx->nboxes; key.nspheres = ctx->nspheres; key.nconn = ctx->nconn; key.tagbits = ctx->tagbits; key.kbits = ctx->kbits; key.debug = ctx->debug; key.solver_mode = ctx->solver_mode;
 	if (!ctx->graph_exec || memcmp(&key, &ctx->graph_key, sizeof(key)) != 0) {
 		if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
 		// Attempt 1 keeps the cooperative-launch attribute on the grid-synchronising kernel nodes (k_sort_coop's software grid barriers,
@@ -711,6 +774,28 @@ int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity
 	return NB_OK;
 }
 
+// ---------------- solver mode and kernel timing ----------------
+int nb_set_solver_mode(nb_context* ctx, int mode) {
+	if (mode != NB_SOLVER_PARITY && mode != NB_SOLVER_THROUGHPUT) { ctx->error = "unknown solver mode"; return NB_ERR_ARGUMENT; }
+	ctx->solver_mode = mode;
+	return NB_OK;
+}
+int nb_get_solver_mode(const nb_context* ctx) { return ctx->solver_mode; }
+
+// CUDA events around every launch of the dominant solver kernel (k_solve in parity mode, k_jacobi_sweep in throughput mode) while
+// enabled; plain launches only (the stage calls, or nb_step with NB_GRAPH=0).  nb_debug_timing synchronises the stream and returns
+// the number of timed launches and their summed duration, then clears the list.
+int nb_debug_timing_enable(nb_context* ctx, int on) { ctx->timing = on; ctx->tev_n = 0; return NB_OK; }
+int nb_debug_timing(nb_context* ctx, uint32_t* launches, float* total_ms, void* stream) {
+	CK(cudaStreamSynchronize((cudaStream_t)stream));
+	float sum = 0.0f;
+	for (int i = 0; i < ctx->tev_n; ++i) { float ms = 0.0f; CK(cudaEventElapsedTime(&ms, ctx->tev[0][i], ctx->tev[1][i])); sum += ms; }
+	if (launches) *launches = (uint32_t)ctx->tev_n;
+	if (total_ms) *total_ms = sum;
+	ctx->tev_n = 0;
+	return NB_OK;
+}
+
 // ---------------- parity-test introspection ----------------
 int nb_debug_read(nb_context* ctx, const char* name, void* dst, size_t max_bytes, size_t* bytes, void* stream) {
 	u32 c[CNT__COUNT];
@@ -739,6 +824,8 @@ int nb_debug_read(nb_context* ctx, const char* name, void* dst, size_t max_bytes
 		{ "row_planes", ctx->rows.plane, sizeof(float) * (size_t)ROW_PLANES * ctx->cstride },
 		{ "row_states", ctx->rows.state, sizeof(float) * 3 * (size_t)ctx->cstride },
 		{ "inertia", ctx->inertia, sizeof(float4) * 2 * ctx->B },
+		{ "row_planes_all", ctx->rows.plane, sizeof(float) * (size_t)ROW_PLANES_TOTAL * ctx->cstride },
+		{ "body_contacts", ctx->jcnt, sizeof(u32) * ctx->B },
 	};
 	if (!strcmp(name, "row_stride")) { if (max_bytes < 4) return NB_ERR_ARGUMENT; *(u32*)dst = ctx->cstride; if (bytes) *bytes = 4; return NB_OK; }
 	if (!strcmp(name, "graph_coop")) { if (max_bytes < 4) return NB_ERR_ARGUMENT; *(u32*)dst = ctx->graph_exec ? (ctx->graph_is_coop ? 2u : 1u) : 0u; if (bytes) *bytes = 4; return NB_OK; }

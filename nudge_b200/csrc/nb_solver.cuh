@@ -438,8 +438,12 @@ __global__ void __launch_bounds__(NB_BLOCK) k_waits(const u64* chain_keys, const
 // ---------------- constraint rows (nudge.cpp:4350-4561), one thread per contact, SoA planes ----------------
 struct Rows { float* plane; u32 stride; u32* a; u32* b; u32* contact; float* state; uint2* wait; };  // plane[k*stride + slot], wait[side*stride + slot] = (seq, len)
 
+// SPLIT (throughput mode, nb_jacobi.cuh): body i is split into cnt[i] sub-bodies of mass m_i / cnt[i], one per contact (Tonge et al.,
+// "Mass splitting for jitter-free parallel rigid body simulation", 2012), so every effective-mass term of body i is scaled by
+// cnt[i]; the planes that APPLY an impulse to a body (NA.., UA.., MASS_A/B) stay unscaled because the sub-bodies are averaged back.
+template<bool SPLIT>
 __global__ void __launch_bounds__(NB_BLOCK) k_build_rows(const float4* contacts, const uint2* bodies,
-		const nb_transform* xf, const float4* inertia, const nb_body_momentum* momentum, Rows R, const u32* counts) {
+		const nb_transform* xf, const float4* inertia, const nb_body_momentum* momentum, Rows R, const u32* counts, const u32* cnt) {
 	__shared__ u32 s_rsqrt[2048];
 	for (u32 i = threadIdx.x; i < 2048; i += blockDim.x) s_rsqrt[i] = g_rsqrt_lut[i];
 	__syncthreads();
@@ -472,6 +476,13 @@ __global__ void __launch_bounds__(NB_BLOCK) k_build_rows(const float4* contacts,
 		float r_dot_n = rx*normal_x + ry*normal_y + rz*normal_z;
 		float mass_inverse = a_mass_inverse + b_mass_inverse;
 		float nvtni = mass_inverse + r_dot_n;
+		float sa = 1.0f, sb = 1.0f;
+		if (SPLIT) {
+			sa = (float)max(cnt[a], 1u); sb = (float)max(cnt[b], 1u);
+			float ka = a_mass_inverse + (nat.x*normal_x + nat.y*normal_y + nat.z*normal_z);
+			float kb = b_mass_inverse + (nbt.x*normal_x + nbt.y*normal_y + nbt.z*normal_z);
+			nvtni = sa*ka + sb*kb;
+		}
 		bool nonzero = nvtni < 0.0f || nvtni > 0.0f;  // _CMP_NEQ_OQ is ordered (nudge.cpp:636-638, 4439)
 		nvtni = nonzero ? (-1.0f / nvtni) : 0.0f;
 		float bias = -2.0f * nb_max(penetration - 1e-3f, 0.0f) * nvtni;  // nudge.cpp:4442 with the constants of 49-50
@@ -499,6 +510,11 @@ __global__ void __launch_bounds__(NB_BLOCK) k_build_rows(const float4* contacts,
 		float friction_x = mass_inverse + a_duu + a_suu + a_suu + b_duu + b_suu + b_suu;
 		float friction_y = mass_inverse + a_dvv + a_svv + a_svv + b_dvv + b_svv + b_svv;
 		float friction_z = a_duv + a_duv + a_suv + a_suv + b_duv + b_duv + b_suv + b_suv;
+		if (SPLIT) {
+			friction_x = sa*(a_mass_inverse + a_duu + a_suu + a_suu) + sb*(b_mass_inverse + b_duu + b_suu + b_suu);
+			friction_y = sa*(a_mass_inverse + a_dvv + a_svv + a_svv) + sb*(b_mass_inverse + b_dvv + b_svv + b_svv);
+			friction_z = sa*(a_duv + a_duv + a_suv + a_suv) + sb*(b_duv + b_duv + b_suv + b_suv);
+		}
 		float ua_xt = Ad.x*ua.x + Ao.x*ua.y + Ao.y*ua.z, ua_yt = Ao.x*ua.x + Ad.y*ua.y + Ao.z*ua.z, ua_zt = Ao.y*ua.x + Ao.z*ua.y + Ad.z*ua.z;
 		float va_xt = Ad.x*va.x + Ao.x*va.y + Ao.y*va.z, va_yt = Ao.x*va.x + Ad.y*va.y + Ao.z*va.z, va_zt = Ao.y*va.x + Ao.z*va.y + Ad.z*va.z;
 		float ub_xt = Bd.x*ub.x + Bo.x*ub.y + Bo.y*ub.z, ub_yt = Bo.x*ub.x + Bd.y*ub.y + Bo.z*ub.z, ub_zt = Bo.y*ub.x + Bo.z*ub.y + Bd.z*ub.z;
@@ -552,10 +568,23 @@ __global__ void __launch_bounds__(NB_BLOCK) k_mw_out(u32 B, nb_body_momentum* mo
 	}
 }
 
+// rcpps / rsqrtps of the solver arithmetic as a policy: LutMath reproduces the host CPU's instructions bit for bit (parity mode),
+// FastMath uses the GPU's own reciprocal / rsqrt (throughput mode: more accurate, not bit-comparable with the reference).
+struct LutMath {
+	const u32* rcp_lut; const u32* rsqrt_lut;
+	NB_DEV float rcp(float x) const { return nb_rcp_t(x, rcp_lut); }
+	NB_DEV float rsqrt(float x) const { return nb_rsqrt_t(x, rsqrt_lut); }
+};
+struct FastMath {
+	NB_DEV float rcp(float x) const { return __frcp_rn(x); }
+	NB_DEV float rsqrt(float x) const { return rsqrtf(x); }   // rsqrt(0) = inf, rsqrt(<0) = NaN like rsqrtps
+};
+
 // One contact of the warm start (nudge.cpp:4563-4632); momentum rows passed in registers and updated in place.
-NB_DEV void warm_start_contact(const Rows& R, u32 j, const float4* impulses, float4& al, float4& aw, float4& bl, float4& bw, const u32* s_rsqrt) {
-	const float* P = R.plane + j; const u32 S = R.stride;
-	float4 ci = impulses[R.contact[j]];
+// `state` points at the contact's slot in the three state planes (stride S floats apart).
+// P[k*PS] = row plane k of this contact (global planes: P = R.plane + slot, PS = R.stride; a shared-memory tile: P = tile + lane, PS = tile width).
+template<class M>
+NB_DEV void warm_start_contact_p(const float* P, const u32 S, const float4 ci, float* state, const u32 SS, float4& al, float4& aw, float4& bl, float4& bw, const M m) {
 	float a_mass_inverse = P[MASS_A*S], b_mass_inverse = P[MASS_B*S];
 	float n_x = P[N_X*S], n_y = P[N_Y*S], n_z = P[N_Z*S];
 	float u_x = P[U_X*S], u_y = P[U_Y*S], u_z = P[U_Z*S], v_x = P[V_X*S], v_y = P[V_Y*S], v_z = P[V_Z*S];
@@ -564,7 +593,7 @@ NB_DEV void warm_start_contact(const Rows& R, u32 j, const float4* impulses, flo
 	float fix = u_x*ci.x + u_y*ci.y + u_z*ci.z;
 	float fiy = v_x*ci.x + v_y*ci.y + v_z*ci.z;
 	float fcs = fix*fix + fiy*fiy;
-	fcs = nb_rsqrt_t(fcs, s_rsqrt);
+	fcs = m.rsqrt(fcs);
 	fcs = fcs * max_friction_impulse;
 	fcs = nb_min(1.0f, fcs);  // first operand on NaN
 	fix = fix * fcs; fiy = fiy * fcs;
@@ -581,12 +610,17 @@ NB_DEV void warm_start_contact(const Rows& R, u32 j, const float4* impulses, flo
 	aw.x += aax; aw.y += aay; aw.z += aaz;
 	bl.x += lx * b_mass_inverse; bl.y += ly * b_mass_inverse; bl.z += lz * b_mass_inverse;
 	bw.x += bax; bw.y += bay; bw.z += baz;
-	R.state[0*S + j] = normal_impulse; R.state[1*S + j] = fix; R.state[2*S + j] = fiy;
+	state[0] = normal_impulse; state[SS] = fix; state[2*SS] = fiy;
+}
+template<class M>
+NB_DEV void warm_start_contact(const Rows& R, u32 j, const float4* impulses, float4& al, float4& aw, float4& bl, float4& bw, const M m) {
+	warm_start_contact_p(R.plane + j, R.stride, impulses[R.contact[j]], R.state + j, R.stride, al, aw, bl, bw, m);
 }
 
 // One contact of one projected Gauss-Seidel sweep (nudge.cpp:4646-4853), same operation order, FMAs where the source has madd.
 // The rows arrive in registers (rv[], st[]): they are fetched BEFORE the contact starts waiting for its bodies.
-NB_DEV void solve_contact(const Rows& R, u32 j, const float (&rv)[ROW_PLANES_TOTAL], const float (&st)[3], float4& al, float4& aw, float4& bl, float4& bw, const u32* s_rcp, const u32* s_rsqrt) {
+template<class M>
+NB_DEV void solve_contact(const Rows& R, u32 j, const float (&rv)[ROW_PLANES_TOTAL], const float (&st)[3], float4& al, float4& aw, float4& bl, float4& bw, const M m) {
 	const u32 S = R.stride;
 	float a_velocity_x = al.x, a_velocity_y = al.y, a_velocity_z = al.z, a_mass_inverse = rv[MASS_A];
 	float a_angular_velocity_x = aw.x, a_angular_velocity_y = aw.y, a_angular_velocity_z = aw.z;
@@ -631,7 +665,7 @@ NB_DEV void solve_contact(const Rows& R, u32 j, const float (&rv)[ROW_PLANES_TOT
 	float linear_impulse_y = n_y * normal_impulse;
 	friction_factor = nb_madd(t_xy, rv[FC_Z], friction_factor);
 	float linear_impulse_z = n_z * normal_impulse;
-	friction_factor = nb_rcp_t(friction_factor, s_rcp);
+	friction_factor = m.rcp(friction_factor);
 	a_angular_velocity_x = nb_madd(rv[NA_X], normal_impulse, a_angular_velocity_x);
 	a_angular_velocity_y = nb_madd(rv[NA_Y], normal_impulse, a_angular_velocity_y);
 	a_angular_velocity_z = nb_madd(rv[NA_Z], normal_impulse, a_angular_velocity_z);
@@ -641,7 +675,7 @@ NB_DEV void solve_contact(const Rows& R, u32 j, const float (&rv)[ROW_PLANES_TOT
 	friction_impulse_x = old_friction_impulse_x - friction_impulse_x;
 	friction_impulse_y = old_friction_impulse_y - friction_impulse_y;
 	float friction_clamp_scale = friction_impulse_x*friction_impulse_x + friction_impulse_y*friction_impulse_y;
-	friction_clamp_scale = nb_rsqrt_t(friction_clamp_scale, s_rsqrt);
+	friction_clamp_scale = m.rsqrt(friction_clamp_scale);
 	b_angular_velocity_x = nb_madd(rv[NB_X], normal_impulse, b_angular_velocity_x);
 	b_angular_velocity_y = nb_madd(rv[NB_Y], normal_impulse, b_angular_velocity_y);
 	b_angular_velocity_z = nb_madd(rv[NB_Z], normal_impulse, b_angular_velocity_z);
@@ -725,8 +759,8 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve(Rows R, const float4* imp
 					u32 ra = a ? exp_a - asu(al.w) : 0, rb = b ? exp_b - asu(bl.w) : 0;
 					u32 r = max(ra, rb);
 					if (r == 0 && near && (!a || asu(aw.w) == exp_a) && (!b || asu(bw.w) == exp_b)) {
-						if (sweep) solve_contact(R, slot, rv, st, al, aw, bl, bw, s_rcp, s_rsqrt);
-						else warm_start_contact(R, slot, impulses, al, aw, bl, bw, s_rsqrt);
+						if (sweep) solve_contact(R, slot, rv, st, al, aw, bl, bw, LutMath{ s_rcp, s_rsqrt });
+						else warm_start_contact(R, slot, impulses, al, aw, bl, bw, LutMath{ s_rcp, s_rsqrt });
 						if (a) { float tk = asf(exp_a + 1); al.w = tk; aw.w = tk; st128(mw + 2*a, al); st128(mw + 2*a + 1, aw); }  // body 0 is static: never written
 						if (b) { float tk = asf(exp_b + 1); bl.w = tk; bw.w = tk; st128(mw + 2*b, bl); st128(mw + 2*b + 1, bw); }
 						pending = false;
@@ -876,8 +910,8 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve_exchange(Rows R, const fl
 						else ready = false;
 					}
 					if (ready) {
-						if (sweep) solve_contact(R, slot, rv, st, al, aw, bl, bw, s_rcp, s_rsqrt);
-						else warm_start_contact(R, slot, impulses, al, aw, bl, bw, s_rsqrt);
+						if (sweep) solve_contact(R, slot, rv, st, al, aw, bl, bw, LutMath{ s_rcp, s_rsqrt });
+						else warm_start_contact(R, slot, impulses, al, aw, bl, bw, LutMath{ s_rcp, s_rsqrt });
 						if (a) { float tk = asf(exp_a + 1); al.w = tk; aw.w = tk; st128(mw + 2*a, al); st128(mw + 2*a + 1, aw); }
 						if (b) { float tk = asf(exp_b + 1); bl.w = tk; bw.w = tk; st128(mw + 2*b, bl); st128(mw + 2*b + 1, bw); }
 						if (last_a) publish_row(X, a, ep, w, al, aw);  // this body is done for pass w: hand it to its subscribers

@@ -1,0 +1,119 @@
+"""Throughput-mode solver (mass-splitting Jacobi, nudge_b200/csrc/nb_jacobi.cuh) on the GPU, through the C ABI.
+
+It is NOT bit-comparable with the reference (different iteration, float atomics): the split rows and every pass are compared with
+the CPU restatement oracle/jacobi_ref.py within a stated tolerance (1e-4 of the velocity scale; the restatement is float64 with exact
+1/x and 1/sqrt, the kernel float32 with the GPU's reciprocal/rsqrt), and the physics is compared with parity mode through invariants."""
+import numpy as np
+import pytest
+import nudge_b200
+from nudge_b200 import scenes
+from oracle import jacobi_ref as J
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _rows(g, n):
+    stride = g.debug_scalar("row_stride")
+    P = g.debug("row_planes_all", np.float32).reshape(41, stride)
+    st = g.debug("row_states", np.float32).reshape(3, stride)
+    contact = g.debug("row_contact", np.uint32)
+    used = np.nonzero(contact != 0xffffffff)[0]
+    assert len(used) == n
+    return P[:, used], st[:, used], contact[used].astype(np.int64), g.debug("row_a", np.uint32)[used].astype(np.int64), g.debug("row_b", np.uint32)[used].astype(np.int64)
+
+
+def _vel(g):
+    g.download_bodies()
+    return g.momentum["velocity"].astype(np.float64), g.momentum["angular_velocity"].astype(np.float64)
+
+
+@pytest.mark.parametrize("scene", [scenes.demo_scene(400, 400, iterations=8, spread=4.0, height=40.0), scenes.box_drop(3000, iterations=8)], ids=["mixed", "boxes"])
+def test_split_rows_warm_start_and_sweeps_equal_the_cpu_restatement(scene):
+    g = nudge_b200.Sim(scene, debug=True)
+    for _ in range(150):
+        g.step_staged()
+    g.collide(); g.apply_gravity_damping(); g.read_cached_impulses()
+    g.download_bodies(); m0 = g.momentum.copy()
+    n = g.counts().contacts
+    assert n > 1000
+    # the same contact set through the exact-order setup (rows pinned bit-for-bit against the reference in test_gpu_parity.py)
+    g.setup_contact_constraints()
+    Pp, _, cp, ap, bp = _rows(g, n)
+    order = np.argsort(cp)
+    Pp, ap, bp = Pp[:, order], ap[order], bp[order]                 # keyed by contact index
+    g.momentum[:] = m0; g.upload_bodies()
+    g.set_solver_mode("throughput")
+    assert g.solver_mode() == "throughput"
+    g.setup_contact_constraints()                                   # split rows + Jacobi warm start
+    Pt, st, ct, a, b = _rows(g, n)
+    assert np.array_equal(ct, g.debug("sorted", np.uint32).astype(np.int64)), "throughput slots are the tag order"
+    assert np.array_equal(a, ap[ct]) and np.array_equal(b, bp[ct])
+    cnt = g.debug("body_contacts", np.uint32).astype(np.int64)[:scene.n_bodies]
+    want_cnt = np.bincount(np.concatenate([a, b]), minlength=scene.n_bodies); want_cnt[0] = 0
+    assert np.array_equal(cnt, want_cnt)
+    split = {"NVTNI", "BIAS", "FC_X", "FC_Y", "FC_Z"}
+    for k, name in enumerate(J.PLANES):
+        if name not in split:
+            assert np.array_equal(Pt[k].view(np.uint32), Pp[k][ct].view(np.uint32)), name     # everything else is the reference's row, bit for bit
+    t = J.split_terms(Pp[:, ct], a, b, cnt)
+    for name in split:
+        got = Pt[J.IX[name]].astype(np.float64)
+        assert np.abs(got - t[name]).max() <= 2e-5 * np.abs(t[name]).max(), name
+    # warm start, then three sweeps, each against the restatement started from the GPU's own previous state
+    lin0, ang0 = m0["velocity"].astype(np.float64), m0["angular_velocity"].astype(np.float64)
+    imp = g.impulses_view()["data"]["impulse"][ct]
+    lin_w, ang_w, st_w = J.jacobi_pass(Pt, st, a, b, lin0, ang0, warm=True, impulses=imp)
+    lin, ang = _vel(g)
+    scale = max(1.0, np.abs(lin_w).max(), np.abs(ang_w).max())
+    assert np.abs(lin - lin_w).max() < TOL * scale and np.abs(ang - ang_w).max() < TOL * scale
+    assert np.abs(st - st_w).max() < TOL * max(1.0, np.abs(st_w).max())
+    for sweep in range(3):
+        lin_r, ang_r, st_r = J.jacobi_pass(Pt, st, a, b, lin, ang)
+        g.apply_impulses(1)
+        lin, ang = _vel(g)
+        _, st, _, _, _ = _rows(g, n)
+        scale = max(1.0, np.abs(lin_r).max(), np.abs(ang_r).max())
+        assert np.abs(lin - lin_r).max() < TOL * scale and np.abs(ang - ang_r).max() < TOL * scale, "sweep %d" % sweep
+        assert np.abs(st - st_r).max() < TOL * max(1.0, np.abs(st_r).max()), "sweep %d" % sweep
+    assert g.counts().overflow == 0
+
+
+def _pile_stats(g):
+    g.collide(); g.download_contacts(); g.download_bodies()
+    n = g.contacts.count
+    pen = g.contact_data["penetration"][:n]
+    v = g.momentum["velocity"][1:]
+    mass = 1.0 / g.properties["mass_inverse"][1:]
+    return dict(contacts=n, max_pen=float(pen.max()), mean_pen=float(pen.mean()), ke=float(0.5 * (mass * (v * v).sum(1)).sum()),
+                mean_y=float(g.transforms["position"][1:, 1].mean()), min_y=float(g.transforms["position"][1:, 1].min()))
+
+
+def test_throughput_mode_keeps_a_settled_pile_settled_like_parity_mode():
+    """Invariants vs parity mode on a settled 8k pile, 120 further steps each: nothing sinks or explodes, penetration and
+    kinetic energy stay in the same range.  nb_step (CUDA graph) drives the throughput run."""
+    import torch
+    s = scenes.box_drop(8000, iterations=8)
+    side = torch.cuda.Stream()
+    a = nudge_b200.Sim(s, stream=side.cuda_stream)
+    for _ in range(500):
+        a.step()
+    a.download_bodies(); a.download_cache()
+    b = nudge_b200.Sim(s, stream=side.cuda_stream)
+    for name in ("transforms", "momentum", "idle"):
+        getattr(b, name)[:] = getattr(a, name)
+    nc = a.cache.count
+    b.cache_tags[:nc] = a.cache_tags[:nc]; b.cache_features[:nc] = a.cache_features[:nc]; b.cache_data[:nc] = a.cache_data[:nc]; b.cache.count = nc
+    b.upload_bodies(); b.upload_cache()
+    b.set_solver_mode("throughput")
+    for _ in range(120):
+        a.step(); b.step()
+    sa, sb = _pile_stats(a), _pile_stats(b)
+    print("parity    ", sa); print("throughput", sb)
+    assert b.counts().overflow == 0
+    assert np.isfinite(b.transforms["position"]).all()
+    assert sb["min_y"] > -1.0                                            # nothing fell through the ground (top at y = 0)
+    assert abs(sb["mean_y"] - sa["mean_y"]) < 0.05 * max(1.0, abs(sa["mean_y"]))
+    assert sb["max_pen"] < 3.0 * sa["max_pen"] + 0.05
+    assert sb["ke"] < 10.0 * sa["ke"] + 50.0                              # still at rest (the falling pile had > 1e6)
+    assert abs(sb["contacts"] - sa["contacts"]) < 0.1 * sa["contacts"]
