@@ -128,31 +128,30 @@ def settle_gpu(sim, steps):
 
 
 def run_sharded(args, rank, world, local):
-    """N > 1: ONE scene of world x 65,536 boxes, bodies partitioned across the GPUs in x-slabs with ghost copies; the ghost bodies'
-    momentum is exchanged after the warm start and after every solver sweep with a single NCCL all-gather (nudge_b200/shard.py)."""
+    """N > 1: ONE scene sharded across the GPUs (gx x gz cells, ghost copies of the neighbours' bodies); the ghost bodies' momentum is
+    exchanged after the warm start and after every solver sweep by the C++ host behind nb_shard_* (include/nudge_b200.h): one
+    ncclAllGather ("nccl") or the library's own peer-memory push/pull kernels over NVLink ("peer").  The whole sharded sub-step,
+    exchanges included, is one CUDA-graph replay per step (nb_shard_step)."""
     import torch
     import torch.distributed as dist
     import nudge_b200
     from nudge_b200 import shard
-    # NB_SHARD_GRAPH=1: record a whole sharded step (kernels + NCCL all-gathers) into a CUDA graph on a non-default stream and
-    # replay it (measured at 2 GPUs: 1.74 vs 1.95 ms per step).  Off by default: plain launches on torch's current stream.
-    use_graph = os.environ.get("NB_SHARD_GRAPH", "0") == "1"
-    side = None
-    if use_graph:
-        os.environ.setdefault("NB_COOP_LAUNCH", "0")   # grid-synchronising kernels as ordinary launches: capturable, same speed
-        side = torch.cuda.Stream()
-        torch.cuda.set_stream(side)
-    stream = torch.cuda.current_stream().cuda_stream
+    side = torch.cuda.Stream()                     # a capturable stream: nb_shard_step records the step into a CUDA graph there
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
     cfg = CONFIGS[args.config]
     g = cfg["scene"](args, world)
     strong = cfg["scaling"] == "strong"
     unit_bodies = 65536.0 if not strong else float(g.n_bodies - 1)     # `value` counts steps of a scene of this many bodies
+    gloo = dist.new_group(backend="gloo")          # host-side bookkeeping (handles, re-partition) and the parity check's host transport
 
     def make_sim(scene, max_bodies):
-        return nudge_b200.Sim(scene, device=local, stream=stream, max_bodies=max_bodies, max_boxes=max_bodies, max_spheres=(max_bodies if g.n_spheres else 0), contact_capacity=30 * max_bodies)
+        sm = nudge_b200.Sim(scene, device=local, stream=stream, max_bodies=max_bodies, max_boxes=max_bodies, max_spheres=(max_bodies if g.n_spheres else 0), contact_capacity=30 * max_bodies)
+        if args.solver == "throughput":
+            sm.set_solver_mode("throughput")
+        return sm
 
-    dataflow = os.environ.get("NB_SHARD_DATAFLOW", "0") == "1"   # experimental: ghost hand-over inside the solver, peer memory (DESIGN.md §7)
-    sim = shard.ShardedSim(g, rank, world, make_sim, halo=8.0, device_exchange=True, dataflow=dataflow)
+    sim = shard.ShardedSim(g, rank, world, make_sim, margin=args.margin, transport=args.transport, group=gloo)
     for k in range(args.presim):
         if k and k % 25 == 0:
             sim.reshard()
@@ -160,26 +159,66 @@ def run_sharded(args, rank, world, local):
     sim.reshard()
     for _ in range(2):
         sim.step()
-    graphed = use_graph and sim.capture(side)
-    for _ in range(max(args.warmup, 3)):
-        sim.step()
+
+    # ---- parity of the path that is timed: the same steps from the same state through NCCL, peer memory and the host exchange ----
+    def snapshot():
+        sim.sim.download_bodies(); sim.sim.download_cache()
+        s_ = sim.sim
+        n = s_.cache.count
+        return dict(transforms=s_.transforms.copy(), momentum=s_.momentum.copy(), idle=s_.idle.copy(), n=n,
+                    tags=s_.cache_tags[:n].copy(), feats=s_.cache_features[:n].copy(), data=s_.cache_data[:n].copy())
+
+    def restore(st):
+        s_ = sim.sim
+        s_.transforms[:] = st["transforms"]; s_.momentum[:] = st["momentum"]; s_.idle[:] = st["idle"]
+        n = st["n"]; s_.cache_tags[:n] = st["tags"]; s_.cache_features[:n] = st["feats"]; s_.cache_data[:n] = st["data"]; s_.cache.count = n
+        s_.upload_bodies(); s_.upload_cache()
+
+    parity = None
+    if not args.no_parity_check and args.solver == "parity":
+        s0 = snapshot()
+        res = {}
+        for t in ("nccl", "peer", "host"):
+            restore(s0)
+            for _ in range(3):
+                sim.step(t)
+            r_ = snapshot()
+            res[t] = (r_["transforms"].tobytes(), r_["momentum"].tobytes(), r_["idle"].tobytes())
+        same = torch.tensor([float(res["nccl"] == res["host"]), float(res["peer"] == res["host"])], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        parity = {"steps": 3, "nccl_equals_host_exchange": bool(same[0] > 0), "peer_equals_host_exchange": bool(same[1] > 0),
+                  "what": "3 steps from the same state through each transport; transforms, momentum and idle counters of every rank compared bit for bit"}
+        restore(s0)
+        if not (parity["nccl_equals_host_exchange"] and parity["peer_equals_host_exchange"]):
+            if rank == 0:
+                print("PARITY CHECK FAILED: %r" % parity, file=sys.stderr)
+
     K = args.steps
     E = lambda: torch.cuda.Event(enable_timing=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    step_ev = [(E(), E()) for _ in range(K)]
+
+    def timed(transport):
+        for _ in range(max(args.warmup, 3)):
+            sim.step(transport)
+        ev = [(E(), E()) for _ in range(K)]
+        dist.barrier(); torch.cuda.synchronize()
+        l0 = sim.launch_count()
+        for k in range(K):
+            flush.fill_(k & 255)
+            ev[k][0].record()
+            sim.step(transport)
+            ev[k][1].record()
+        torch.cuda.synchronize()
+        n_launch = sim.launch_count() - l0
+        dist.barrier()
+        return float(sum(a.elapsed_time(b) for a, b in ev)), n_launch
+
+    other = "nccl" if args.transport == "peer" else "peer"
+    other_ms, _ = timed(other)
     sampler = ClockSampler(local); sampler.start()
-    dist.barrier(); torch.cuda.synchronize()
-    launches0 = sim.launch_count()
-    for k in range(K):
-        flush.fill_(k & 255)
-        step_ev[k][0].record()
-        sim.step()
-        step_ev[k][1].record()
-    torch.cuda.synchronize()
-    launches = sim.launch_count() - launches0
-    dist.barrier()
+    total_ms, launches = timed(args.transport)
     sampler.stop_flag = True
-    total_ms = float(sum(a.elapsed_time(b) for a, b in step_ev))
+    graphed = sim.sim.shard_graph_active()
     cnt = sim.sim.counts()
     lc = sim.local_counts()
     # end to end: host state of the local bodies in and out every step
@@ -194,33 +233,38 @@ def run_sharded(args, rank, world, local):
         sim.sim.upload_bodies(); sim.step(); sim.sim.download_bodies()
     e1.record(); torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1)
-    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_ms, other_ms], dtype=torch.float64, device="cuda")
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ssum = torch.tensor([float(cnt.contacts), float(lc["owned"]), float(lc["ghosts"]), float(lc["export"]), float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+    ssum = torch.tensor([float(cnt.contacts), float(lc["owned"]), float(lc["ghosts"]), float(lc["export"]), float(h2d), float(d2h), float(cnt.overflow)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ssum, op=dist.ReduceOp.SUM)
     if rank == 0:
-        total_ms, e2e_ms = float(tmax[0]), float(tmax[1])
+        total_ms, e2e_ms, other_ms = float(tmax[0]), float(tmax[1]), float(tmax[2])
         rate = K / (total_ms * 1e-3)
+        gx, gz = sim.part["grid"]
+        exch = {"nccl": "pack -> ONE ncclAllGather (called from the C++ host) -> unpack, after the warm start and after every sweep",
+                "peer": "k_shard_push / k_shard_pull: export rows stored straight into the subscribers' inboxes over NVLink peer memory (CUDA IPC), arrival flags instead of a collective, after the warm start and after every sweep"}
         line = {
             "metric": "simulation steps/s", "value": rate * (g.n_bodies - 1) / unit_bodies, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "config": args.config, "bodies_total": int(g.n_bodies), "bodies_per_gpu_owned": int(ssum[1] / world), "ghost_bodies_per_gpu": int(ssum[2] / world),
                        "exchanged_rows_per_gpu_per_sweep": int(ssum[3] / world), "solver_iterations": int(g.iterations), "contacts_incl_ghost_copies": int(ssum[0]),
-                       "exchange": "solver dataflow over peer-memory inboxes (experimental)" if dataflow else "pack -> ncclAllGather -> unpack after the warm start and after every sweep",
-                       "step_call": ("CUDA graph replay of one sharded step (kernels + 9 NCCL all-gathers)" if graphed else "plain launches" + (": " + getattr(sim, "capture_error", "") if getattr(sim, "capture_error", None) else "")),
-                       "presim_steps": args.presim, "parallelism": "one scene of %d bodies sharded into %d x-slabs; ghost momentum exchanged by one NCCL all-gather after the warm start and after each sweep" % (g.n_bodies - 1, world),
+                       "transport": args.transport, "exchange": exch[args.transport], "other_transport": other, "other_transport_scene_steps_per_s": K / (other_ms * 1e-3),
+                       "step_call": ("nb_shard_step: one CUDA-graph replay per step (kernels + exchanges)" if graphed else "nb_shard_step: plain launches"),
+                       "presim_steps": args.presim, "parallelism": "one scene of %d bodies in %d x %d cells (x, z), one cell per GPU; halo = body radius + max radius + %.2f" % (g.n_bodies - 1, gx, gz, args.margin),
                        "value_definition": ("scene steps/s of the fixed-size scene" if strong else "scene steps/s x (total bodies / 65,536): 65,536-box-equivalent steps per second of the whole job"),
                        "scene_steps_per_s": rate, "l2": "flushed between timed steps (256 MiB write), flush excluded", "timing": "CUDA events per step, summed; max over ranks",
-                       "solver_mode": "exact reference Gauss-Seidel order inside a rank, block-Jacobi across ranks"},
+                       "overflow_flags": int(ssum[6]),
+                       "solver_mode": ("throughput (mass-splitting Jacobi) inside a rank" if args.solver == "throughput" else "exact reference Gauss-Seidel order inside a rank") + ", block-Jacobi across ranks"},
+            "parity_check": parity,
             "e2e": {"value": ((g.n_bodies - 1) / unit_bodies) * K / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(ssum[4]), "d2h_bytes_per_step": int(ssum[5]),
-                    "what": "per rank: nb_upload_bodies (host) + sharded step + nb_download_bodies, every step"},
+                    "what": "per rank: nb_upload_bodies (host) + nb_shard_step + nb_download_bodies, every step"},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_solve", "achieved": None, "peak": peaks()[0], "unit": "GB/s", "frac": None, "traffic": None,
-                         "note": "per-sweep launches interleaved with the all-gather; see the N=1 line for the solver roofline"},
+                         "note": "per-sweep launches interleaved with the ghost exchange; see the N=1 line for the solver roofline"},
         }
         emit(line)
-    if not graphed:  # with recorded collectives alive the teardown can block; the process leaves through os._exit below
-        dist.destroy_process_group()
+    sim.sim.close()
+    dist.destroy_process_group()
 
 
 def run_ours(args):
@@ -486,6 +530,9 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solver", default="parity", choices=["parity", "throughput"], help="parity = the reference's exact Gauss-Seidel order (default, bit-identical results); throughput = mass-splitting Jacobi")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="N > 1: ghost exchange through the library's peer-memory kernels (default) or one ncclAllGather; both are timed, `value` is this one")
+    ap.add_argument("--margin", type=float, default=0.5, help="N > 1: extra halo width beyond the bounding radii (room for motion between re-partitions)")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the NCCL / peer / host-exchange bit-equality check before the timed region")
     ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent copies of the workload instead of one sharded scene")
     args = ap.parse_args()
     if args.presim < 0:
@@ -499,7 +546,3 @@ def main():
 if __name__ == "__main__":
     main()
     sys.stdout.flush(); sys.stderr.flush()
-    if os.environ.get("NB_SHARD_GRAPH", "0") == "1" and int(os.environ.get("WORLD_SIZE", 1)) > 1:
-        # opt-in mode only: with NCCL collectives recorded inside a live torch CUDA graph the interpreter teardown blocked once;
-        # every other run exits normally (atexit hooks run, teardown failures show in the exit code)
-        os._exit(0)

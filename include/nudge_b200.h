@@ -100,17 +100,28 @@ int nb_download_transforms(nb_context*, nb_transform* host, uint32_t count, void
 int nb_pack_momentum(nb_context*, const uint32_t* dev_indices, uint32_t n, void* dev_out, void* stream);
 int nb_unpack_momentum(nb_context*, const uint32_t* dev_indices, const uint32_t* dev_sources, uint32_t n, const void* dev_in, void* stream);
 
-/* EXPERIMENTAL (opt-in, not yet validated on hardware): the same ghost exchange carried by the solver's dataflow
- * over peer memory instead of collectives between launches.  nb_exchange_create allocates this rank's inbox and returns its CUDA IPC
- * handle (64 bytes); the ranks swap handles out of band and map each other's inbox with nb_exchange_open; nb_exchange_plan uploads, per
- * local body, its subscribers (CSR exp_off[B+1] over (exp_rank, exp_slot)) and, per ghost body, its inbox slot (0xffffffff otherwise).
- * A step then calls nb_setup_contact_constraints_deferred (setup without the warm-start launch) and nb_solve_exchange (warm start and
- * all sweeps in one launch, ghosts fed by their owners' GPUs) in place of nb_setup_contact_constraints + nb_apply_impulses. */
-int nb_exchange_create(nb_context*, uint32_t rank, uint32_t world, uint32_t ghost_capacity, uint32_t max_passes, void* ipc_handle_out);
-int nb_exchange_open(nb_context*, uint32_t peer, const void* ipc_handle);
-int nb_exchange_plan(nb_context*, const uint32_t* exp_off, const uint32_t* exp_rank, const uint32_t* exp_slot, uint32_t n_targets, const uint32_t* ghost_slot, void* stream);
-int nb_setup_contact_constraints_deferred(nb_context*, void* stream);
-int nb_solve_exchange(nb_context*, uint32_t sweeps, void* stream);
+/* One scene sharded across GPUs: C++ host, one process or thread per GPU, one nb_context per rank holding the
+ * rank's OWNED bodies plus GHOST copies of neighbouring bodies.  After the warm start and after every solver sweep the ghosts'
+ * BodyMomentum rows are replaced by their owners' (nb_shard_exchange), either with ONE ncclAllGather (NB_SHARD_NCCL, what BASELINE.json
+ * prescribes; NCCL is bound at run time with dlopen) or with this library's own push/pull kernels over CUDA-IPC peer memory
+ * (NB_SHARD_PEER: neighbour-only traffic over NVLink, no collective).  Both give bit-identical ghost rows.
+ *   rank 0: nb_shard_unique_id -> broadcast the 128 bytes -> every rank: nb_shard_create;  every rank: nb_shard_ipc_handle -> all-gather
+ *   the 64-byte handles -> nb_shard_open_peer for every other rank;  after every (re)partition: nb_shard_plan;  then nb_shard_step per
+ *   sub-step (or nb_shard_exchange between the stage calls).  nb_shard_partition is the (host, deterministic) partition rule. */
+typedef struct nb_shard nb_shard;
+enum nb_shard_transport { NB_SHARD_NCCL = 0, NB_SHARD_PEER = 1 };
+int nb_shard_unique_id(void* nccl_id_out /* 128 bytes */);
+int nb_shard_create(nb_context*, uint32_t rank, uint32_t world, const void* nccl_id /* null: peer transport only */, uint32_t ghost_capacity, uint32_t export_capacity, nb_shard** out);
+void nb_shard_destroy(nb_shard*);
+int nb_shard_ipc_handle(nb_shard*, void* handle_out /* 64 bytes */);
+int nb_shard_open_peer(nb_shard*, uint32_t peer, const void* handle);
+int nb_shard_plan(nb_shard*, const uint32_t* export_local, uint32_t n_export, const uint32_t* sub_off, const uint32_t* sub_rank, const uint32_t* sub_slot,
+                  const uint32_t* ghost_local, const uint32_t* ghost_src, uint32_t n_ghost, uint32_t max_export, void* stream);
+int nb_shard_exchange(nb_shard*, int transport, void* stream);
+int nb_shard_step(nb_shard*, float time_step, uint32_t iterations, float gravity, float damping, int transport, void* stream);
+int nb_shard_graph_active(const nb_shard*);
+int nb_shard_partition(const float* pos_xyz, const float* radius, uint32_t n, uint32_t gx, uint32_t gz, float margin,
+                       uint32_t* owner_out, uint32_t* ghost_off /* gx*gz + 1 */, uint32_t* ghost_ids, uint32_t ghost_capacity);
 
 /* The simulation step, device resident.  Same order of calls as example/main.cpp:274-328. */
 int nb_collide(nb_context*, void* stream);

@@ -17,7 +17,8 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_download_momentum", "nb_download_transforms", "nb_collide", "nb_apply_gravity_damping", "nb_read_cached_impulses",
            "nb_setup_contact_constraints", "nb_apply_impulses", "nb_update_cached_impulses", "nb_write_cached_impulses", "nb_advance", "nb_step",
            "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact", "nb_debug_sort", "nb_debug_scan", "nb_debug_enable", "nb_pack_momentum", "nb_unpack_momentum",
-           "nb_exchange_create", "nb_exchange_open", "nb_exchange_plan", "nb_setup_contact_constraints_deferred", "nb_solve_exchange",
+           "nb_shard_unique_id", "nb_shard_create", "nb_shard_destroy", "nb_shard_ipc_handle", "nb_shard_open_peer", "nb_shard_plan", "nb_shard_exchange",
+           "nb_shard_step", "nb_shard_graph_active", "nb_shard_partition",
            "nb_set_solver_mode", "nb_get_solver_mode", "nb_debug_timing_enable", "nb_debug_timing"]
 
 
@@ -65,11 +66,16 @@ def load_library():
         lib.nb_debug_enable.argtypes = [V, C.c_int]
         lib.nb_pack_momentum.argtypes = [V, V, C.c_uint32, V, V]
         lib.nb_unpack_momentum.argtypes = [V, V, V, C.c_uint32, V, V]
-        lib.nb_exchange_create.argtypes = [V, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, V]
-        lib.nb_exchange_open.argtypes = [V, C.c_uint32, V]
-        lib.nb_exchange_plan.argtypes = [V, V, V, V, C.c_uint32, V, V]
-        lib.nb_setup_contact_constraints_deferred.argtypes = [V, V]
-        lib.nb_solve_exchange.argtypes = [V, C.c_uint32, V]
+        lib.nb_shard_unique_id.argtypes = [V]
+        lib.nb_shard_create.argtypes = [V, C.c_uint32, C.c_uint32, V, C.c_uint32, C.c_uint32, V]
+        lib.nb_shard_destroy.argtypes = [V]; lib.nb_shard_destroy.restype = None
+        lib.nb_shard_ipc_handle.argtypes = [V, V]
+        lib.nb_shard_open_peer.argtypes = [V, C.c_uint32, V]
+        lib.nb_shard_plan.argtypes = [V, V, C.c_uint32, V, V, V, V, V, C.c_uint32, C.c_uint32, V]
+        lib.nb_shard_exchange.argtypes = [V, C.c_int, V]
+        lib.nb_shard_step.argtypes = [V, C.c_float, C.c_uint32, C.c_float, C.c_float, C.c_int, V]
+        lib.nb_shard_graph_active.argtypes = [V]
+        lib.nb_shard_partition.argtypes = [V, V, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, V, V, V, C.c_uint32]
         lib.nb_set_solver_mode.argtypes = [V, C.c_int]
         lib.nb_get_solver_mode.argtypes = [V]
         lib.nb_debug_timing_enable.argtypes = [V, C.c_int]
@@ -80,6 +86,33 @@ def load_library():
 
 class NudgeError(RuntimeError):
     pass
+
+
+def nccl_unique_id():
+    """128 bytes from ncclGetUniqueId (rank 0 calls it and broadcasts them)."""
+    buf = (C.c_ubyte * 128)()
+    r = load_library().nb_shard_unique_id(buf)
+    if r != 0:
+        raise NudgeError("nb_shard_unique_id failed (%d): NCCL not loadable" % r)
+    return bytes(buf)
+
+
+def shard_partition(pos, radius, gx, gz, margin):
+    """nb_shard_partition (C++ host code, runs without a GPU): owner[n] and the ghost list of every rank."""
+    lib = load_library()
+    pos = np.ascontiguousarray(pos, np.float32); radius = np.ascontiguousarray(radius, np.float32)
+    n, world = len(radius), gx * gz
+    owner = np.zeros(n, np.uint32); off = np.zeros(world + 1, np.uint32)
+    cap = max(1024, n)
+    while True:
+        ids = np.zeros(cap, np.uint32)
+        r = lib.nb_shard_partition(abi.ptr(pos), abi.ptr(radius), n, int(gx), int(gz), C.c_float(margin), abi.ptr(owner), abi.ptr(off), abi.ptr(ids), cap)
+        if r == 0:
+            break
+        if r != -2:
+            raise NudgeError("nb_shard_partition failed (%d)" % r)
+        cap = int(off[world]) + 16
+    return owner, [ids[off[k]:off[k + 1]].copy() for k in range(world)]
 
 
 class Sim(abi.HostState):
@@ -106,6 +139,9 @@ class Sim(abi.HostState):
         self.upload()
 
     def close(self):
+        if getattr(self, "shard", None):
+            self.lib.nb_shard_destroy(self.shard)
+            self.shard = None
         if getattr(self, "ctx", None):
             self.lib.nb_destroy(self.ctx)
             self.ctx = None
@@ -134,28 +170,38 @@ class Sim(abi.HostState):
     def unpack_momentum(self, dev_indices_ptr, dev_sources_ptr, n, dev_in_ptr):
         self._ck(self.lib.nb_unpack_momentum(self.ctx, C.c_void_p(dev_indices_ptr), C.c_void_p(dev_sources_ptr), int(n), C.c_void_p(dev_in_ptr), self.stream), "nb_unpack_momentum")
 
+    # ---- one scene sharded across GPUs: the C++ host behind nb_shard_* (include/nudge_b200.h) ----
+    TRANSPORT = {"nccl": 0, "peer": 1}
+
+    def shard_create(self, rank, world, nccl_id, ghost_capacity, export_capacity):
+        self.shard = C.c_void_p()
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(nccl_id) if nccl_id is not None else None
+        self._ck(self.lib.nb_shard_create(self.ctx, int(rank), int(world), idbuf, int(ghost_capacity), int(export_capacity), C.byref(self.shard)), "nb_shard_create")
+
+    def shard_ipc_handle(self):
+        h = (C.c_ubyte * 64)()
+        self._ck(self.lib.nb_shard_ipc_handle(self.shard, h), "nb_shard_ipc_handle")
+        return bytes(h)
+
+    def shard_open_peer(self, peer, handle):
+        self._ck(self.lib.nb_shard_open_peer(self.shard, int(peer), (C.c_ubyte * 64).from_buffer_copy(handle)), "nb_shard_open_peer")
+
+    def shard_plan(self, export_local, sub_off, sub_rank, sub_slot, ghost_local, ghost_src, max_export):
+        arrs = [np.ascontiguousarray(x, np.uint32) for x in (export_local, sub_off, sub_rank, sub_slot, ghost_local, ghost_src)]
+        e, so, sr, ss, gl, gs = arrs
+        self._ck(self.lib.nb_shard_plan(self.shard, abi.ptr(e), len(e), abi.ptr(so), abi.ptr(sr), abi.ptr(ss), abi.ptr(gl), abi.ptr(gs), len(gl), int(max_export), self.stream), "nb_shard_plan")
+
+    def shard_exchange(self, transport):
+        self._ck(self.lib.nb_shard_exchange(self.shard, self.TRANSPORT[transport], self.stream), "nb_shard_exchange")
+
+    def shard_step(self, transport):
+        s = self.scene
+        self._ck(self.lib.nb_shard_step(self.shard, float(s.time_step), int(s.iterations), float(s.gravity), float(s.damping), self.TRANSPORT[transport], self.stream), "nb_shard_step")
+
+    def shard_graph_active(self):
+        return bool(self.lib.nb_shard_graph_active(self.shard))
+
     # ---- host <-> HBM ----
-    # ---- experimental cross-GPU dataflow exchange (include/nudge_b200.h) ----
-    def exchange_create(self, rank, world, ghost_capacity, max_passes):
-        handle = (C.c_ubyte * 64)()
-        self._ck(self.lib.nb_exchange_create(self.ctx, int(rank), int(world), int(ghost_capacity), int(max_passes), handle), "nb_exchange_create")
-        return bytes(handle)
-
-    def exchange_open(self, peer, handle):
-        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
-        self._ck(self.lib.nb_exchange_open(self.ctx, int(peer), buf), "nb_exchange_open")
-
-    def exchange_plan(self, exp_off, exp_rank, exp_slot, ghost_slot):
-        exp_off = np.ascontiguousarray(exp_off, np.uint32); exp_rank = np.ascontiguousarray(exp_rank, np.uint32)
-        exp_slot = np.ascontiguousarray(exp_slot, np.uint32); ghost_slot = np.ascontiguousarray(ghost_slot, np.uint32)
-        self._ck(self.lib.nb_exchange_plan(self.ctx, abi.ptr(exp_off), abi.ptr(exp_rank), abi.ptr(exp_slot), len(exp_rank), abi.ptr(ghost_slot), self.stream), "nb_exchange_plan")
-
-    def setup_contact_constraints_deferred(self):
-        self._ck(self.lib.nb_setup_contact_constraints_deferred(self.ctx, self.stream), "nb_setup_contact_constraints_deferred")
-
-    def solve_exchange(self, sweeps):
-        self._ck(self.lib.nb_solve_exchange(self.ctx, int(sweeps), self.stream), "nb_solve_exchange")
-
     def upload(self):
         self._ck(self.lib.nb_upload_bodies(self.ctx, C.byref(self.bodies), self.stream), "nb_upload_bodies")
         self._ck(self.lib.nb_upload_colliders(self.ctx, C.byref(self.colliders), self.stream), "nb_upload_colliders")

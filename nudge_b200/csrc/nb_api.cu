@@ -2,13 +2,15 @@
 // The reference keeps all memory caller-owned and bump-allocates scratch from an Arena (nudge.cpp:990-1055);
 // here the context plays both roles for device memory: every buffer is carved once from cudaMalloc at
 // nb_create and reused every step, nothing is allocated or synchronised inside the step.
-#include "nb_jacobi.cuh"
+#include "nb_shard.cuh"
 #define NB_DEFAULT_COOP_LAUNCH 1
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <math.h>
 
 extern "C" void nb_host_sample_luts(u32* rcp_lut, u32* rsqrt_lut);   // nb_lut_host.cpp
 extern "C" int nb_host_check_lut_model(const u32* rcp_lut, const u32* rsqrt_lut);
@@ -29,10 +31,6 @@ struct nb_context {
 	int coop_blocks_solve; int coop_launch;
 	u64* keybits;  // OR, AND of the Morton codes of the current collide
 	bool defer_warm_start;  // nb_step: the warm start runs inside the first solver launch
-	// cross-GPU dataflow exchange (nb_exchange_*): opt-in
-	bool xch_enabled; bool warm_pending; Exchange xch; u32 xch_rank, xch_world; int xch_blocks;
-	float4** xch_peers_dev; std::vector<float4*> xch_peers; std::vector<void*> xch_opened;
-	u32* xch_exp_off; uint2* xch_exp_tgt; u32 xch_tgt_cap; u32* xch_ghost_slot; u32* xch_epoch;
 	// nb_step as a CUDA graph: captured once per (stream, parameters, scene shape), replayed afterwards
 	struct StepKey { cudaStream_t stream; float ts, gravity, damping; u32 iterations, B, nboxes, nspheres, nconn, tagbits, kbits; int debug, solver_mode; } graph_key;
 	cudaGraphExec_t graph_exec; unsigned long long graph_launches; int graph_enabled; bool capturing;
@@ -250,7 +248,6 @@ void nb_destroy(nb_context* ctx) {
 	if (!ctx) return;
 	cudaDeviceSynchronize();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
-	for (size_t i = 0; i < ctx->xch_opened.size(); ++i) cudaIpcCloseMemHandle(ctx->xch_opened[i]);
 	for (size_t i = 0; i < ctx->allocs.size(); ++i) cudaFree(ctx->allocs[i]);
 	delete ctx;
 }
@@ -599,7 +596,6 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 		ctx->offs, ctx->left_count, ctx->batch_of, ctx->slot_idx, ctx->rows.contact, ctx->cstride, ctx->sb.keys[0], ctx->sb.vals[0], ctx->batchbits, counts);
 	++ctx->launches;
 	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_ENTRIES, 0, (int)(ctx->bodybits + ctx->batchbits), true, 0);
-	if (ctx->xch_enabled) CK(cudaMemsetAsync(ctx->chain_len, 0, sizeof(u32) * B, st));  // "no contacts on this rank" must read as length 0
 	k_chain_heads<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->batchbits, ctx->chain_start, ctx->chain_len, counts); ++ctx->launches;
 	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, ctx->slot_idx, ctx->chain_start, ctx->chain_len, ctx->rows.wait, ctx->cstride, counts);
 	k_build_rows<false><<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts, nullptr);
@@ -627,88 +623,6 @@ int nb_update_cached_impulses(nb_context* ctx, void* stream) {
 int nb_advance(nb_context* ctx, float time_step, void* stream) {
 	k_advance<<<GRID(ctx->B), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->active_idx, ctx->xf, ctx->mom, ctx->idle, time_step, ctx->counts);
 	++ctx->launches;
-	CK(cudaGetLastError());
-	return NB_OK;
-}
-
-// ---------------- cross-GPU dataflow exchange (opt-in; kernels in nb_solver.cuh, plan in nudge_b200/shard.py) ----------------
-// nb_exchange_create allocates this rank's inbox and returns its CUDA IPC handle (64 bytes); the ranks swap handles (any
-// out-of-band channel) and nb_exchange_open maps every peer's inbox.  Every rank must use the same capacities.
-int nb_exchange_create(nb_context* ctx, uint32_t rank, uint32_t world, uint32_t ghost_capacity, uint32_t max_passes, void* handle_out) {
-	if (ctx->xch_enabled) { ctx->error = "exchange already created"; return NB_ERR_ARGUMENT; }
-	if (!world || rank >= world || !ghost_capacity || !max_passes || max_passes > 63) { ctx->error = "bad exchange configuration"; return NB_ERR_ARGUMENT; }
-	const u32 B = ctx->cfg.max_bodies;
-	size_t rows = 2 * (size_t)max_passes * ghost_capacity;  // two epoch parities
-	ALLOC(ctx->xch.inbox, 2 * rows);
-	ALLOC(ctx->xch_peers_dev, world); ALLOC(ctx->xch_exp_off, (size_t)B + 1); ALLOC(ctx->xch_ghost_slot, B); ALLOC(ctx->xch_epoch, 1);
-	ctx->xch_tgt_cap = 2 * B; ALLOC(ctx->xch_exp_tgt, ctx->xch_tgt_cap);
-	CK(cudaMemset(ctx->xch_ghost_slot, 0xff, sizeof(u32) * B));
-	ctx->xch_peers.assign(world, nullptr);
-	ctx->xch_peers[rank] = ctx->xch.inbox;
-	CK(cudaMemcpy(ctx->xch_peers_dev, ctx->xch_peers.data(), sizeof(float4*) * world, cudaMemcpyHostToDevice));
-	ctx->xch.peer_inbox = ctx->xch_peers_dev; ctx->xch.exp_off = ctx->xch_exp_off; ctx->xch.exp_tgt = ctx->xch_exp_tgt; ctx->xch.ghost_slot = ctx->xch_ghost_slot;
-	ctx->xch.ghost_cap = ghost_capacity; ctx->xch.passes_cap = max_passes; ctx->xch.epoch = ctx->xch_epoch;
-	ctx->xch_rank = rank; ctx->xch_world = world;
-	int per_sm = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_exchange, NB_BLOCK, 0));
-	if (per_sm < 1) { ctx->error = "k_solve_exchange does not fit on an SM"; return NB_ERR_CUDA; }
-	ctx->xch_blocks = ctx->sms * per_sm;
-	if (handle_out) { cudaIpcMemHandle_t h; CK(cudaIpcGetMemHandle(&h, ctx->xch.inbox)); memcpy(handle_out, &h, sizeof(h)); }
-	ctx->xch_enabled = true;
-	return NB_OK;
-}
-int nb_exchange_open(nb_context* ctx, uint32_t peer, const void* handle) {
-	if (!ctx->xch_enabled || peer >= ctx->xch_world) { ctx->error = "exchange not created / bad peer"; return NB_ERR_ARGUMENT; }
-	if (peer != ctx->xch_rank) {
-		cudaIpcMemHandle_t h; memcpy(&h, handle, sizeof(h));
-		void* p = nullptr;
-		CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-		ctx->xch_opened.push_back(p);
-		ctx->xch_peers[peer] = (float4*)p;
-	}
-	CK(cudaMemcpy(ctx->xch_peers_dev, ctx->xch_peers.data(), sizeof(float4*) * ctx->xch_world, cudaMemcpyHostToDevice));
-	return NB_OK;
-}
-// exp_off[B + 1]: CSR over (exp_rank, exp_slot) = the subscribers of every local body; ghost_slot[B]: inbox slot or 0xffffffff.
-int nb_exchange_plan(nb_context* ctx, const uint32_t* exp_off, const uint32_t* exp_rank, const uint32_t* exp_slot, uint32_t n_targets, const uint32_t* ghost_slot, void* stream) {
-	if (!ctx->xch_enabled) { ctx->error = "exchange not created"; return NB_ERR_ARGUMENT; }
-	if (n_targets > ctx->xch_tgt_cap) { ctx->error = "too many exchange targets"; return NB_ERR_CAPACITY; }
-	const u32 B = ctx->B;
-	std::vector<uint2> tg(n_targets);
-	for (u32 i = 0; i < n_targets; ++i) {
-		if (exp_rank[i] >= ctx->xch_world || exp_slot[i] >= ctx->xch.ghost_cap || !ctx->xch_peers[exp_rank[i]]) { ctx->error = "exchange target out of range / peer not opened"; return NB_ERR_ARGUMENT; }
-		tg[i] = make_uint2(exp_rank[i], exp_slot[i]);
-	}
-	for (u32 i = 0; i < B; ++i) if (ghost_slot[i] != 0xffffffffu && ghost_slot[i] >= ctx->xch.ghost_cap) { ctx->error = "ghost slot out of range"; return NB_ERR_ARGUMENT; }
-	CK(cudaStreamSynchronize((cudaStream_t)stream));
-	CK(cudaMemcpy(ctx->xch_exp_off, exp_off, sizeof(u32) * ((size_t)B + 1), cudaMemcpyHostToDevice));
-	if (n_targets) CK(cudaMemcpy(ctx->xch_exp_tgt, tg.data(), sizeof(uint2) * n_targets, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(ctx->xch_ghost_slot, ghost_slot, sizeof(u32) * B, cudaMemcpyHostToDevice));
-	return NB_OK;
-}
-// setup_contact_constraints without its warm-start launch: nb_solve_exchange runs the warm start as pass 0
-int nb_setup_contact_constraints_deferred(nb_context* ctx, void* stream) {
-	ctx->defer_warm_start = true;
-	int r = nb_setup_contact_constraints(ctx, stream);
-	ctx->defer_warm_start = false;
-	ctx->warm_pending = r == NB_OK;
-	return r;
-}
-// warm start + `sweeps` sweeps in one launch, ghosts fed by their owners' GPUs through the inboxes (k_solve_exchange)
-int nb_solve_exchange(nb_context* ctx, uint32_t sweeps, void* stream) {
-	if (!ctx->xch_enabled || !ctx->warm_pending) { ctx->error = "nb_solve_exchange needs nb_exchange_create and nb_setup_contact_constraints_deferred"; return NB_ERR_ARGUMENT; }
-	const u32 passes = sweeps + 1;
-	if (passes > ctx->xch.passes_cap) { ctx->error = "more passes than the inbox holds"; return NB_ERR_CAPACITY; }
-	cudaStream_t st = (cudaStream_t)stream;
-	const u32 B = ctx->B;
-	Rows R = ctx->rows; const float4* impulses = ctx->impulses; float4* mw = ctx->mw; u32* counts = ctx->counts; u32 hop = ctx->solve_backoff_ns; Exchange X = ctx->xch;
-	k_exchange_epoch<<<1, 1, 0, st>>>(ctx->xch_epoch);
-	k_mw_in_exchange<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw, ctx->chain_len, X, passes);
-	void* args[] = { &R, &impulses, &mw, &sweeps, &hop, &counts, &X };
-	CK(cudaLaunchCooperativeKernel((void*)k_solve_exchange, dim3(ctx->xch_blocks), dim3(NB_BLOCK), args, 0, st));
-	k_mw_out_exchange<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw, X, passes);
-	ctx->launches += 4;
-	ctx->warm_pending = false;
 	CK(cudaGetLastError());
 	return NB_OK;
 }
@@ -883,3 +797,5 @@ int nb_debug_rcp(nb_context* ctx, const float* x, float* y, uint32_t n, int rsq)
 }
 
 }
+
+#include "nb_shard_api.cuh"

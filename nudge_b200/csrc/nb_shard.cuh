@@ -1,0 +1,119 @@
+// nudge_b200 — one scene sharded across GPUs: the C++ host of SURVEY.md §8(e), behind the C ABI (nb_shard_*, include/nudge_b200.h).
+//
+// One process (or thread) per GPU.  A rank simulates its OWNED bodies plus GHOST copies of neighbouring bodies with the complete
+// single-GPU pipeline; after the warm start and after every solver sweep each ghost's BodyMomentum row (32 B) is replaced by its
+// owner's.  Two transports for that exchange, bit-identical in effect:
+//
+//   NB_SHARD_NCCL  pack (gather export rows) -> ONE ncclAllGather over NVLink/NVSwitch -> unpack (scatter into ghost rows): what
+//                  BASELINE.json's north_star prescribes.  NCCL is bound at run time (dlopen libnccl.so.2: the copy torch loaded,
+//                  or the system one), so the library itself has no link-time dependency on it.
+//   NB_SHARD_PEER  our own kernels over peer memory: k_shard_push stores each export row straight into every subscriber's inbox
+//                  (CUDA-IPC mapped memory of the neighbouring GPU, st.global over NVLink) and raises a per-rank arrival flag with a
+//                  system-scope release; k_shard_pull waits for the flags of all ranks and scatters its inbox into the ghost rows.
+//                  Neighbour-only traffic (a row travels to its subscribers, not to everybody), no host involvement, two small
+//                  launches per exchange, capturable in a CUDA graph with the rest of the step.
+//
+// Inbox protocol: two parities, selected by the exchange epoch.  Every rank signals every other rank every epoch (a flag store is
+// 4 bytes), so a rank can run at most one epoch ahead of any peer: push #e+2 (same parity as #e) is issued after pull #e+1, which
+// waited for every peer's push #e+1, which that peer issued after ITS pull #e — the rows of epoch e have been consumed everywhere
+// before they are overwritten.  (This is the back-pressure the round-1 prototype lacked.)
+#pragma once
+#include "nb_jacobi.cuh"
+#include <string>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#define NB_SHARD_FLAG_WORDS 64   // header of the inbox allocation: arrival epoch per source rank (world <= 64)
+enum { OVF_EXCHANGE = 16 };      // counts[CNT_OVERFLOW] bit: a pull gave up waiting for a peer
+
+struct ShardPlanDev {
+	const u32* export_local;   // [n_export] local body index of every row this rank exports
+	const u32* sub_off;        // [n_export + 1] CSR over the subscribers of each export row
+	const uint2* sub_tgt;      // (rank, inbox slot on that rank)
+	const u32* ghost_local;    // [n_ghost] local body index of inbox slot j
+	const u32* ghost_src;      // [n_ghost] row in the all-gather buffer (owner * max_export + row in the owner's export list)
+	u32 n_export, n_ghost;
+};
+
+NB_DEV void st_release_sys(u32* p, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+NB_DEV u32 ld_acquire_sys(const u32* p) { u32 v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+NB_DEV float4 ld_volatile_f4(const float4* p) { float4 v; asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v; }
+
+// rows -> subscribers' inboxes; the last block to finish raises this rank's flag on every peer.  peers[r] = base of rank r's inbox
+// allocation (flags first, then [2][ghost_cap][2] float4).  *epoch is advanced by the last block, so the pull that follows reads it.
+__global__ void __launch_bounds__(NB_BLOCK) k_shard_push(const float4* mom, ShardPlanDev P, unsigned char* const* peers, u32 ghost_cap, u32 rank, u32 world,
+														 u32* epoch, u32* done) {
+	const u32 ep = *epoch + 1;
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_export; i += gridDim.x * blockDim.x) {
+		const u32 body = P.export_local[i];
+		const float4 l = mom[2 * body], w = mom[2 * body + 1];
+		for (u32 t = P.sub_off[i]; t < P.sub_off[i + 1]; ++t) {
+			const uint2 tg = P.sub_tgt[t];
+			float4* dst = reinterpret_cast<float4*>(peers[tg.x] + NB_SHARD_FLAG_WORDS * 4) + 2 * ((size_t)(ep & 1u) * ghost_cap + tg.y);
+			dst[0] = l; dst[1] = w;
+		}
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const u32 old = atomicAdd(done, 1u);
+		if (old == gridDim.x - 1) {      // every block's rows are out (each fenced before it arrived here)
+			__threadfence_system();
+			for (u32 r = 0; r < world; ++r)
+				if (r != rank) st_release_sys(reinterpret_cast<u32*>(peers[r]) + rank, ep);
+			*done = 0;
+			*epoch = ep;
+		}
+	}
+}
+
+// waits until every peer has pushed this epoch, then scatters the inbox into the ghost rows
+__global__ void __launch_bounds__(NB_BLOCK) k_shard_pull(float4* mom, ShardPlanDev P, unsigned char* inbox, u32 ghost_cap, u32 rank, u32 world, const u32* epoch, u32* counts, long long timeout_cycles) {
+	const u32 ep = *epoch;
+	__shared__ int ok;
+	if (threadIdx.x == 0) {
+		const u32* flags = reinterpret_cast<const u32*>(inbox);
+		const long long t0 = clock64();
+		int good = 1;
+		for (u32 r = 0; r < world && good; ++r) {
+			if (r == rank) continue;
+			while ((int)(ld_acquire_sys(flags + r) - ep) < 0) {
+				if (clock64() - t0 > timeout_cycles) { good = 0; atomicOr(&counts[CNT_OVERFLOW], OVF_EXCHANGE); break; }
+				__nanosleep(200);
+			}
+		}
+		ok = good;
+	}
+	__syncthreads();
+	if (!ok) return;
+	const float4* rows = reinterpret_cast<const float4*>(inbox + NB_SHARD_FLAG_WORDS * 4) + 2 * (size_t)(ep & 1u) * ghost_cap;
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * P.n_ghost; i += gridDim.x * blockDim.x)
+		mom[2 * P.ghost_local[i >> 1] + (i & 1)] = ld_volatile_f4(rows + i);
+}
+
+// ---- NCCL bound at run time ----
+struct NcclApi {
+	void* lib;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+	ncclResult_t (*CommDestroy)(ncclComm_t);
+	const char* (*GetErrorString)(ncclResult_t);
+};
+static NcclApi* nccl_api(std::string* err) {
+	static NcclApi api; static int state = 0;   // 0 untried, 1 ok, -1 failed
+	if (state == 0) {
+		const char* names[] = { "libnccl.so.2", "libnccl.so" };
+		for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+		if (api.lib) {
+			api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+			api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+			api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+			api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+			api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+		}
+		state = (api.lib && api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString) ? 1 : -1;
+	}
+	if (state != 1) { if (err) *err = "NCCL (libnccl.so.2) could not be loaded"; return nullptr; }
+	return &api;
+}

@@ -1,0 +1,265 @@
+// nudge_b200 — host side of nb_shard_* (include/nudge_b200.h): NCCL communicator, peer-memory inboxes, exchange plan, the sharded
+// sub-step and its CUDA graph.  Included at the end of nb_api.cu (needs nb_context's internals).  Kernels: nb_shard.cuh.
+#pragma once
+
+struct nb_shard {
+	nb_context* ctx;
+	u32 rank, world;
+	ncclComm_t comm; bool has_nccl;
+	// peer-memory transport
+	unsigned char* inbox; u32 ghost_cap; std::vector<unsigned char*> peers; unsigned char** peers_dev; std::vector<void*> opened; bool peers_ready;
+	u32* epoch; u32* done;
+	// plan (device copies)
+	u32* d_export_local; u32* d_sub_off; uint2* d_sub_tgt; u32* d_ghost_local; u32* d_ghost_src;
+	u32 cap_export, cap_ghost, cap_sub;
+	ShardPlanDev plan; u32 max_export; unsigned long long plan_version;
+	// NCCL transport buffers
+	float4* d_export; float4* d_gather;
+	// sharded step as a CUDA graph
+	struct Key { cudaStream_t stream; float ts, gravity, damping; u32 iterations; int transport, solver_mode; unsigned long long plan_version; u32 B, nboxes, nspheres; } key;
+	cudaGraphExec_t graph; unsigned long long graph_launches; int graph_enabled;
+	long long pull_timeout_cycles;
+};
+
+#define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { sh->ctx->error = std::string(#call) + ": " + cudaGetErrorString(e_); return NB_ERR_CUDA; } } while (0)
+
+extern "C" {
+
+int nb_shard_unique_id(void* id_out) {
+	std::string err;
+	NcclApi* api = nccl_api(&err);
+	if (!api || !id_out) return NB_ERR_ARGUMENT;
+	ncclUniqueId id;
+	if (api->GetUniqueId(&id) != ncclSuccess) return NB_ERR_CUDA;
+	memcpy(id_out, &id, sizeof(id));
+	return NB_OK;
+}
+
+// ghost_capacity / export_capacity: upper bounds for the plans this shard will see (every rank must pass the same ghost_capacity).
+// nccl_id: the 128 bytes rank 0 obtained from nb_shard_unique_id, or null to run without NCCL (peer transport only).
+int nb_shard_create(nb_context* ctx, uint32_t rank, uint32_t world, const void* nccl_id, uint32_t ghost_capacity, uint32_t export_capacity, nb_shard** out) {
+	if (!ctx || !out || !world || rank >= world || world > NB_SHARD_FLAG_WORDS || !ghost_capacity || !export_capacity) { if (ctx) ctx->error = "bad shard configuration"; return NB_ERR_ARGUMENT; }
+	nb_shard* sh = new nb_shard();
+	*out = sh;
+	sh->ctx = ctx; sh->rank = rank; sh->world = world; sh->ghost_cap = ghost_capacity;
+	sh->cap_export = export_capacity; sh->cap_ghost = ghost_capacity; sh->cap_sub = 4 * export_capacity + 64;
+	CK(cudaSetDevice(ctx->cfg.device));
+	size_t inbox_bytes = NB_SHARD_FLAG_WORDS * 4 + sizeof(float4) * 2 * 2 * (size_t)ghost_capacity;
+	ALLOC(sh->inbox, inbox_bytes);
+	ALLOC(sh->peers_dev, world); ALLOC(sh->epoch, 1); ALLOC(sh->done, 1);
+	ALLOC(sh->d_export_local, sh->cap_export); ALLOC(sh->d_sub_off, (size_t)sh->cap_export + 1); ALLOC(sh->d_sub_tgt, sh->cap_sub);
+	ALLOC(sh->d_ghost_local, sh->cap_ghost); ALLOC(sh->d_ghost_src, sh->cap_ghost);
+	ALLOC(sh->d_export, 2 * (size_t)export_capacity); ALLOC(sh->d_gather, 2 * (size_t)export_capacity * world);
+	sh->peers.assign(world, nullptr); sh->peers[rank] = sh->inbox;
+	sh->graph_enabled = ctx->graph_enabled;
+	int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->cfg.device);
+	sh->pull_timeout_cycles = (long long)(khz ? khz : 1500000) * 1000LL * 5;   // 5 s: a peer that never pushes is reported, not waited for forever
+	if (nccl_id) {
+		std::string err;
+		NcclApi* api = nccl_api(&err);
+		if (!api) { ctx->error = err; return NB_ERR_CUDA; }
+		ncclUniqueId id; memcpy(&id, nccl_id, sizeof(id));
+		ncclResult_t r = api->CommInitRank(&sh->comm, (int)world, id, (int)rank);
+		if (r != ncclSuccess) { ctx->error = std::string("ncclCommInitRank: ") + api->GetErrorString(r); return NB_ERR_CUDA; }
+		sh->has_nccl = true;
+	}
+	return NB_OK;
+}
+
+void nb_shard_destroy(nb_shard* sh) {
+	if (!sh) return;
+	cudaDeviceSynchronize();
+	if (sh->graph) cudaGraphExecDestroy(sh->graph);
+	for (void* p : sh->opened) cudaIpcCloseMemHandle(p);
+	if (sh->has_nccl) { NcclApi* api = nccl_api(nullptr); if (api) api->CommDestroy(sh->comm); }
+	delete sh;   // device buffers belong to the nb_context's allocation list
+}
+
+// CUDA IPC handle (64 bytes) of this rank's inbox; the ranks swap them out of band and call nb_shard_open_peer for every other rank.
+int nb_shard_ipc_handle(nb_shard* sh, void* handle_out) {
+	cudaIpcMemHandle_t h;
+	SCK(cudaIpcGetMemHandle(&h, sh->inbox));
+	memcpy(handle_out, &h, sizeof(h));
+	return NB_OK;
+}
+int nb_shard_open_peer(nb_shard* sh, uint32_t peer, const void* handle) {
+	if (peer >= sh->world) { sh->ctx->error = "bad peer"; return NB_ERR_ARGUMENT; }
+	if (peer != sh->rank && !sh->peers[peer]) {
+		cudaIpcMemHandle_t h; memcpy(&h, handle, sizeof(h));
+		void* p = nullptr;
+		SCK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		sh->opened.push_back(p);
+		sh->peers[peer] = (unsigned char*)p;
+	}
+	bool all = true;
+	for (u32 r = 0; r < sh->world; ++r) all = all && sh->peers[r];
+	if (all) { SCK(cudaMemcpy(sh->peers_dev, sh->peers.data(), sizeof(unsigned char*) * sh->world, cudaMemcpyHostToDevice)); sh->peers_ready = true; }
+	return NB_OK;
+}
+
+// The exchange plan of the current partition (host arrays; synchronises the stream).  export_local[n_export]: local body index of
+// the rows this rank exports, in the order of its export list; sub_off[n_export+1] / sub_rank / sub_slot: the subscribers of each
+// export row (rank, index in that rank's ghost list); ghost_local[n_ghost]: local body index of ghost j; ghost_src[n_ghost]: its
+// row in the all-gather buffer = owner * max_export + position in the owner's export list; max_export: the largest export list of
+// any rank (the all-gather is padded to it).
+int nb_shard_plan(nb_shard* sh, const uint32_t* export_local, uint32_t n_export, const uint32_t* sub_off, const uint32_t* sub_rank, const uint32_t* sub_slot,
+				  const uint32_t* ghost_local, const uint32_t* ghost_src, uint32_t n_ghost, uint32_t max_export, void* stream) {
+	nb_context* ctx = sh->ctx;
+	const u32 n_sub = n_export ? sub_off[n_export] : 0;
+	if (n_export > sh->cap_export || n_ghost > sh->cap_ghost || n_sub > sh->cap_sub || max_export > sh->cap_export || n_export > max_export) { ctx->error = "exchange plan exceeds the shard's capacities"; return NB_ERR_CAPACITY; }
+	std::vector<uint2> tg(n_sub);
+	for (u32 i = 0; i < n_sub; ++i) {
+		if (sub_rank[i] >= sh->world || sub_rank[i] == sh->rank || sub_slot[i] >= sh->ghost_cap) { ctx->error = "exchange plan: subscriber out of range"; return NB_ERR_ARGUMENT; }
+		tg[i] = make_uint2(sub_rank[i], sub_slot[i]);
+	}
+	for (u32 i = 0; i < n_export; ++i) if (export_local[i] >= ctx->B) { ctx->error = "exchange plan: export row out of range"; return NB_ERR_ARGUMENT; }
+	for (u32 i = 0; i < n_ghost; ++i) if (ghost_local[i] >= ctx->B || ghost_src[i] >= sh->world * max_export) { ctx->error = "exchange plan: ghost out of range"; return NB_ERR_ARGUMENT; }
+	SCK(cudaStreamSynchronize((cudaStream_t)stream));
+	if (n_export) SCK(cudaMemcpy(sh->d_export_local, export_local, sizeof(u32) * n_export, cudaMemcpyHostToDevice));
+	u32 zero = 0;
+	SCK(cudaMemcpy(sh->d_sub_off, n_export ? sub_off : &zero, sizeof(u32) * ((size_t)n_export + 1), cudaMemcpyHostToDevice));
+	if (n_sub) SCK(cudaMemcpy(sh->d_sub_tgt, tg.data(), sizeof(uint2) * n_sub, cudaMemcpyHostToDevice));
+	if (n_ghost) { SCK(cudaMemcpy(sh->d_ghost_local, ghost_local, sizeof(u32) * n_ghost, cudaMemcpyHostToDevice)); SCK(cudaMemcpy(sh->d_ghost_src, ghost_src, sizeof(u32) * n_ghost, cudaMemcpyHostToDevice)); }
+	sh->plan.export_local = sh->d_export_local; sh->plan.sub_off = sh->d_sub_off; sh->plan.sub_tgt = sh->d_sub_tgt;
+	sh->plan.ghost_local = sh->d_ghost_local; sh->plan.ghost_src = sh->d_ghost_src; sh->plan.n_export = n_export; sh->plan.n_ghost = n_ghost;
+	sh->max_export = max_export;
+	++sh->plan_version;
+	return NB_OK;
+}
+
+// Ghost rows <- owners' rows.  Every rank must call it the same number of times with the same transport.
+int nb_shard_exchange(nb_shard* sh, int transport, void* stream) {
+	nb_context* ctx = sh->ctx;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (sh->world == 1) return NB_OK;
+	const ShardPlanDev P = sh->plan;
+	if (transport == NB_SHARD_NCCL) {
+		if (!sh->has_nccl) { ctx->error = "this shard was created without an NCCL id"; return NB_ERR_ARGUMENT; }
+		NcclApi* api = nccl_api(nullptr);
+		if (P.n_export) { k_pack_rows<<<GRID(2 * P.n_export), NB_BLOCK, 0, st>>>((const float4*)ctx->mom, P.export_local, P.n_export, sh->d_export); ++ctx->launches; }
+		ncclResult_t r = api->AllGather(sh->d_export, sh->d_gather, (size_t)sh->max_export * 8, ncclFloat, sh->comm, st);
+		if (r != ncclSuccess) { ctx->error = std::string("ncclAllGather: ") + api->GetErrorString(r); return NB_ERR_CUDA; }
+		if (P.n_ghost) { k_unpack_rows<<<GRID(2 * P.n_ghost), NB_BLOCK, 0, st>>>((float4*)ctx->mom, P.ghost_local, P.ghost_src, P.n_ghost, sh->d_gather); ++ctx->launches; }
+	}
+	else if (transport == NB_SHARD_PEER) {
+		if (!sh->peers_ready) { ctx->error = "peer inboxes not opened (nb_shard_open_peer for every rank)"; return NB_ERR_ARGUMENT; }
+		const unsigned grid = std::max(1u, std::min(GRID(std::max(P.n_export, 1u)), 64u));
+		k_shard_push<<<grid, NB_BLOCK, 0, st>>>((const float4*)ctx->mom, P, sh->peers_dev, sh->ghost_cap, sh->rank, sh->world, sh->epoch, sh->done);
+		k_shard_pull<<<std::max(1u, std::min(GRID(2 * std::max(P.n_ghost, 1u)), 64u)), NB_BLOCK, 0, st>>>((float4*)ctx->mom, P, sh->inbox, sh->ghost_cap, sh->rank, sh->world, sh->epoch, ctx->counts, sh->pull_timeout_cycles);
+		ctx->launches += 2;
+	}
+	else { ctx->error = "unknown transport"; return NB_ERR_ARGUMENT; }
+	SCK(cudaGetLastError());
+	return NB_OK;
+}
+
+static int shard_step_body(nb_shard* sh, float time_step, uint32_t iterations, float gravity, float damping, int transport, void* stream) {
+	nb_context* ctx = sh->ctx;
+	int r;
+	if ((r = nb_collide(ctx, stream))) return r;
+	if ((r = nb_apply_gravity_damping(ctx, time_step, gravity, damping, stream))) return r;
+	if ((r = nb_read_cached_impulses(ctx, stream))) return r;
+	if ((r = nb_setup_contact_constraints(ctx, stream))) return r;        // includes the warm start
+	if ((r = nb_shard_exchange(sh, transport, stream))) return r;
+	for (uint32_t i = 0; i < iterations; ++i) {
+		if ((r = nb_apply_impulses(ctx, 1, stream))) return r;
+		if ((r = nb_shard_exchange(sh, transport, stream))) return r;
+	}
+	if ((r = nb_update_cached_impulses(ctx, stream))) return r;
+	if ((r = nb_write_cached_impulses(ctx, stream))) return r;
+	return nb_advance(ctx, time_step, stream);
+}
+
+// One sub-step of the sharded scene (example/main.cpp:274-328 with the ghost exchange after the warm start and after every sweep).
+// On a capturable stream the whole step — kernels, NCCL all-gathers or peer pushes/pulls — is recorded once per plan into a CUDA
+// graph and replayed (NB_GRAPH=0 keeps plain launches).
+int nb_shard_step(nb_shard* sh, float time_step, uint32_t iterations, float gravity, float damping, int transport, void* stream) {
+	nb_context* ctx = sh->ctx;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (!sh->graph_enabled || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread || ctx->debug)
+		return shard_step_body(sh, time_step, iterations, gravity, damping, transport, stream);
+	nb_shard::Key key;
+	memset(&key, 0, sizeof(key));
+	key.stream = st; key.ts = time_step; key.gravity = gravity; key.damping = damping; key.iterations = iterations; key.transport = transport;
+	key.solver_mode = ctx->solver_mode; key.plan_version = sh->plan_version; key.B = ctx->B; key.nboxes = ctx->nboxes; key.nspheres = ctx->nspheres;
+	if (!sh->graph || memcmp(&key, &sh->key, sizeof(key)) != 0) {
+		if (sh->graph) { cudaGraphExecDestroy(sh->graph); sh->graph = nullptr; }
+		for (int attempt = ctx->graph_coop ? 0 : 1; attempt < 2 && !sh->graph; ++attempt) {
+			const unsigned long long before = ctx->launches;
+			const int coop = ctx->sb.coop_launch, gcoop = ctx->graph_coop;
+			if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); break; }
+			ctx->capturing = true;
+			if (attempt == 1) { ctx->sb.coop_launch = 0; ctx->graph_coop = 0; }
+			int r = shard_step_body(sh, time_step, iterations, gravity, damping, transport, stream);
+			ctx->capturing = false; ctx->sb.coop_launch = coop; ctx->graph_coop = gcoop;
+			cudaGraph_t graph = nullptr;
+			cudaError_t e = cudaStreamEndCapture(st, &graph);
+			if (r == NB_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&sh->graph, graph, 0);
+			if (graph) cudaGraphDestroy(graph);
+			sh->graph_launches = ctx->launches - before;
+			ctx->launches = before;
+			if (r != NB_OK || e != cudaSuccess || !sh->graph) { cudaGetLastError(); sh->graph = nullptr; if (attempt == 0) ctx->graph_coop = 0; }
+		}
+		if (!sh->graph) { sh->graph_enabled = 0; return shard_step_body(sh, time_step, iterations, gravity, damping, transport, stream); }
+		sh->key = key;
+	}
+	SCK(cudaGraphLaunch(sh->graph, st));
+	ctx->launches += sh->graph_launches;
+	ctx->contacts_internal = true;
+	return NB_OK;
+}
+
+int nb_shard_graph_active(const nb_shard* sh) { return sh->graph != nullptr; }
+
+// Partition of a scene for `gx * gz` ranks (rank = ix * gz + iz): equal-count columns along x, each cut into equal-count cells
+// along z.  A body is OWNED by the cell its centre lies in; it is a GHOST of every other cell whose box, grown by
+// radius[i] + max_radius + margin, contains its centre (two bodies can only touch if their centres are closer than the sum of their
+// bounding radii).  pos: n x 3 floats (x, y, z), radius: n bounding radii.  owner_out[n]; ghost lists as CSR over ranks
+// (ghost_off[world + 1], ghost_ids up to ghost_cap entries, ascending per rank).  Returns NB_ERR_CAPACITY if ghost_cap is too small
+// (ghost_off[world] then holds the required size).  Pure host code, deterministic: every rank computes the same partition.
+int nb_shard_partition(const float* pos, const float* radius, uint32_t n, uint32_t gx, uint32_t gz, float margin,
+					   uint32_t* owner_out, uint32_t* ghost_off, uint32_t* ghost_ids, uint32_t ghost_cap) {
+	if (!gx || !gz || !pos || !radius || !owner_out || !ghost_off) return NB_ERR_ARGUMENT;
+	const u32 world = gx * gz;
+	std::vector<u32> idx(n);
+	for (u32 i = 0; i < n; ++i) idx[i] = i;
+	std::stable_sort(idx.begin(), idx.end(), [&](u32 a, u32 b) { return pos[3 * a] < pos[3 * b]; });
+	std::vector<float> xlo(gx), xhi(gx), zlo(world), zhi(world);
+	float rmax = 0.0f;
+	for (u32 i = 0; i < n; ++i) rmax = std::max(rmax, radius[i]);
+	const float inf = INFINITY;
+	for (u32 cx = 0; cx < gx; ++cx) {
+		const size_t b0 = (size_t)n * cx / gx, b1 = (size_t)n * (cx + 1) / gx;
+		xlo[cx] = cx == 0 ? -inf : 0.5f * (pos[3 * idx[b0 - 1]] + pos[3 * idx[b0]]);
+		if (cx) xhi[cx - 1] = xlo[cx];
+		std::vector<u32> col(idx.begin() + b0, idx.begin() + b1);
+		std::stable_sort(col.begin(), col.end(), [&](u32 a, u32 b) { return pos[3 * a + 2] < pos[3 * b + 2]; });
+		const size_t m = col.size();
+		for (u32 cz = 0; cz < gz; ++cz) {
+			const size_t c0 = m * cz / gz, c1 = m * (cz + 1) / gz;
+			const u32 r = cx * gz + cz;
+			zlo[r] = cz == 0 ? -inf : 0.5f * (pos[3 * col[c0 - 1] + 2] + pos[3 * col[c0] + 2]);
+			if (cz) zhi[r - 1] = zlo[r];
+			if (cz == gz - 1) zhi[r] = inf;
+			for (size_t k = c0; k < c1; ++k) owner_out[col[k]] = r;
+		}
+	}
+	xhi[gx - 1] = inf;
+	size_t total = 0;
+	for (u32 r = 0; r < world; ++r) {
+		ghost_off[r] = (u32)total;
+		const u32 cx = r / gz;
+		for (u32 i = 0; i < n; ++i) {
+			if (owner_out[i] == r) continue;
+			const float h = radius[i] + rmax + margin, x = pos[3 * i], z = pos[3 * i + 2];
+			if (x >= xlo[cx] - h && x < xhi[cx] + h && z >= zlo[r] - h && z < zhi[r] + h) {
+				if (ghost_ids && total < ghost_cap) ghost_ids[total] = i;
+				++total;
+			}
+		}
+	}
+	ghost_off[world] = (u32)total;
+	return (ghost_ids && total <= ghost_cap) ? NB_OK : NB_ERR_CAPACITY;
+}
+
+}  // extern "C"

@@ -777,159 +777,6 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve(Rows R, const float4* imp
 	}
 }
 
-// ---------------- cross-GPU dataflow exchange (opt-in: nb_exchange_*) ----------------
-// One scene sharded over several GPUs (nudge_b200/shard.py): a body owned by one rank is a GHOST on its neighbours, and after the
-// warm start and after every sweep the ghost's momentum has to become the owner's.  Instead of pack -> all-gather -> unpack
-// between nine solver launches, the hand-over rides on the solver's own dataflow: the thread that applies the LAST contact of
-// an exported body in pass w also stores the row, tagged (epoch, w), into an inbox in each subscriber's memory (peer memory over
-// NVLink, mapped through CUDA IPC); on the subscriber, the FIRST contact of that ghost in pass w+1 waits for the tag exactly as
-// it waits for a body token and starts from the owner's values.  All passes run in one launch per GPU.  One inbox row per
-// (epoch parity, pass, ghost): nothing is ever overwritten before it has been consumed, so the result is the same block-Jacobi
-// coupling as the collective version, deterministically.
-struct Exchange {
-	float4* inbox;               // [2 parities][passes_cap][ghost_cap] rows of 2 x float4 in THIS GPU's memory
-	float4* const* peer_inbox;   // [world] the inbox of every rank (own rank: inbox itself)
-	const u32* exp_off;          // [B + 1] CSR over exp_tgt: the subscribers of an owned body
-	const uint2* exp_tgt;        // (rank, ghost slot on that rank)
-	const u32* ghost_slot;       // [B] inbox slot of a ghost body, NB_NONE for everything else
-	u32 ghost_cap, passes_cap;
-	const u32* epoch;            // bumped once per exchange launch, identically on every rank
-};
-NB_DEV size_t inbox_row(const Exchange& X, u32 ep, u32 pass, u32 slot) { return 2 * ((((size_t)(ep & 1u) * X.passes_cap) + pass) * X.ghost_cap + slot); }
-NB_DEV u32 inbox_tag(u32 ep, u32 pass) { return ep * 64u + pass + 1u; }  // passes <= 63 per launch
-NB_DEV float4 ld128_sys(const float4* p) {
-	float4 v;
-	asm volatile("{\n .reg .b128 q;\n ld.relaxed.sys.global.b128 q, [%4];\n mov.b128 {%0,%1,%2,%3}, q;\n}" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-	return v;
-}
-NB_DEV void st128_sys(float4* p, float4 v) {
-	asm volatile("{\n .reg .b128 q;\n mov.b128 q, {%1,%2,%3,%4};\n st.relaxed.sys.global.b128 [%0], q;\n}" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-NB_DEV void publish_row(const Exchange& X, u32 body, u32 ep, u32 pass, float4 l, float4 w) {
-	const float tag = asf(inbox_tag(ep, pass));
-	l.w = tag; w.w = tag;
-	for (u32 t = X.exp_off[body]; t < X.exp_off[body + 1]; ++t) {
-		const uint2 tg = X.exp_tgt[t];
-		float4* dst = X.peer_inbox[tg.x] + inbox_row(X, ep, pass, tg.y);
-		st128_sys(dst, l); st128_sys(dst + 1, w);
-	}
-}
-
-__global__ void k_exchange_epoch(u32* epoch) { if (blockIdx.x == 0 && threadIdx.x == 0) *epoch += 1; }
-
-// working copy like k_mw_in; exported bodies WITHOUT contacts on this rank never get a "last contact": their (unchanging) row is
-// published for every pass up front
-__global__ void __launch_bounds__(NB_BLOCK) k_mw_in_exchange(u32 B, const nb_body_momentum* momentum, float4* mw, const u32* chain_len, Exchange X, u32 passes) {
-	const u32 ep = *X.epoch;
-	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
-		const float4* p = reinterpret_cast<const float4*>(momentum + i);
-		float4 l = p[0], w = p[1];
-		l.w = 0.0f; w.w = 0.0f;
-		mw[2*i] = l; mw[2*i + 1] = w;
-		if (i && X.exp_off[i + 1] > X.exp_off[i] && chain_len[i] == 0)
-			for (u32 q = 0; q < passes; ++q) publish_row(X, i, ep, q, l, w);
-	}
-}
-
-// like k_mw_out(mode 1); a ghost ends the step with its owner's momentum after the last pass
-__global__ void __launch_bounds__(NB_BLOCK) k_mw_out_exchange(u32 B, nb_body_momentum* momentum, const float4* mw, Exchange X, u32 passes) {
-	const u32 ep = *X.epoch;
-	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
-		float4* p = reinterpret_cast<float4*>(momentum + i);
-		float4 l = mw[2*i], w = mw[2*i + 1];
-		const bool touched = asu(l.w) != 0;
-		const u32 gs = X.ghost_slot[i];
-		if (gs != NB_NONE) {
-			const float4* src = X.inbox + inbox_row(X, ep, passes - 1, gs);
-			const u32 tag = inbox_tag(ep, passes - 1);
-			float4 il, iw;
-			do { il = ld128_sys(src); iw = ld128_sys(src + 1); } while (asu(il.w) != tag || asu(iw.w) != tag);
-			l = il; w = iw;
-		}
-		float4 ol = p[0], ow = p[1];
-		p[0] = make_float4(l.x, l.y, l.z, ol.w);
-		p[1] = make_float4(w.x, w.y, w.z, touched ? 0.0f : ow.w);
-	}
-}
-
-// k_solve(mode 2) with the exchange woven in: pass 0 = warm start, passes 1..sweeps = PGS sweeps
-__global__ void __launch_bounds__(NB_BLOCK, 2) k_solve_exchange(Rows R, const float4* impulses, float4* mw, u32 sweeps, u32 hop_ns, u32* counts, Exchange X) {
-	__shared__ u32 s_rcp[2048];
-	__shared__ u32 s_rsqrt[2048];
-	for (u32 i = threadIdx.x; i < 2048; i += blockDim.x) { s_rcp[i] = g_rcp_lut[i]; s_rsqrt[i] = g_rsqrt_lut[i]; }
-	__syncthreads();
-	const u32 NS = 8 * counts[CNT_BATCHES];
-	const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-	const u32 passes = sweeps + 1;
-	const u32 S = R.stride;
-	const u32 ep = *X.epoch;
-	for (u32 w = 0; w < passes; ++w) {
-		const bool sweep = w > 0;
-		for (u32 s0 = 0; s0 < NS; s0 += nth) {  // uniform trip count for the whole grid
-			u32 slot = s0 + tid;
-			bool pending = false, near = false, ga = false, gb = false, last_a = false, last_b = false;
-			u32 a = 0, b = 0, exp_a = 0, exp_b = 0;
-			const float4* in_a = nullptr; const float4* in_b = nullptr;
-			float rv[ROW_PLANES_TOTAL], st[3];
-			if (slot < NS && R.contact[slot] != NB_NONE) {
-				pending = true;
-				a = R.a[slot]; b = R.b[slot];
-				uint2 wa = R.wait[slot], wb = R.wait[S + slot];
-				exp_a = w * wa.y + wa.x; exp_b = w * wb.y + wb.x;
-				last_a = a && wa.x + 1 == wa.y && X.exp_off[a + 1] > X.exp_off[a];
-				last_b = b && wb.x + 1 == wb.y && X.exp_off[b + 1] > X.exp_off[b];
-				if (sweep) {
-					// the first contact of a ghost in this pass starts from what its owner published at the end of the previous pass
-					u32 sa = a ? X.ghost_slot[a] : NB_NONE, sb = b ? X.ghost_slot[b] : NB_NONE;
-					ga = sa != NB_NONE && wa.x == 0; gb = sb != NB_NONE && wb.x == 0;
-					if (ga) in_a = X.inbox + inbox_row(X, ep, w - 1, sa);
-					if (gb) in_b = X.inbox + inbox_row(X, ep, w - 1, sb);
-					const float* c = R.plane + slot;
-					#pragma unroll
-					for (int k = 0; k < ROW_PLANES_TOTAL; ++k) rv[k] = c[(size_t)k * S];
-					st[0] = R.state[0*S + slot]; st[1] = R.state[1*S + slot]; st[2] = R.state[2*S + slot];
-				}
-			}
-			const u32 tag_in = inbox_tag(ep, w - 1);  // only used when sweep
-			while (__any_sync(0xffffffffu, pending)) {
-				u32 want = 0xffffffffu;
-				if (pending) {
-					float4 al = ld128(mw + 2*a), bl = ld128(mw + 2*b), aw, bw;
-					if (near) { aw = ld128(mw + 2*a + 1); bw = ld128(mw + 2*b + 1); }
-					u32 ra = a ? exp_a - asu(al.w) : 0, rb = b ? exp_b - asu(bl.w) : 0;
-					u32 r = max(ra, rb);
-					bool ready = r == 0 && near && (!a || asu(aw.w) == exp_a) && (!b || asu(bw.w) == exp_b);
-					if (ready && ga) {
-						float4 il = ld128_sys(in_a), iw = ld128_sys(in_a + 1);
-						if (asu(il.w) == tag_in && asu(iw.w) == tag_in) { al.x = il.x; al.y = il.y; al.z = il.z; aw.x = iw.x; aw.y = iw.y; aw.z = iw.z; }
-						else ready = false;
-					}
-					if (ready && gb) {
-						float4 il = ld128_sys(in_b), iw = ld128_sys(in_b + 1);
-						if (asu(il.w) == tag_in && asu(iw.w) == tag_in) { bl.x = il.x; bl.y = il.y; bl.z = il.z; bw.x = iw.x; bw.y = iw.y; bw.z = iw.z; }
-						else ready = false;
-					}
-					if (ready) {
-						if (sweep) solve_contact(R, slot, rv, st, al, aw, bl, bw, LutMath{ s_rcp, s_rsqrt });
-						else warm_start_contact(R, slot, impulses, al, aw, bl, bw, LutMath{ s_rcp, s_rsqrt });
-						if (a) { float tk = asf(exp_a + 1); al.w = tk; aw.w = tk; st128(mw + 2*a, al); st128(mw + 2*a + 1, aw); }
-						if (b) { float tk = asf(exp_b + 1); bl.w = tk; bw.w = tk; st128(mw + 2*b, bl); st128(mw + 2*b + 1, bw); }
-						if (last_a) publish_row(X, a, ep, w, al, aw);  // this body is done for pass w: hand it to its subscribers
-						if (last_b) publish_row(X, b, ep, w, bl, bw);
-						pending = false;
-					}
-					else {
-						near = r <= 1;
-						want = r >= 2 ? (r - 1) * hop_ns : 0;
-					}
-				}
-				want = __reduce_min_sync(0xffffffffu, want);
-				if (want != 0xffffffffu && want) __nanosleep(min(want, 20000u));
-			}
-		}
-	}
-}
-
 // ---------------- update_cached_impulses (nudge.cpp:4857-4884) ----------------
 __global__ void __launch_bounds__(NB_BLOCK) k_update_impulses(Rows R, float4* impulses, const u32* counts) {
 	u32 n = 8 * counts[CNT_BATCHES];

@@ -1,44 +1,64 @@
-"""A scene sharded across GPUs: slab decomposition along x, ghost bodies, one all-gather per solver sweep.
+"""Python harness over the C++ multi-GPU host (include/nudge_b200.h nb_shard_*, nudge_b200/csrc/nb_shard*.cuh): one scene sharded
+across GPUs.  Used by tests and bench.py; everything that runs per step on the device path is in the library.
 
-Every rank runs the complete, exact-order pipeline (collide ... advance) on its OWNED bodies plus GHOST copies of the
-neighbours' bodies that lie within `halo` of its slab.  A contact between bodies of two ranks exists on both ranks; each
-rank applies its impulses to both bodies, and after the warm start and after every sweep the ghost rows are overwritten
-with their owners' BodyMomentum rows:  pack (nb_pack_momentum) -> ONE all-gather -> scatter (nb_unpack_momentum).
-Within a rank the Gauss-Seidel order is exactly the reference's; across ranks the coupling is block-Jacobi, so results for
-world_size > 1 differ from the single-GPU trajectory (they agree bit-for-bit for world_size == 1, and a rank's result is a
-deterministic function of the partition, which is what the tests pin).  Ghosts are integrated locally with their owner's
-momentum, so no transform exchange is needed inside a partition epoch; `reshard()` re-partitions from the gathered global
-state (bodies that drift further than the halo margin must not happen between two reshards).
+Every rank runs the complete exact-order pipeline (collide ... advance) on its OWNED bodies plus GHOST copies of the neighbours'
+bodies near its cell.  A contact between bodies of two ranks exists on both; each rank applies its impulses to both bodies, and
+after the warm start and after every sweep the ghost rows are overwritten with their owners' BodyMomentum rows
+(nb_shard_exchange: one ncclAllGather, or the library's own peer-memory push/pull kernels).  Within a rank the Gauss-Seidel order is
+exactly the reference's; across ranks the coupling is block-Jacobi, so world_size > 1 is not bit-identical to the single-GPU
+trajectory (world_size 1 is; a rank's result is a deterministic function of the partition; tests/ pin both and bound the physical
+difference).  Ghosts are integrated locally with their owner's momentum, so no transform exchange is needed inside a partition
+epoch; `reshard()` re-partitions from the gathered global state.
 
-The partition logic is pure numpy and the exchange goes through torch.distributed (NCCL on device buffers, or gloo on host
-buffers for the CPU tests), so the host logic is testable without a GPU."""
+Partition (nb_shard_partition, C++ host code): gx x gz cells of equal body count in the (x, z) plane; body i is a ghost of every
+other cell within radius_i + max_radius + margin of its centre.  Transports: "nccl" / "peer" (device, through the C ABI) and "host"
+(numpy + torch.distributed on host buffers: the CPU tests over gloo, and bench.py's parity check of the device transports)."""
 import numpy as np
 from . import scenes as S
 
 
-def slab_boundaries(x, world):
-    """Equal-count slabs along x: world+1 boundaries, -inf / +inf at the ends."""
-    qs = np.quantile(np.asarray(x, np.float64), np.linspace(0, 1, world + 1)[1:-1]) if world > 1 else np.zeros(0)
-    return np.concatenate([[-np.inf], qs, [np.inf]])
+def body_radius(g):
+    """Bounding radius of every body about its origin (max over its colliders; box: |half extents|, sphere: radius, plus the collider offset)."""
+    r = np.zeros(g.n_bodies, np.float32)
+    if g.n_boxes:
+        rb = np.linalg.norm(g.box_data["size"], axis=1) + np.linalg.norm(g.box_transforms["position"], axis=1)
+        np.maximum.at(r, g.box_transforms["body"].astype(np.int64), rb.astype(np.float32))
+    if g.n_spheres:
+        rs = g.sphere_data["radius"] + np.linalg.norm(g.sphere_transforms["position"], axis=1)
+        np.maximum.at(r, g.sphere_transforms["body"].astype(np.int64), rs.astype(np.float32))
+    return r
 
 
-def partition(x, world, halo):
-    """x: positions of the dynamic bodies 1..N (index 0 = body 1).  Returns per rank (owned, ghosts, export) as arrays of global body ids.
-    export[r] = owned bodies of r that some other rank holds as ghosts, in ascending id order: the rows r contributes to the all-gather."""
-    x = np.asarray(x, np.float64)
-    b = slab_boundaries(x, world)
-    owner = np.clip(np.searchsorted(b, x, side="right") - 1, 0, world - 1)
-    ids = np.arange(1, len(x) + 1, dtype=np.int64)
-    owned, ghosts = [], []
-    for r in range(world):
-        mine = owner == r
-        near = (~mine) & (x >= b[r] - halo) & (x < b[r + 1] + halo)
-        owned.append(ids[mine]); ghosts.append(ids[near])
-    exported = np.zeros(len(x) + 1, bool)
+def choose_grid(pos, world):
+    """gx x gz = world minimising the total cut length for this scene's footprint (a thin wall gets world x 1, a square pile 4 x 2 ...)."""
+    ex = float(pos[:, 0].max() - pos[:, 0].min()) + 1e-6; ez = float(pos[:, 2].max() - pos[:, 2].min()) + 1e-6
+    best = None
+    for gx in range(1, world + 1):
+        if world % gx:
+            continue
+        gz = world // gx
+        cost = (gx - 1) * ez + (gz - 1) * ex
+        if best is None or cost < best[0]:
+            best = (cost, gx, gz)
+    return best[1], best[2]
+
+
+def partition(g, world, margin=0.5, grid=None):
+    """Owned / ghost / export lists (global body ids, ascending) of every rank for scene `g` (body 0 = static world, on every rank)."""
+    from . import shard_partition
+    pos = g.transforms["position"][1:].astype(np.float32)
+    rad = body_radius(g)[1:]
+    gx, gz = grid if grid is not None else choose_grid(pos, world)
+    assert gx * gz == world
+    owner, ghost_idx = shard_partition(pos, rad, gx, gz, margin)
+    ids = np.arange(1, g.n_bodies, dtype=np.int64)
+    owned = [ids[owner == r] for r in range(world)]
+    ghosts = [ghost_idx[r].astype(np.int64) + 1 for r in range(world)]
+    exported = np.zeros(g.n_bodies, bool)
     for r in range(world):
         exported[ghosts[r]] = True
     export = [owned[r][exported[owned[r]]] for r in range(world)]
-    return dict(boundaries=b, owner=owner, owned=owned, ghosts=ghosts, export=export)
+    return dict(grid=(gx, gz), owner=owner.astype(np.int64), owned=owned, ghosts=ghosts, export=export)
 
 
 def local_scene(g, owned, ghosts):
@@ -62,168 +82,131 @@ def local_scene(g, owned, ghosts):
     return s, gids
 
 
-def dataflow_plan(part, rank):
-    """Plan of the experimental peer-memory exchange (include/nudge_b200.h, nb_exchange_*) for one rank, from the partition every
-    rank computes identically.  Local body order is [world, owned..., ghosts...]; ghost j of a rank uses inbox slot j on that rank.
-    Returns exp_off (CSR over local bodies), exp_rank, exp_slot (the subscribers of each owned body) and ghost_slot per local body."""
+def exchange_plan(part, rank, n_bodies):
+    """The arrays nb_shard_plan takes for `rank` (local body order: [world body, owned..., ghosts...]; ghost j uses inbox slot j)."""
     world = len(part["owned"])
-    owned, ghosts = part["owned"][rank], part["ghosts"][rank]
-    n_local = 1 + len(owned) + len(ghosts)
-    local_of = {int(g): 1 + k for k, g in enumerate(owned)}
-    targets = [[] for _ in range(n_local)]
+    exp, ghosts, owned = part["export"], part["ghosts"], part["owned"]
+    max_export = max(1, max(len(e) for e in exp))
+    pos_in_export = np.zeros(n_bodies, np.int64)
+    for r in range(world):
+        pos_in_export[exp[r]] = np.arange(len(exp[r]))
+    owner_of = np.zeros(n_bodies, np.int64); owner_of[1:] = part["owner"]
+    lid = np.zeros(n_bodies, np.int64)
+    n_owned = len(owned[rank])
+    lid[owned[rank]] = 1 + np.arange(n_owned)
+    export_local = lid[exp[rank]].astype(np.uint32)
+    ghost_local = (1 + n_owned + np.arange(len(ghosts[rank]))).astype(np.uint32)
+    ghost_src = (owner_of[ghosts[rank]] * max_export + pos_in_export[ghosts[rank]]).astype(np.uint32)
+    rows, ranks, slots = [], [], []
     for p in range(world):
         if p == rank:
             continue
-        for j, g in enumerate(part["ghosts"][p]):
-            k = local_of.get(int(g))
-            if k is not None:               # I own this body: rank p wants it in its inbox slot j
-                targets[k].append((p, j))
-    exp_off = np.zeros(n_local + 1, np.uint32)
-    exp_off[1:] = np.cumsum([len(t) for t in targets])
-    flat = [t for ts in targets for t in ts]
-    exp_rank = np.array([t[0] for t in flat], np.uint32); exp_slot = np.array([t[1] for t in flat], np.uint32)
-    ghost_slot = np.full(n_local, 0xffffffff, np.uint32)
-    ghost_slot[1 + len(owned):] = np.arange(len(ghosts), dtype=np.uint32)
-    return dict(exp_off=exp_off, exp_rank=exp_rank, exp_slot=exp_slot, ghost_slot=ghost_slot)
+        mine = owner_of[ghosts[p]] == rank
+        rows.append(pos_in_export[ghosts[p][mine]]); ranks.append(np.full(int(mine.sum()), p, np.int64)); slots.append(np.nonzero(mine)[0])
+    rows = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+    ranks = np.concatenate(ranks) if ranks else np.zeros(0, np.int64); slots = np.concatenate(slots) if slots else np.zeros(0, np.int64)
+    order = np.lexsort((ranks, rows))
+    sub_off = np.zeros(len(export_local) + 1, np.uint32)
+    sub_off[1:] = np.cumsum(np.bincount(rows, minlength=len(export_local)))
+    return dict(export_local=export_local, sub_off=sub_off, sub_rank=ranks[order].astype(np.uint32), sub_slot=slots[order].astype(np.uint32),
+                ghost_local=ghost_local, ghost_src=ghost_src, max_export=max_export)
 
 
 class ShardedSim:
-    """One rank of a sharded simulation.  `make_sim(scene, max_bodies)` builds the per-rank simulator (nudge_b200.Sim on the GPU box;
-    the CPU oracle in the gloo tests); `comm` is a torch.distributed process group wrapper or None for world_size 1."""
+    """One rank of a sharded simulation.  `make_sim(scene, max_bodies)` builds the per-rank simulator (nudge_b200.Sim on the GPU box; the
+    CPU oracle in the gloo tests).  transport: "nccl" | "peer" (the C++ host, device resident) or "host" (numpy exchange through
+    torch.distributed `group`, any simulator)."""
 
-    def __init__(self, global_scene, rank, world, make_sim, halo=8.0, device_exchange=False, dataflow=False):
+    def __init__(self, global_scene, rank, world, make_sim, margin=0.5, transport="host", group=None, grid=None, capacity_factor=1.6, nccl=True):
         self.g = global_scene.copy()
-        self.dataflow = bool(dataflow) and world > 1   # experimental: ghosts fed through peer-memory inboxes by the solver itself
-        self.dataflow_ready = False
-        self.rank, self.world, self.halo = rank, world, float(halo)
+        self.rank, self.world, self.margin, self.grid = rank, world, float(margin), grid
         self.make_sim = make_sim
-        self.device_exchange = device_exchange
+        self.transport = transport
+        self.group = group
+        self.capacity_factor = capacity_factor
+        self.nccl = nccl                       # False: create the C++ shard without an NCCL communicator (peer transport only)
         self.sim = None
+        self.shard_ready = False
         self.exchange_rows = 0
         self._partition()
 
-    # ---- partition bookkeeping (pure numpy) ----
+    # ---- partition bookkeeping ----
     def _partition(self):
         g = self.g
-        x = g.transforms["position"][1:, 0]
-        self.part = partition(x, self.world, self.halo)
+        self.part = partition(g, self.world, self.margin, self.grid)
         owned, ghosts = self.part["owned"][self.rank], self.part["ghosts"][self.rank]
         scene, self.gids = local_scene(g, owned, ghosts)
         self.n_owned = len(owned)
-        cap_bodies = int(1.5 * (len(x) / self.world + 2 * 4096) + 64)
         if self.sim is None:
-            self.sim = self.make_sim(scene, max(cap_bodies, scene.n_bodies))
+            biggest = max(len(self.part["owned"][r]) + len(self.part["ghosts"][r]) for r in range(self.world))
+            self.cap_bodies = int(self.capacity_factor * biggest) + 1024
+            self.sim = self.make_sim(scene, max(self.cap_bodies, scene.n_bodies))
         else:
             self.sim.reload(scene)
-        # exchange plan: where my export rows live locally, and for every ghost (owner rank, row in that rank's export list)
-        exp = self.part["export"]
-        self.max_export = max(1, max(len(e) for e in exp))
-        lid = np.zeros(g.n_bodies, np.int64); lid[self.gids] = np.arange(len(self.gids))
-        self.export_local = lid[exp[self.rank]].astype(np.uint32)
-        pos_in_export = np.zeros(g.n_bodies, np.int64)
-        for r in range(self.world):
-            pos_in_export[exp[r]] = np.arange(len(exp[r]))
-        owner_of = np.zeros(g.n_bodies, np.int64); owner_of[1:] = self.part["owner"]
-        self.ghost_local = (1 + self.n_owned + np.arange(len(ghosts))).astype(np.uint32)
-        self.ghost_source = (owner_of[ghosts] * self.max_export + pos_in_export[ghosts]).astype(np.uint32)
-        self.exchange_rows = len(exp[self.rank])
-        self._setup_buffers()
-        if self.dataflow:
-            self._setup_dataflow()
+        self.plan = exchange_plan(self.part, self.rank, g.n_bodies)
+        self.max_export = self.plan["max_export"]
+        self.export_local, self.ghost_local, self.ghost_source = self.plan["export_local"], self.plan["ghost_local"], self.plan["ghost_src"]
+        self.exchange_rows = len(self.export_local)
+        if self.transport in ("nccl", "peer", "device") and self.world > 1:
+            self._setup_device()
+        self._host_buffers = None
 
-    def _setup_dataflow(self):
+    def _setup_device(self):
+        """Creates the C++ shard once (NCCL communicator + peer inboxes) and uploads the plan of the current partition."""
         import torch.distributed as dist
+        import nudge_b200
         sim = self.sim
-        if not self.dataflow_ready:   # one inbox per rank for the lifetime of the simulator; handles swapped once
-            cap = int(self.sim.cfg_max_bodies) if hasattr(self.sim, "cfg_max_bodies") else int(1.5 * (self.g.n_bodies / self.world + 2 * 4096) + 64)
-            handle = sim.exchange_create(self.rank, self.world, cap, int(self.g.iterations) + 1)
+        if not self.shard_ready:
+            ids = [nudge_b200.nccl_unique_id() if (self.rank == 0 and self.nccl) else None]
+            if self.nccl:
+                dist.broadcast_object_list(ids, src=0, group=self.group)
+            sim.shard_create(self.rank, self.world, ids[0], self.cap_bodies, self.cap_bodies)
             handles = [None] * self.world
-            dist.all_gather_object(handles, handle)
+            dist.all_gather_object(handles, sim.shard_ipc_handle(), group=self.group)
             for p in range(self.world):
-                sim.exchange_open(p, handles[p])
-            self.dataflow_ready = True
-        plan = dataflow_plan(self.part, self.rank)
-        sim.exchange_plan(plan["exp_off"], plan["exp_rank"], plan["exp_slot"], plan["ghost_slot"])
+                if p != self.rank:
+                    sim.shard_open_peer(p, handles[p])
+            self.shard_ready = True
+        p = self.plan
+        sim.shard_plan(p["export_local"], p["sub_off"], p["sub_rank"], p["sub_slot"], p["ghost_local"], p["ghost_src"], p["max_export"])
 
-    def _setup_buffers(self):
-        import torch
-        dev = "cuda" if self.device_exchange else "cpu"
-        self.t_export = torch.zeros((self.max_export, 8), dtype=torch.float32, device=dev)
-        self.t_gather = torch.zeros((self.world * self.max_export, 8), dtype=torch.float32, device=dev)
-        if self.device_exchange:
-            self.t_export_idx = torch.from_numpy(self.export_local.astype(np.int32)).to(dev)
-            self.t_ghost_idx = torch.from_numpy(self.ghost_local.astype(np.int32)).to(dev)
-            self.t_ghost_src = torch.from_numpy(self.ghost_source.astype(np.int32)).to(dev)
-
-    # ---- ghost exchange: pack -> ONE all-gather -> unpack ----
-    def exchange(self):
+    # ---- ghost exchange ----
+    def exchange(self, transport=None):
         if self.world == 1:
             return
-        import torch.distributed as dist
+        t = transport or self.transport
+        if t in ("nccl", "peer"):
+            self.sim.shard_exchange(t)
+            return
+        import torch, torch.distributed as dist   # host path: same plan, numpy gathers
         sim = self.sim
-        if self.device_exchange:
-            sim.pack_momentum(self.t_export_idx.data_ptr(), len(self.export_local), self.t_export.data_ptr())
-            dist.all_gather_into_tensor(self.t_gather, self.t_export)
-            sim.unpack_momentum(self.t_ghost_idx.data_ptr(), self.t_ghost_src.data_ptr(), len(self.ghost_local), self.t_gather.data_ptr())
-        else:  # host path (gloo): same plan, numpy gathers
-            sim.download_bodies()
-            rows = sim.momentum.view(np.float32).reshape(-1, 8)
-            self.t_export.numpy()[:len(self.export_local)] = rows[self.export_local.astype(np.int64)]
-            parts = [self.t_gather[r * self.max_export:(r + 1) * self.max_export] for r in range(self.world)]
-            dist.all_gather(parts, self.t_export)
-            rows[self.ghost_local.astype(np.int64)] = self.t_gather.numpy()[self.ghost_source.astype(np.int64)]
-            sim.upload_bodies()
+        if self._host_buffers is None:
+            self._host_buffers = (torch.zeros((self.max_export, 8), dtype=torch.float32), torch.zeros((self.world * self.max_export, 8), dtype=torch.float32))
+        t_export, t_gather = self._host_buffers
+        sim.download_bodies()
+        rows = sim.momentum.view(np.float32).reshape(-1, 8)
+        t_export.numpy()[:len(self.export_local)] = rows[self.export_local.astype(np.int64)]
+        parts = [t_gather[r * self.max_export:(r + 1) * self.max_export] for r in range(self.world)]
+        dist.all_gather(parts, t_export, group=self.group)
+        rows[self.ghost_local.astype(np.int64)] = t_gather.numpy()[self.ghost_source.astype(np.int64)]
+        sim.upload_bodies()
 
     # ---- one simulation step (example/main.cpp:274-328) with the exchanges ----
-    def step(self):
-        if getattr(self, "graph", None) is not None:
-            self.graph.replay()
-            self.replayed_launches = getattr(self, "replayed_launches", 0) + self.graph_launches
+    def step(self, transport=None):
+        t = transport or self.transport
+        if self.world > 1 and t in ("nccl", "peer"):
+            self.sim.shard_step(t)          # the whole sharded sub-step inside the library (CUDA graph replay on a capturable stream)
             return
-        self._step_launches()
-
-    def launch_count(self):
-        """Kernels the library launched for this rank, including the ones replayed from a recorded step."""
-        return self.sim.launch_count() + getattr(self, "replayed_launches", 0)
-
-    def capture(self, torch_stream):
-        """Records one step (the library's launches on `torch_stream` - the stream the Sim was created with - and the NCCL
-        all-gathers) into a CUDA graph; step() replays it until the next reshard().  Returns False (and keeps plain launches) if
-        the capture is refused."""
-        import torch
-        self.graph = None
-        if self.world > 1 and not self.device_exchange:
-            return False
-        try:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            before = self.sim.launch_count()
-            with torch.cuda.graph(g, stream=torch_stream):
-                self._step_launches()
-            torch.cuda.synchronize()
-            self.graph_launches = self.sim.launch_count() - before
-            self.graph = g
-            return True
-        except Exception as e:  # noqa: BLE001 - any capture failure means: stay on plain launches
-            self.graph = None
-            self.capture_error = repr(e)
-            try: torch.cuda.synchronize()
-            except Exception: pass
-            return False
-
-    def _step_launches(self):
         sim = self.sim
-        if self.dataflow:
-            sim.collide(); sim.apply_gravity_damping(); sim.read_cached_impulses(); sim.setup_contact_constraints_deferred()
-            sim.solve_exchange(int(self.g.iterations))   # warm start + all sweeps, ghost hand-over inside the kernel
-            sim.update_cached_impulses(); sim.write_cached_impulses(); sim.advance()
-            return
         sim.collide(); sim.apply_gravity_damping(); sim.read_cached_impulses(); sim.setup_contact_constraints()
-        self.exchange()
+        self.exchange(t)
         for _ in range(int(self.g.iterations)):
             sim.apply_impulses()
-            self.exchange()
+            self.exchange(t)
         sim.update_cached_impulses(); sim.write_cached_impulses(); sim.advance()
+
+    def launch_count(self):
+        return self.sim.launch_count()
 
     # ---- gather the global state on every rank and re-partition ----
     def gather_global(self):
@@ -235,16 +218,15 @@ class ShardedSim:
         if self.world == 1:
             g.transforms[ids] = sim.transforms[own]; g.momentum[ids] = sim.momentum[own]; g.idle[ids] = sim.idle[own]
             return g
-        import torch, torch.distributed as dist
+        import torch.distributed as dist
         payload = (ids.copy(), sim.transforms[own].copy(), sim.momentum[own].copy(), sim.idle[own].copy())
         out = [None] * self.world
-        dist.all_gather_object(out, payload)
+        dist.all_gather_object(out, payload, group=self.group)
         for (i, t, m, c) in out:
             g.transforms[i] = t; g.momentum[i] = m; g.idle[i] = c
         return g
 
     def reshard(self):
-        self.graph = None  # the partition (sizes, export plan) changes: a recorded step is stale
         self.gather_global()
         self._partition()
 

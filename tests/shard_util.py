@@ -39,14 +39,20 @@ def free_port():
     return p
 
 
-def _worker(rank, world, port, kind, steps, reshard_every, out_dir, n_boxes):
+def _worker(rank, world, port, kind, steps, reshard_every, out_dir, n_boxes, init=None):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
     from nudge_b200 import scenes, shard
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = scenes.box_drop(n_boxes, iterations=4, seed=5, spacing=(2.4, 2.2, 2.4))
-    sim = shard.ShardedSim(g, rank, world, make_oracle_sim if kind == "oracle" else make_gpu_sim, halo=6.0, dataflow=(kind == "gpu_dataflow"))
+    if init is not None:            # start from a given state (transforms / momentum / idle of the global scene)
+        st = np.load(init)
+        g.transforms[:] = st["transforms"]; g.momentum[:] = st["momentum"]; g.idle[:] = st["idle"]
+    if kind == "gpu_peer":          # the library's own push/pull kernels over CUDA-IPC peer memory (both ranks may share one GPU in the tests)
+        sim = shard.ShardedSim(g, rank, world, make_gpu_sim, margin=0.5, transport="peer", nccl=False)
+    else:
+        sim = shard.ShardedSim(g, rank, world, make_oracle_sim if kind == "oracle" else make_gpu_sim, margin=0.5, transport="host")
     log = []
     for k in range(steps):
         if reshard_every and k and k % reshard_every == 0:
@@ -61,9 +67,9 @@ def _worker(rank, world, port, kind, steps, reshard_every, out_dir, n_boxes):
     dist.destroy_process_group()
 
 
-def run_ranks(world, kind, steps=12, reshard_every=5, n_boxes=600):
+def run_ranks(world, kind, steps=12, reshard_every=5, n_boxes=600, init=None):
     import torch.multiprocessing as mp
     out_dir = tempfile.mkdtemp(prefix="nb_shard_")
     port = free_port()
-    mp.spawn(_worker, args=(world, port, kind, steps, reshard_every, out_dir, n_boxes), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, kind, steps, reshard_every, out_dir, n_boxes, init), nprocs=world, join=True)
     return [np.load(os.path.join(out_dir, "%s_rank%d.npz" % (kind, r))) for r in range(world)]

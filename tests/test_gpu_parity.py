@@ -233,17 +233,17 @@ def test_sharded_scene_two_ranks_gpu_equals_oracle_ranks():
         assert np.array_equal(a[r]["counts"], b[r]["counts"])
 
 
-@pytest.mark.skipif(os.environ.get("NB_TEST_DATAFLOW") != "1", reason="experimental peer-memory exchange: opt-in until validated on hardware (NB_TEST_DATAFLOW=1)")
-def test_sharded_dataflow_exchange_equals_collective_exchange():
-    """The ghost hand-over carried by the solver's dataflow (nb_exchange_*, inboxes in peer memory) is the same block-Jacobi coupling as
-    the per-sweep collective: identical transforms and velocities on every rank.  (Two ranks on ONE GPU time-slice each other while
-    they wait on each other's kernels, so this is slow there; it is meant for a multi-GPU box.)"""
+def test_sharded_peer_memory_exchange_equals_host_exchange():
+    """The C++ host's peer transport (nb_shard_step: k_shard_push / k_shard_pull over CUDA-IPC mapped inboxes, the arrival-flag protocol,
+    the exchange plan) against the host-side exchange of the same partition: identical transforms and velocities on every rank.
+    Two processes share cuda:0 here (they time-slice while waiting for each other); bench.py repeats the check on real multi-GPU boxes."""
     from tests import shard_util
-    a = shard_util.run_ranks(2, "gpu_dataflow", steps=6, reshard_every=4, n_boxes=400)
-    b = shard_util.run_ranks(2, "gpu", steps=6, reshard_every=4, n_boxes=400)
+    a = shard_util.run_ranks(2, "gpu_peer", steps=8, reshard_every=4, n_boxes=500)
+    b = shard_util.run_ranks(2, "gpu", steps=8, reshard_every=4, n_boxes=500)
     for r in range(2):
         assert np.array_equal(a[r]["transforms"].view(np.uint8), b[r]["transforms"].view(np.uint8))
         assert np.array_equal(a[r]["momentum"]["velocity"], b[r]["momentum"]["velocity"])
+        assert np.array_equal(a[r]["counts"], b[r]["counts"])
 
 
 def test_body_connections_join_islands():

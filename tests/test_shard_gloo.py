@@ -5,37 +5,103 @@ from nudge_b200 import scenes, shard
 from tests import shard_util
 
 
+def _numpy_partition(pos, rad, gx, gz, margin):
+    """The rule nb_shard_partition implements (nudge_b200/csrc/nb_shard_api.cuh), restated in numpy."""
+    n = len(rad)
+    world = gx * gz
+    owner = np.zeros(n, np.int64)
+    order = np.argsort(pos[:, 0], kind="stable")
+    xlo, xhi = np.full(gx, -np.inf), np.full(gx, np.inf); zlo, zhi = np.full(world, -np.inf), np.full(world, np.inf)
+    f = np.float32
+    for cx in range(gx):
+        b0, b1 = n * cx // gx, n * (cx + 1) // gx
+        if cx:
+            xlo[cx] = f(0.5) * (pos[order[b0 - 1], 0] + pos[order[b0], 0]); xhi[cx - 1] = xlo[cx]
+        col = order[b0:b1]
+        col = col[np.argsort(pos[col, 2], kind="stable")]
+        m = len(col)
+        for cz in range(gz):
+            c0, c1 = m * cz // gz, m * (cz + 1) // gz
+            r = cx * gz + cz
+            if cz:
+                zlo[r] = f(0.5) * (pos[col[c0 - 1], 2] + pos[col[c0], 2]); zhi[r - 1] = zlo[r]
+            owner[col[c0:c1]] = r
+    rmax = rad.max()
+    ghosts = []
+    for r in range(world):
+        cx = r // gz
+        h = rad + rmax + f(margin)
+        x, z = pos[:, 0], pos[:, 2]
+        near = (owner != r) & (x >= f(xlo[cx]) - h) & (x < f(xhi[cx]) + h) & (z >= f(zlo[r]) - h) & (z < f(zhi[r]) + h)
+        ghosts.append(np.nonzero(near)[0])
+    return owner, ghosts
+
+
 def test_partition_covers_every_body_once_and_plans_the_exchange():
+    import nudge_b200
     g = scenes.box_drop(5000, iterations=4, seed=3)
-    x = g.transforms["position"][1:, 0]
-    for world in (1, 2, 4, 8):
-        p = shard.partition(x, world, halo=5.0)
+    pos = g.transforms["position"][1:].astype(np.float32); rad = shard.body_radius(g)[1:]
+    n = len(rad)
+    for world, grid in ((1, None), (2, None), (4, None), (8, None), (8, (8, 1)), (6, (2, 3))):
+        p = shard.partition(g, world, margin=0.5, grid=grid)
+        gx, gz = p["grid"]
+        assert gx * gz == world
         owned = np.concatenate(p["owned"])
-        assert np.array_equal(np.sort(owned), np.arange(1, len(x) + 1))
+        assert np.array_equal(np.sort(owned), np.arange(1, n + 1))
         sizes = [len(o) for o in p["owned"]]
-        assert max(sizes) - min(sizes) <= 2
-        b = p["boundaries"]
+        assert max(sizes) - min(sizes) <= gz + 1
+        # the C++ rule equals its numpy restatement
+        o2, g2 = _numpy_partition(pos, rad, gx, gz, 0.5)
+        assert np.array_equal(p["owner"], o2)
         for r in range(world):
-            gx = x[p["ghosts"][r] - 1]
-            assert ((gx >= b[r] - 5.0) & (gx < b[r + 1] + 5.0)).all()
+            assert np.array_equal(p["ghosts"][r] - 1, g2[r])
             assert not np.intersect1d(p["ghosts"][r], p["owned"][r]).size
             assert np.isin(p["export"][r], p["owned"][r]).all()
-        # every ghost is exported by its owner
+        # completeness: two bodies of different ranks whose bounding spheres touch are each a ghost on the other's rank
+        if world > 1:
+            rng = np.random.default_rng(0)
+            i = rng.integers(0, n, 20000); j = rng.integers(0, n, 20000)
+            d = np.linalg.norm(pos[i] - pos[j], axis=1)
+            close = (d < rad[i] + rad[j]) & (p["owner"][i] != p["owner"][j])
+            assert close.sum() > 0
+            for a, b in zip(i[close], j[close]):
+                assert (a + 1) in p["ghosts"][p["owner"][b]] and (b + 1) in p["ghosts"][p["owner"][a]]
         allexp = np.concatenate(p["export"]) if world > 1 else np.zeros(0, np.int64)
         for r in range(world):
-            assert np.isin(p["ghosts"][r], allexp).all()
+            assert np.isin(p["ghosts"][r], allexp).all()     # every ghost is exported by its owner
+        # exchange plan: every ghost slot of every rank is fed by exactly one subscriber entry of its owner
+        if world > 1:
+            plans = [shard.exchange_plan(p, r, g.n_bodies) for r in range(world)]
+            fed = [np.zeros(len(p["ghosts"][r]), np.int64) for r in range(world)]
+            for r in range(world):
+                pl = plans[r]
+                assert pl["sub_off"][-1] == len(pl["sub_rank"]) and len(pl["sub_off"]) == len(pl["export_local"]) + 1
+                for k in range(len(pl["export_local"])):
+                    gid = p["export"][r][k]
+                    for t in range(pl["sub_off"][k], pl["sub_off"][k + 1]):
+                        q, slot = int(pl["sub_rank"][t]), int(pl["sub_slot"][t])
+                        assert q != r and p["ghosts"][q][slot] == gid
+                        fed[q][slot] += 1
+                # all-gather view of the same plan
+                assert np.array_equal(pl["ghost_src"] // pl["max_export"], p["owner"][p["ghosts"][r] - 1])
+            for r in range(world):
+                assert np.all(fed[r] == 1)
+    # a thin wall is cut along x only, a square pile in both directions
+    w = scenes.brick_wall(4000, iterations=4)
+    assert shard.choose_grid(w.transforms["position"][1:], 8) == (8, 1)
+    assert shard.choose_grid(pos, 8) in ((4, 2), (2, 4))
 
 
 def test_local_scene_keeps_global_tags_and_static_body():
     g = scenes.box_drop(300, iterations=4, seed=3)
-    p = shard.partition(g.transforms["position"][1:, 0], 2, halo=4.0)
+    p = shard.partition(g, 2, margin=0.5)
     s, gids = shard.local_scene(g, p["owned"][0], p["ghosts"][0])
     assert gids[0] == 0 and s.box_tags[0] == 0 and s.properties["mass_inverse"][0] == 0
     # every collider of a local body is present exactly once, in global collider order, still carrying its global tag
     assert np.array_equal(s.box_tags, np.sort(g.box_tags[gids])) and np.array_equal(gids[s.box_transforms["body"]], g.box_transforms["body"][s.box_tags])
     # mixed scenes: spheres travel with their bodies and keep their (box-count offset) tags
     m = scenes.demo_scene(40, 30, spread=6.0, height=10.0)
-    pm = shard.partition(m.transforms["position"][1:, 0], 2, halo=1.0)
+    pm = shard.partition(m, 2, margin=0.1)
     sm, gm = shard.local_scene(m, pm["owned"][1], pm["ghosts"][1])
     assert sm.n_boxes + sm.n_spheres == len(gm) and sm.n_spheres > 0
     assert np.array_equal(gm[sm.sphere_transforms["body"]], m.sphere_transforms["body"][sm.sphere_tags - m.n_boxes])
@@ -77,28 +143,37 @@ def test_world2_gloo_ranks_agree_and_are_deterministic():
     assert np.isfinite(a[0]["transforms"]["position"]).all() and y.min() > -0.5 and y.max() < 400.0
 
 
-def test_dataflow_plan_is_consistent_across_ranks():
-    """Host logic of the experimental peer-memory exchange: every ghost slot of every rank is fed by exactly one owner."""
-    import numpy as np
-    from nudge_b200 import shard
-    rng = np.random.default_rng(5)
-    x = rng.uniform(-60, 60, 5000)
-    for world in (2, 3, 5):
-        part = shard.partition(x, world, 8.0)
-        plans = [shard.dataflow_plan(part, r) for r in range(world)]
-        fed = [np.zeros(len(part["ghosts"][p]), np.int64) for p in range(world)]
-        for r in range(world):
-            pl = plans[r]
-            n_owned, n_ghost = len(part["owned"][r]), len(part["ghosts"][r])
-            assert len(pl["exp_off"]) == 1 + n_owned + n_ghost + 1 and pl["exp_off"][-1] == len(pl["exp_rank"])
-            assert pl["exp_off"][1] == 0                                  # the static world body is never exported
-            assert np.all(np.diff(pl["exp_off"].astype(np.int64))[1 + n_owned:] == 0)   # ghosts are never exported
-            assert np.array_equal(pl["ghost_slot"][1 + n_owned:], np.arange(n_ghost)) and np.all(pl["ghost_slot"][:1 + n_owned] == 0xffffffff)
-            for k in range(1, 1 + n_owned):
-                gid = part["owned"][r][k - 1]
-                for t in range(pl["exp_off"][k], pl["exp_off"][k + 1]):
-                    p, j = int(pl["exp_rank"][t]), int(pl["exp_slot"][t])
-                    assert p != r and part["ghosts"][p][j] == gid
-                    fed[p][j] += 1
-        for p in range(world):
-            assert np.all(fed[p] == 1)
+def test_two_ranks_stay_close_to_one_rank_physics():
+    """SURVEY.md section 8e parity statement for N > 1: across ranks the Gauss-Seidel coupling becomes block-Jacobi, so 2 ranks are not
+    bit-identical to 1 rank; they must stay within a stated tolerance after one step from identical state and a cold contact cache
+    (positions 5e-3 units — boxes are 1 to 3 units across — and velocities 0.5 units/s with only 4 sweeps; measured 1.4e-3 / 0.17),
+    and keep the invariants over a longer run (resting height, a pile at rest, momentum)."""
+    import os, tempfile
+    from oracle import pyoracle
+    g = scenes.box_drop(600, iterations=4, seed=5, spacing=(2.4, 2.2, 2.4))
+    o = pyoracle.OracleSim(g, contact_capacity=40 * 700)
+    for _ in range(160):
+        o.step()
+    init = os.path.join(tempfile.mkdtemp(prefix="nb_shard_init_"), "state.npz")
+    np.savez(init, transforms=o.transforms, momentum=o.momentum, idle=o.idle)
+
+    def single(steps):
+        s = g.copy(); s.transforms[:] = o.transforms; s.momentum[:] = o.momentum; s.idle[:] = o.idle
+        one = pyoracle.OracleSim(s, contact_capacity=40 * 700)
+        for _ in range(steps):
+            one.step()
+        return one
+
+    one1 = single(1)
+    two1 = shard_util.run_ranks(2, "oracle", steps=1, reshard_every=0, n_boxes=600, init=init)[0]
+    dpos = np.abs(two1["transforms"]["position"][1:] - one1.transforms["position"][1:]).max()
+    dvel = np.abs(two1["momentum"]["velocity"][1:] - one1.momentum["velocity"][1:]).max()
+    assert dpos < 5e-3 and dvel < 0.5, (dpos, dvel)
+    one, two = single(40), shard_util.run_ranks(2, "oracle", steps=40, reshard_every=10, n_boxes=600, init=init)[0]
+    mass = 1.0 / g.properties["mass_inverse"][1:]
+    ke = lambda m: float(0.5 * (mass * (m["velocity"][1:].astype(np.float64) ** 2).sum(1)).sum())
+    y1, y2 = one.transforms["position"][1:, 1], two["transforms"]["position"][1:, 1]
+    assert abs(y1.mean() - y2.mean()) < 0.02 * max(1.0, abs(y1.mean())) and y2.min() > -0.5
+    assert ke(two["momentum"]) < 10.0 * ke(one.momentum) + 5.0
+    px = lambda m: (mass[:, None] * m["velocity"][1:]).sum(0)
+    assert np.abs(px(two["momentum"]) - px(one.momentum)).max() < 0.05 * mass.sum()
