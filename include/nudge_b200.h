@@ -136,6 +136,19 @@ int nb_advance(nb_context*, float time_step, void* stream);
  * are recorded once into a CUDA graph and replayed; NB_GRAPH=0 in the environment keeps plain launches. */
 int nb_step(nb_context*, float time_step, uint32_t iterations, float gravity, float damping, void* stream);
 
+/* CUDA streams for hosts that do not link the CUDA runtime (cgo / JNI / ctypes callers): a created stream is capturable, so nb_step
+ * replays its CUDA graph there; a null stream means the legacy default stream and plain launches. */
+void* nb_stream_create(nb_context*);
+void nb_stream_destroy(nb_context*, void* stream);
+int nb_stream_synchronize(nb_context*, void* stream);
+
+/* State serialisation: the caller-owned PODs of nudge.h:73-129 (BodyData, ColliderData, BodyConnections,
+ * ContactCache, widened layout) as one flat file, from / into the device-resident context.  Checkpoint, and what tools/nb_replay
+ * steps headless; layout in nudge_b200/csrc/nb_state_api.cuh.  All three synchronise. */
+int nb_save_state(nb_context*, const char* path, void* stream);
+int nb_load_state(nb_context*, const char* path, void* stream);
+int nb_state_info(const char* path, uint32_t counts[5] /* bodies, boxes, spheres, connections, cache entries */);
+
 /* Solver mode.  NB_SOLVER_PARITY (default): the reference's exact Gauss-Seidel order (nudge.cpp:4206-4340 schedule, 4640-4855 sweeps),
  * bit-identical impulses.  NB_SOLVER_THROUGHPUT: mass-splitting Jacobi over the same constraint rows (nudge_b200/csrc/nb_jacobi.cuh) -
  * order independent, HBM-streaming, converges to the same contact problem but its impulses after N sweeps differ from the reference's

@@ -19,7 +19,8 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact", "nb_debug_sort", "nb_debug_scan", "nb_debug_enable", "nb_pack_momentum", "nb_unpack_momentum",
            "nb_shard_unique_id", "nb_shard_create", "nb_shard_destroy", "nb_shard_ipc_handle", "nb_shard_open_peer", "nb_shard_plan", "nb_shard_exchange",
            "nb_shard_step", "nb_shard_graph_active", "nb_shard_partition",
-           "nb_set_solver_mode", "nb_get_solver_mode", "nb_debug_timing_enable", "nb_debug_timing"]
+           "nb_set_solver_mode", "nb_get_solver_mode", "nb_debug_timing_enable", "nb_debug_timing",
+           "nb_stream_create", "nb_stream_destroy", "nb_stream_synchronize", "nb_save_state", "nb_load_state", "nb_state_info"]
 
 
 class Config(C.Structure):
@@ -80,6 +81,12 @@ def load_library():
         lib.nb_get_solver_mode.argtypes = [V]
         lib.nb_debug_timing_enable.argtypes = [V, C.c_int]
         lib.nb_debug_timing.argtypes = [V, V, V, V]
+        lib.nb_stream_create.argtypes = [V]; lib.nb_stream_create.restype = V
+        lib.nb_stream_destroy.argtypes = [V, V]; lib.nb_stream_destroy.restype = None
+        lib.nb_stream_synchronize.argtypes = [V, V]
+        lib.nb_save_state.argtypes = [V, C.c_char_p, V]
+        lib.nb_load_state.argtypes = [V, C.c_char_p, V]
+        lib.nb_state_info.argtypes = [C.c_char_p, V]
         _lib = lib
     return _lib
 
@@ -270,6 +277,13 @@ class Sim(abi.HostState):
 
     def launch_count(self):
         return int(self.lib.nb_launch_count(self.ctx))
+
+    # ---- state files (nb_save_state / nb_load_state; tools/nb_replay steps them headless) ----
+    def save_state(self, path):
+        self._ck(self.lib.nb_save_state(self.ctx, os.fsencode(path), self.stream), "nb_save_state")
+
+    def load_state(self, path):
+        self._ck(self.lib.nb_load_state(self.ctx, os.fsencode(path), self.stream), "nb_load_state")
 
     # ---- solver mode (include/nudge_b200.h): "parity" = the reference's exact Gauss-Seidel order, "throughput" = mass-splitting Jacobi ----
     def set_solver_mode(self, mode):

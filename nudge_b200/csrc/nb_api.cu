@@ -688,6 +688,15 @@ int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity
 	return NB_OK;
 }
 
+// ---------------- streams for hosts that do not link the CUDA runtime themselves ----------------
+void* nb_stream_create(nb_context* ctx) {
+	cudaStream_t s = nullptr;
+	if (cudaSetDevice(ctx->cfg.device) != cudaSuccess || cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { ctx->error = "cudaStreamCreate failed"; return nullptr; }
+	return (void*)s;
+}
+void nb_stream_destroy(nb_context* ctx, void* stream) { (void)ctx; if (stream) { cudaStreamSynchronize((cudaStream_t)stream); cudaStreamDestroy((cudaStream_t)stream); } }
+int nb_stream_synchronize(nb_context* ctx, void* stream) { CK(cudaStreamSynchronize((cudaStream_t)stream)); return NB_OK; }
+
 // ---------------- solver mode and kernel timing ----------------
 int nb_set_solver_mode(nb_context* ctx, int mode) {
 	if (mode != NB_SOLVER_PARITY && mode != NB_SOLVER_THROUGHPUT) { ctx->error = "unknown solver mode"; return NB_ERR_ARGUMENT; }
@@ -799,3 +808,4 @@ int nb_debug_rcp(nb_context* ctx, const float* x, float* y, uint32_t n, int rsq)
 }
 
 #include "nb_shard_api.cuh"
+#include "nb_state_api.cuh"

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "nudge_b200.h")).read()
-    return sorted(set(re.findall(r"^(?:int|void|uint64_t|const char\*)\s+(nb_[a-z0-9_]+)\s*\(", text, re.M)))
+    return sorted(set(re.findall(r"^(?:int|void\*?|uint64_t|const char\*)\s+(nb_[a-z0-9_]+)\s*\(", text, re.M)))
 
 
 def test_header_symbols_are_exported():
