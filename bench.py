@@ -436,8 +436,28 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(args)
+        line["dropin_seven_call_steps_per_s"] = dropin_sample()
     emit(line)
     if world > 1: dist.destroy_process_group()
+
+
+def dropin_sample():
+    """Cost of the LITERAL drop-in (libnudge_compat.so: the seven nudge:: calls with HOST pointers, every call uploading what it reads and
+    downloading what it writes): oracle/_ref/headless_gpu, an application loop in the shape of example/main.cpp:274-328 on 1024 boxes + 1024
+    spheres (BASELINE configs[0]), next to the same binary linked with the reference's nudge.cpp.  Not the fast path (nb_step is)."""
+    d = os.path.join(ROOT, "oracle", "_ref")
+    out = {}
+    for name in ("headless_gpu", "headless_ref"):
+        exe = os.path.join(d, name)
+        if not os.path.exists(exe):
+            return None
+        try:
+            r = subprocess.run([exe, "1024", "1024", "400", "8"], capture_output=True, text=True, timeout=300)
+            out[name] = float([l for l in r.stdout.splitlines() if l.startswith("steps_per_s")][0].split()[1])
+        except Exception as e:  # noqa: BLE001
+            out[name] = None; out[name + "_error"] = repr(e)[:200]
+    return {"gpu_dropin": out.get("headless_gpu"), "reference_cpu_1_thread": out.get("headless_ref"),
+            "scene": "1024 boxes + 1024 spheres falling, 400 steps from the drop, 8 iterations, gravity loop on the host between the calls"}
 
 
 def cpu_baseline_sample(args):

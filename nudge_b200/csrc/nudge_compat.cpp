@@ -8,12 +8,18 @@
 // reads and downloads the ones it writes.  That makes this shim a correctness/compatibility layer, not the fast path —
 // the resident C ABI (nb_step) is.  The returned opaque pointers are carved from the caller's Arena like nudge.cpp:4022,
 // 4174 do, and only reference the shim's context.  There is no CPU fallback: without a GPU the first call aborts.
+//
+// The reference is re-entrant on disjoint data (no globals), so the shim keeps ONE device context PER WORLD:
+// a world is identified by the caller's BodyData::transforms array (collide / advance) and, from collide on, by its ContactData::data
+// array (read_cached_impulses); the opaque handles carry their world.  Two worlds can be stepped from two threads.
 #include "../../include/nudge_b200.h"
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <map>
+#include <mutex>
 
 // The interface structs, re-declared with the reference's names and layout (nudge.h:29-129) so that the mangled symbols match.
 namespace nudge {
@@ -35,8 +41,8 @@ namespace nudge {
 	struct CachedContactImpulse { float impulse[3]; float unused; };
 	struct ContactCache { uint64_t* tags; CachedContactImpulse* data; uint32_t capacity; uint32_t count; };
 	struct ActiveBodies { uint16_t* indices; uint32_t capacity; uint32_t count; };
-	struct ContactImpulseData { uint64_t magic; };
-	struct ContactConstraintData { uint64_t magic; };
+	struct ContactImpulseData { uint64_t magic; void* world; };
+	struct ContactConstraintData { uint64_t magic; void* world; };
 
 	void collide(ActiveBodies* active_bodies, ContactData* contacts, BodyData bodies, ColliderData colliders, BodyConnections body_connections, Arena temporary);
 	ContactImpulseData* read_cached_impulses(ContactCache contact_cache, ContactData contacts, Arena* memory);
@@ -55,32 +61,53 @@ struct Shim {
 	std::vector<uint32_t> box_tags, sphere_tags, active32, features;
 	std::vector<nb_body_pair> pairs32, conn32;
 	std::vector<uint64_t> tags64, sleeping64;
+	std::mutex lock;   // one world is still single-threaded, like the reference
 };
-static Shim g;
 
-static void die(const char* what) {
+// worlds by the identity of the caller's arrays
+static std::mutex g_registry_lock;
+static std::map<const void*, Shim*> g_by_bodies, g_by_contacts;
+
+static Shim& world_of_bodies(const void* transforms) {
+	std::lock_guard<std::mutex> l(g_registry_lock);
+	Shim*& s = g_by_bodies[transforms];
+	if (!s) s = new Shim();
+	return *s;
+}
+static void bind_contacts(const void* contact_rows, Shim* s) {
+	std::lock_guard<std::mutex> l(g_registry_lock);
+	g_by_contacts[contact_rows] = s;
+}
+static Shim& world_of_contacts(const void* contact_rows) {
+	std::lock_guard<std::mutex> l(g_registry_lock);
+	auto it = g_by_contacts.find(contact_rows);
+	if (it == g_by_contacts.end() || !it->second) { fprintf(stderr, "nudge_b200 compat: read_cached_impulses on a ContactData that no collide() call has filled\n"); abort(); }
+	return *it->second;
+}
+
+static void die(Shim& g, const char* what) {
 	fprintf(stderr, "nudge_b200 compat: %s: %s\n", what, g.ctx ? nb_last_error(g.ctx) : "no context");
 	abort();  // the reference asserts on its failure paths (nudge.cpp:1000-1039, 3010, 4118); there is no CPU fallback
 }
-#define NBCK(call) do { if ((call) != NB_OK) die(#call); } while (0)
+#define NBCK(call) do { if ((call) != NB_OK) die(g, #call); } while (0)
 
 static uint32_t grow(uint32_t have, uint32_t need, uint32_t floor_) { uint32_t c = have ? have : floor_; while (c < need) c *= 2; return c; }
 
-static void ensure(uint32_t bodies, uint32_t boxes, uint32_t spheres, uint32_t conn, uint32_t contacts) {
+static void ensure(Shim& g, uint32_t bodies, uint32_t boxes, uint32_t spheres, uint32_t conn, uint32_t contacts) {
 	if (g.ctx && bodies <= g.cap_bodies && boxes <= g.cap_boxes && spheres <= g.cap_spheres && conn <= g.cap_conn && contacts <= g.cap_contacts) return;
 	if (g.ctx) nb_destroy(g.ctx);
 	g.cap_bodies = grow(g.cap_bodies, bodies, 64); g.cap_boxes = grow(g.cap_boxes, boxes, 64); g.cap_spheres = grow(g.cap_spheres, spheres, 64);
 	g.cap_conn = grow(g.cap_conn, conn, 16); g.cap_contacts = grow(g.cap_contacts, contacts, 4096);
 	nb_config cfg = { g.cap_bodies, g.cap_boxes, g.cap_spheres, g.cap_conn, 0, g.cap_contacts, 0 };
-	if (nb_create(&cfg, &g.ctx) != NB_OK) die("nb_create");
+	if (nb_create(&cfg, &g.ctx) != NB_OK) die(g, "nb_create");
 }
 
-static void upload_bodies(const nudge::BodyData& b) {
+static void upload_bodies(Shim& g, const nudge::BodyData& b) {
 	nb_body_data hb = { (nb_transform*)b.transforms, (nb_body_properties*)b.properties, (nb_body_momentum*)b.momentum, b.idle_counters, b.count };
 	NBCK(nb_upload_bodies(g.ctx, &hb, nullptr));
 }
 
-static void upload_contacts(const nudge::ContactData& c, const nudge::ActiveBodies* active) {
+static void upload_contacts(Shim& g, const nudge::ContactData& c, const nudge::ActiveBodies* active) {
 	// uint64 tag = feature | A<<32 | B<<48 (nudge.cpp:2089, 2108)  ->  tags = A | B<<32, features
 	g.tags64.resize(c.count); g.features.resize(c.count); g.pairs32.resize(c.count);
 	for (uint32_t i = 0; i < c.count; ++i) {
@@ -114,8 +141,11 @@ namespace nudge {
 
 void collide(ActiveBodies* active_bodies, ContactData* contacts, BodyData bodies, ColliderData colliders, BodyConnections body_connections, Arena) {
 	contacts->count = 0; contacts->sleeping_count = 0; active_bodies->count = 0;  // nudge.cpp:3001-3003
-	ensure(bodies.count, colliders.boxes.count, colliders.spheres.count, body_connections.count, contacts->capacity);
-	upload_bodies(bodies);
+	Shim& g = world_of_bodies(bodies.transforms);
+	std::lock_guard<std::mutex> guard(g.lock);
+	bind_contacts(contacts->data, &g);
+	ensure(g, bodies.count, colliders.boxes.count, colliders.spheres.count, body_connections.count, contacts->capacity);
+	upload_bodies(g, bodies);
 	g.box_tags.assign(colliders.boxes.tags, colliders.boxes.tags + colliders.boxes.count);
 	g.sphere_tags.assign(colliders.spheres.tags, colliders.spheres.tags + colliders.spheres.count);
 	nb_collider_data hc = { { g.box_tags.data(), (nb_box_collider*)colliders.boxes.data, (nb_transform*)colliders.boxes.transforms, colliders.boxes.count },
@@ -146,9 +176,11 @@ void collide(ActiveBodies* active_bodies, ContactData* contacts, BodyData bodies
 
 ContactImpulseData* read_cached_impulses(ContactCache contact_cache, ContactData contacts, Arena* memory) {
 	ContactImpulseData* h = arena_alloc<ContactImpulseData>(memory, 64);
-	h->magic = 0x6e62696d70756c73ull;
-	ensure(g.cap_bodies, g.cap_boxes, g.cap_spheres, g.cap_conn, contact_cache.count > contacts.count ? contact_cache.count : contacts.count);
-	upload_contacts(contacts, nullptr);
+	Shim& g = world_of_contacts(contacts.data);
+	std::lock_guard<std::mutex> guard(g.lock);
+	h->magic = 0x6e62696d70756c73ull; h->world = &g;
+	ensure(g, g.cap_bodies, g.cap_boxes, g.cap_spheres, g.cap_conn, contact_cache.count > contacts.count ? contact_cache.count : contacts.count);
+	upload_contacts(g, contacts, nullptr);
 	g.tags64.resize(contact_cache.count); g.features.resize(contact_cache.count);
 	for (uint32_t i = 0; i < contact_cache.count; ++i) {
 		uint64_t t = contact_cache.tags[i];
@@ -160,11 +192,16 @@ ContactImpulseData* read_cached_impulses(ContactCache contact_cache, ContactData
 	return h;
 }
 
-ContactConstraintData* setup_contact_constraints(ActiveBodies active_bodies, ContactData contacts, BodyData bodies, ContactImpulseData*, Arena* memory) {
+ContactConstraintData* setup_contact_constraints(ActiveBodies active_bodies, ContactData contacts, BodyData bodies, ContactImpulseData* contact_impulses, Arena* memory) {
 	ContactConstraintData* h = arena_alloc<ContactConstraintData>(memory, 64);
-	h->magic = 0x6e62636f6e737472ull;
-	upload_bodies(bodies);  // the caller applied gravity to momentum on the host (example/main.cpp:291-305)
-	(void)active_bodies; (void)contacts;
+	Shim& g = *static_cast<Shim*>(contact_impulses->world);
+	std::lock_guard<std::mutex> guard(g.lock);
+	h->magic = 0x6e62636f6e737472ull; h->world = &g;
+	upload_bodies(g, bodies);  // the caller applied gravity to momentum on the host (example/main.cpp:291-305)
+	// the caller may have edited contact rows (friction, penetration, normals ...) or the active list since read_cached_impulses
+	// (example/main.cpp:288): the constraint rows are built from what it passes NOW, like nudge.cpp:4350-4561 reads `contacts` here.
+	// Count and tags must be the ones read_cached_impulses saw (the reference's sorted order indexes them, nudge.cpp:4044).
+	upload_contacts(g, contacts, &active_bodies);
 	NBCK(nb_setup_contact_constraints(g.ctx, nullptr));
 	NBCK(nb_download_momentum(g.ctx, (nb_body_momentum*)bodies.momentum, bodies.count, nullptr));  // unused0 + warm start (nudge.cpp:4198, 4626-4632)
 	nb_body_data none = { nullptr, nullptr, nullptr, nullptr, 0 };
@@ -172,7 +209,9 @@ ContactConstraintData* setup_contact_constraints(ActiveBodies active_bodies, Con
 	return h;
 }
 
-void apply_impulses(ContactConstraintData*, BodyData bodies) {
+void apply_impulses(ContactConstraintData* data, BodyData bodies) {
+	Shim& g = *static_cast<Shim*>(data->world);
+	std::lock_guard<std::mutex> guard(g.lock);
 	NBCK(nb_upload_momentum(g.ctx, (const nb_body_momentum*)bodies.momentum, bodies.count, nullptr));  // custom impulses may have been applied (example/main.cpp:316)
 	NBCK(nb_apply_impulses(g.ctx, 1, nullptr));
 	NBCK(nb_download_momentum(g.ctx, (nb_body_momentum*)bodies.momentum, bodies.count, nullptr));
@@ -180,11 +219,15 @@ void apply_impulses(ContactConstraintData*, BodyData bodies) {
 	NBCK(nb_download_bodies(g.ctx, &none, nullptr));
 }
 
-void update_cached_impulses(ContactConstraintData*, ContactImpulseData*) {
+void update_cached_impulses(ContactConstraintData* data, ContactImpulseData*) {
+	Shim& g = *static_cast<Shim*>(data->world);
+	std::lock_guard<std::mutex> guard(g.lock);
 	NBCK(nb_update_cached_impulses(g.ctx, nullptr));
 }
 
-void write_cached_impulses(ContactCache* contact_cache, ContactData contacts, ContactImpulseData*) {
+void write_cached_impulses(ContactCache* contact_cache, ContactData contacts, ContactImpulseData* contact_impulses) {
+	Shim& g = *static_cast<Shim*>(contact_impulses->world);
+	std::lock_guard<std::mutex> guard(g.lock);
 	NBCK(nb_write_cached_impulses(g.ctx, nullptr));
 	uint32_t cap = contact_cache->capacity;
 	g.tags64.resize(cap); g.features.resize(cap);
@@ -197,7 +240,10 @@ void write_cached_impulses(ContactCache* contact_cache, ContactData contacts, Co
 }
 
 void advance(ActiveBodies active_bodies, BodyData bodies, float time_step) {
-	upload_bodies(bodies);
+	Shim& g = world_of_bodies(bodies.transforms);
+	std::lock_guard<std::mutex> guard(g.lock);
+	if (!g.ctx) ensure(g, bodies.count, 1, 1, 1, 1024);   // advance() on a world that never collided: still valid in the reference
+	upload_bodies(g, bodies);
 	g.active32.assign(active_bodies.indices, active_bodies.indices + active_bodies.count);
 	nb_active_bodies ha = { g.active32.data(), active_bodies.count, active_bodies.count };
 	NBCK(nb_upload_contacts(g.ctx, nullptr, &ha, nullptr));

@@ -357,3 +357,20 @@ def test_two_simulations_on_two_streams_step_concurrently():
         x.download_bodies()
     assert a.debug_scalar("graph_coop") in (1, 2)
     assert a.transforms.tobytes() == c.transforms.tobytes() and b.transforms.tobytes() == c.transforms.tobytes()
+
+
+def test_headless_application_loop_on_the_dropin_equals_the_reference():
+    """oracle/headless_example.cpp — an application loop over nudge.h in the shape of example/main.cpp:274-328, with the user's gravity
+    loop on the host between the calls — linked with the reference's nudge.cpp (headless_ref) and with the GPU drop-in (headless_gpu):
+    identical transform hashes after 120 steps, for one world and for two worlds stepped concurrently from two threads (one device
+    context per world; the reference is re-entrant on disjoint data)."""
+    import subprocess
+    d = os.path.join(os.path.dirname(G.HERE), "oracle", "_ref")
+    if not (os.path.exists(os.path.join(d, "headless_ref")) and os.path.exists(os.path.join(d, "headless_gpu"))):
+        pytest.skip("oracle/_ref/headless_* not built (needs /root/reference in the build container)")
+    for args in (["300", "300", "120", "8"], ["150", "150", "60", "8", "2"]):
+        ref = subprocess.run([os.path.join(d, "headless_ref")] + args, capture_output=True, text=True, timeout=600)
+        gpu = subprocess.run([os.path.join(d, "headless_gpu")] + args, capture_output=True, text=True, timeout=600)
+        assert ref.returncode == 0 and gpu.returncode == 0, gpu.stdout + gpu.stderr
+        worlds = lambda out: [l for l in out.splitlines() if l.startswith("world")]
+        assert worlds(ref.stdout) == worlds(gpu.stdout) and len(worlds(ref.stdout)) == (2 if len(args) == 5 else 1), ref.stdout + gpu.stdout
