@@ -136,6 +136,24 @@ int nb_advance(nb_context*, float time_step, void* stream);
  * are recorded once into a CUDA graph and replayed; NB_GRAPH=0 in the environment keeps plain launches. */
 int nb_step(nb_context*, float time_step, uint32_t iterations, float gravity, float damping, void* stream);
 
+/* User constraint rows: the device-resident form of the hook at example/main.cpp:316 ("Custom constraint impulses
+ * should be applied here", after every apply_impulses sweep).  One row = one scalar velocity constraint between bodies a and b
+ * (0 = the static world):  J v + bias -> 0  with the accumulated impulse kept inside [lo, hi]; rows are applied by sequential impulses in
+ * upload order after every contact sweep, their accumulated impulses warm-start the next step (nudge_b200/csrc/nb_rows_api.cuh).
+ * Connect the bodies of a joint with nb_upload_connections too, so that islands treat them as one (example/main.cpp:285). */
+typedef struct {
+	uint32_t a, b;
+	float lin_a[3], ang_a[3];   /* Jacobian of body a: linear and angular part */
+	float lin_b[3], ang_b[3];   /* Jacobian of body b */
+	float bias;                 /* velocity target term (e.g. Baumgarte: beta / dt * position error) */
+	float lo, hi;               /* bounds of the accumulated impulse: (-inf, inf) joint, [0, inf) unilateral, [-f, f] motor / friction */
+	float impulse;              /* accumulated impulse: warm start on upload, result on download */
+	float softness;             /* constraint force mixing added to the effective inverse mass; 0 = rigid */
+	float reserved;
+} nb_constraint_row;            /* 80 bytes */
+int nb_upload_constraint_rows(nb_context*, const nb_constraint_row* host_rows, uint32_t n, void* stream);   /* replaces the set; n = 0 removes it; synchronises */
+int nb_download_constraint_rows(nb_context*, nb_constraint_row* host_rows, uint32_t n, void* stream);       /* caller's order; synchronises */
+
 /* CUDA streams for hosts that do not link the CUDA runtime (cgo / JNI / ctypes callers): a created stream is capturable, so nb_step
  * replays its CUDA graph there; a null stream means the legacy default stream and plain launches. */
 void* nb_stream_create(nb_context*);

@@ -20,7 +20,8 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_shard_unique_id", "nb_shard_create", "nb_shard_destroy", "nb_shard_ipc_handle", "nb_shard_open_peer", "nb_shard_plan", "nb_shard_exchange",
            "nb_shard_step", "nb_shard_graph_active", "nb_shard_partition",
            "nb_set_solver_mode", "nb_get_solver_mode", "nb_debug_timing_enable", "nb_debug_timing",
-           "nb_stream_create", "nb_stream_destroy", "nb_stream_synchronize", "nb_save_state", "nb_load_state", "nb_state_info"]
+           "nb_stream_create", "nb_stream_destroy", "nb_stream_synchronize", "nb_save_state", "nb_load_state", "nb_state_info",
+           "nb_upload_constraint_rows", "nb_download_constraint_rows"]
 
 
 class Config(C.Structure):
@@ -87,12 +88,20 @@ def load_library():
         lib.nb_save_state.argtypes = [V, C.c_char_p, V]
         lib.nb_load_state.argtypes = [V, C.c_char_p, V]
         lib.nb_state_info.argtypes = [C.c_char_p, V]
+        lib.nb_upload_constraint_rows.argtypes = [V, V, C.c_uint32, V]
+        lib.nb_download_constraint_rows.argtypes = [V, V, C.c_uint32, V]
         _lib = lib
     return _lib
 
 
 class NudgeError(RuntimeError):
     pass
+
+
+# nb_constraint_row (80 bytes)
+ROW = np.dtype([("a", "<u4"), ("b", "<u4"), ("lin_a", "<f4", 3), ("ang_a", "<f4", 3), ("lin_b", "<f4", 3), ("ang_b", "<f4", 3),
+                ("bias", "<f4"), ("lo", "<f4"), ("hi", "<f4"), ("impulse", "<f4"), ("softness", "<f4"), ("reserved", "<f4")])
+assert ROW.itemsize == 80
 
 
 def nccl_unique_id():
@@ -277,6 +286,16 @@ class Sim(abi.HostState):
 
     def launch_count(self):
         return int(self.lib.nb_launch_count(self.ctx))
+
+    # ---- user constraint rows (nb_constraint_row, include/nudge_b200.h) ----
+    def upload_constraint_rows(self, rows):
+        rows = np.ascontiguousarray(rows, ROW)
+        self._ck(self.lib.nb_upload_constraint_rows(self.ctx, abi.ptr(rows) if len(rows) else None, len(rows), self.stream), "nb_upload_constraint_rows")
+
+    def download_constraint_rows(self, n):
+        rows = np.zeros(n, ROW)
+        self._ck(self.lib.nb_download_constraint_rows(self.ctx, abi.ptr(rows) if n else None, n, self.stream), "nb_download_constraint_rows")
+        return rows
 
     # ---- state files (nb_save_state / nb_load_state; tools/nb_replay steps them headless) ----
     def save_state(self, path):

@@ -32,7 +32,7 @@ struct nb_context {
 	u64* keybits;  // OR, AND of the Morton codes of the current collide
 	bool defer_warm_start;  // nb_step: the warm start runs inside the first solver launch
 	// nb_step as a CUDA graph: captured once per (stream, parameters, scene shape), replayed afterwards
-	struct StepKey { cudaStream_t stream; float ts, gravity, damping; u32 iterations, B, nboxes, nspheres, nconn, tagbits, kbits; int debug, solver_mode; } graph_key;
+	struct StepKey { cudaStream_t stream; float ts, gravity, damping; u32 iterations, B, nboxes, nspheres, nconn, tagbits, kbits; int debug, solver_mode; unsigned long long urow_version; } graph_key;
 	cudaGraphExec_t graph_exec; unsigned long long graph_launches; int graph_enabled; bool capturing;
 	int graph_is_coop;  // the recorded graph holds cooperative kernel nodes
 	int graph_coop;  // 1: grid-synchronising kernels keep the cooperative-launch attribute inside the captured graph (co-residency guaranteed by the driver)
@@ -43,6 +43,8 @@ struct nb_context {
 	int solver_mode; u32* jcnt; float4* jd; int jacobi_blocks;
 	// CUDA-event timing of the dominant solver kernel (nb_debug_timing): bench.py's roofline numerator is measured live
 	int timing; cudaEvent_t tev[2][64]; int tev_n; bool tev_made;
+	// user constraint rows (nb_upload_constraint_rows, nb_rows_api.cuh)
+	nb_constraint_row* urows; u32 urow_cap, urow_n, urow_levels; unsigned long long urow_version; std::vector<u32> urow_level_off, urow_order;
 
 	// scene
 	nb_transform* xf; nb_body_properties* props; nb_body_momentum* mom; uint8_t* idle;
@@ -91,6 +93,7 @@ static int dev_alloc(nb_context* ctx, T** p, size_t n) {
 static u32 bits_for(u64 n) { u32 b = 1; while (((u64)1 << b) < n) ++b; return b; }
 static Launch mk_launch(nb_context* ctx, void* stream) { Launch L = { (cudaStream_t)stream, &ctx->launches, ctx->sms }; return L; }
 #define GRID(n) nb_grid_for((unsigned)(n), ctx->sms)
+static int launch_user_rows(nb_context* ctx, int warm, cudaStream_t st);   // nb_rows_api.cuh
 
 __global__ void k_reset_collide(u32* counts, u32 K, u64* keybits) {
 	if (threadIdx.x == 0) {
@@ -582,7 +585,7 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 		k_jacobi_prepare<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->jcnt, ctx->rows, ctx->cstride, counts);
 		k_build_rows<true><<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts, ctx->jcnt);
 		ctx->launches += 3;
-		if (!ctx->defer_warm_start) { int r = launch_solve(ctx, 0, 1, st); if (r) return r; }
+		if (!ctx->defer_warm_start) { int r = launch_solve(ctx, 0, 1, st); if (r) return r; if (ctx->urow_n && (r = launch_user_rows(ctx, 1, st))) return r; }
 		CK(cudaGetLastError());
 		return NB_OK;
 	}
@@ -600,13 +603,23 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, ctx->slot_idx, ctx->chain_start, ctx->chain_len, ctx->rows.wait, ctx->cstride, counts);
 	k_build_rows<false><<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts, nullptr);
 	ctx->launches += 2;
-	if (!ctx->defer_warm_start) { int r = launch_solve(ctx, 0, 1, st); if (r) return r; }  // warm start (nudge.cpp:4563-4632)
+	if (!ctx->defer_warm_start) {  // warm start (nudge.cpp:4563-4632), then the user rows' accumulated impulses
+		int r = launch_solve(ctx, 0, 1, st); if (r) return r;
+		if (ctx->urow_n && (r = launch_user_rows(ctx, 1, st))) return r;
+	}
 	CK(cudaGetLastError());
 	return NB_OK;
 }
 
 int nb_apply_impulses(nb_context* ctx, uint32_t sweeps, void* stream) {
 	if (!sweeps) return NB_OK;
+	if (ctx->urow_n && !ctx->defer_warm_start) {   // user rows run after EVERY sweep (example/main.cpp:314-317): one sweep per solver launch
+		for (uint32_t w = 0; w < sweeps; ++w) {
+			int r = launch_solve(ctx, 1, 1, (cudaStream_t)stream); if (r) return r;
+			if ((r = launch_user_rows(ctx, 0, (cudaStream_t)stream))) return r;
+		}
+		return NB_OK;
+	}
 	int r = launch_solve(ctx, ctx->defer_warm_start ? 2 : 1, sweeps, (cudaStream_t)stream); if (r) return r;
 	ctx->defer_warm_start = false;
 	CK(cudaGetLastError());
@@ -632,7 +645,7 @@ static int step_body(nb_context* ctx, float time_step, uint32_t iterations, floa
 	if ((r = nb_collide(ctx, stream))) return r;
 	if ((r = nb_apply_gravity_damping(ctx, time_step, gravity, damping, stream))) return r;
 	if ((r = nb_read_cached_impulses(ctx, stream))) return r;
-	ctx->defer_warm_start = iterations > 0;  // warm start + sweeps in one solver launch (same arithmetic, same order)
+	ctx->defer_warm_start = iterations > 0 && !ctx->urow_n;  // warm start + sweeps in one solver launch (same arithmetic, same order); not with user rows between the sweeps
 	r = nb_setup_contact_constraints(ctx, stream);
 	if (!r) r = nb_apply_impulses(ctx, iterations, stream);
 	ctx->defer_warm_start = false;
@@ -652,7 +665,7 @@ int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity
 	nb_context::StepKey key;
 	memset(&key, 0, sizeof(key));  // padding bytes included: the key is compared with memcmp
 	key.stream = st; key.ts = time_step; key.gravity = gravity; key.damping = damping; key.iterations = iterations;
-	key.B = ctx->B; key.nboxes = ctx->nboxes; key.nspheres = ctx->nspheres; key.nconn = ctx->nconn; key.tagbits = ctx->tagbits; key.kbits = ctx->kbits; key.debug = ctx->debug; key.solver_mode = ctx->solver_mode;
+	key.B = ctx->B; key.nboxes = ctx->nboxes; key.nspheres = ctx->nspheres; key.nconn = ctx->nconn; key.tagbits = ctx->tagbits; key.kbits = ctx->kbits; key.debug = ctx->debug; key.solver_mode = ctx->solver_mode; key.urow_version = ctx->urow_version;
 	if (!ctx->graph_exec || memcmp(&key, &ctx->graph_key, sizeof(key)) != 0) {
 		if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
 		// Attempt 1 keeps the cooperative-launch attribute on the grid-synchronising kernel nodes (k_sort_coop's software grid barriers,
@@ -809,3 +822,4 @@ int nb_debug_rcp(nb_context* ctx, const float* x, float* y, uint32_t n, int rsq)
 
 #include "nb_shard_api.cuh"
 #include "nb_state_api.cuh"
+#include "nb_rows_api.cuh"

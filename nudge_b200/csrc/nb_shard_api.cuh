@@ -16,7 +16,7 @@ struct nb_shard {
 	// NCCL transport buffers
 	float4* d_export; float4* d_gather;
 	// sharded step as a CUDA graph
-	struct Key { cudaStream_t stream; float ts, gravity, damping; u32 iterations; int transport, solver_mode; unsigned long long plan_version; u32 B, nboxes, nspheres; } key;
+	struct Key { cudaStream_t stream; float ts, gravity, damping; u32 iterations; int transport, solver_mode; unsigned long long plan_version, urow_version; u32 B, nboxes, nspheres; } key;
 	cudaGraphExec_t graph; unsigned long long graph_launches; int graph_enabled;
 	long long pull_timeout_cycles;
 };
@@ -181,7 +181,7 @@ int nb_shard_step(nb_shard* sh, float time_step, uint32_t iterations, float grav
 	nb_shard::Key key;
 	memset(&key, 0, sizeof(key));
 	key.stream = st; key.ts = time_step; key.gravity = gravity; key.damping = damping; key.iterations = iterations; key.transport = transport;
-	key.solver_mode = ctx->solver_mode; key.plan_version = sh->plan_version; key.B = ctx->B; key.nboxes = ctx->nboxes; key.nspheres = ctx->nspheres;
+	key.solver_mode = ctx->solver_mode; key.plan_version = sh->plan_version; key.urow_version = ctx->urow_version; key.B = ctx->B; key.nboxes = ctx->nboxes; key.nspheres = ctx->nspheres;
 	if (!sh->graph || memcmp(&key, &sh->key, sizeof(key)) != 0) {
 		if (sh->graph) { cudaGraphExecDestroy(sh->graph); sh->graph = nullptr; }
 		for (int attempt = ctx->graph_coop ? 0 : 1; attempt < 2 && !sh->graph; ++attempt) {
