@@ -594,13 +594,18 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 		ctx->flags, ctx->left_count, counts);
 	ctx->launches += 3;
 	nb_scan<1>(L, ctx->flags, ctx->offs, S, counts + CNT_CONTACTS, 0, ctx->block_sums, counts + CNT_FULL_BATCHES);
+	// key layout of the per-body chain sort: (body | batch).  Sides on the static world become dummies spread over the unused part
+	// of the body field (an extra bit if less than a quarter of it is free), so no sort bucket collects them all.
+	u32 chain_bodybits = bits_for(std::max(B, 2u));
+	if (((u64)1 << chain_bodybits) - B < ((u64)1 << chain_bodybits) / 4) ++chain_bodybits;
+	const u32 dummy_span = (u32)std::min<u64>(((u64)1 << chain_bodybits) - B, 0x7fffffffu);
 	CK(cudaMemsetAsync(ctx->rows.contact, 0xff, sizeof(u32) * ctx->cstride, st));
 	k_batch_index<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,
-		ctx->offs, ctx->left_count, ctx->batch_of, ctx->slot_idx, ctx->rows.contact, ctx->cstride, ctx->sb.keys[0], ctx->sb.vals[0], ctx->batchbits, counts);
+		ctx->offs, ctx->left_count, ctx->batch_of, ctx->slot_idx, ctx->rows.contact, ctx->cstride, ctx->sb.keys[0], ctx->sb.vals[0], ctx->batchbits, B, dummy_span, counts);
 	++ctx->launches;
-	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_ENTRIES, 0, (int)(ctx->bodybits + ctx->batchbits), true, 0);
-	k_chain_heads<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->batchbits, ctx->chain_start, ctx->chain_len, counts); ++ctx->launches;
-	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, ctx->slot_idx, ctx->chain_start, ctx->chain_len, ctx->rows.wait, ctx->cstride, counts);
+	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_ENTRIES, 0, (int)(chain_bodybits + ctx->batchbits), true, 0);
+	k_chain_heads<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->batchbits, B, ctx->chain_start, ctx->chain_len, counts); ++ctx->launches;
+	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, B, ctx->slot_idx, ctx->chain_start, ctx->chain_len, ctx->rows.wait, ctx->cstride, counts);
 	k_build_rows<false><<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts, nullptr);
 	ctx->launches += 2;
 	if (!ctx->defer_warm_start) {  // warm start (nudge.cpp:4563-4632), then the user rows' accumulated impulses

@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(32) k_schedule(const uint2* cab, const uint8_t
 // batch index and slot (batch*8 + lane) of every contact + the (body, batch) chain entries
 __global__ void __launch_bounds__(NB_BLOCK) k_batch_index(const u32* sorted, const uint2* bodies, const u32* slot_of, const u32* slot_done, const u32* slot_left,
 		u32 slots_per_bucket, const u32* complete_off, const u32* left_count, u32* batch_of, u32* slot_idx, u32* slot_contact, u32 max_slots,
-		u64* chain_keys, u32* chain_vals, u32 batchbits, u32* counts) {
+		u64* chain_keys, u32* chain_vals, u32 batchbits, u32 nbodies, u32 dummy_span, u32* counts) {
 	u32 n = counts[CNT_CONTACTS];
 	u32 nfull = counts[CNT_FULL_BATCHES];
 	u32 left_base[17]; left_base[0] = 0;
@@ -397,8 +397,12 @@ __global__ void __launch_bounds__(NB_BLOCK) k_batch_index(const u32* sorted, con
 		slot_idx[i] = slot;
 		if (slot < max_slots) slot_contact[slot] = sorted[i];
 		uint2 ab = bodies[sorted[i]];
-		chain_keys[2*i] = ab.x ? (((u64)ab.x << batchbits) | batch) : ~(u64)0;
-		chain_keys[2*i + 1] = ab.y ? (((u64)ab.y << batchbits) | batch) : ~(u64)0;
+		// A side on the static world (body 0) has no chain.  Its entry still goes through the sort, as a DUMMY whose body field lies beyond
+		// the real bodies, spread evenly over [nbodies, nbodies + dummy_span): one shared key (round 1) put every ground contact of
+		// the pile - 10 % of all entries - into a single sort bucket, the slowest block of the step.
+		const u64 dummy = ((u64)(nbodies + i % dummy_span) << batchbits) | batch;
+		chain_keys[2*i] = ab.x ? (((u64)ab.x << batchbits) | batch) : dummy;
+		chain_keys[2*i + 1] = ab.y ? (((u64)ab.y << batchbits) | batch) : dummy;
 		chain_vals[2*i] = 2*i; chain_vals[2*i + 1] = 2*i + 1;
 	}
 }
@@ -410,19 +414,19 @@ __global__ void __launch_bounds__(NB_BLOCK) k_batch_index(const u32* sorted, con
 // contact at position `seq` of a body's chain of length `len` therefore runs in sweep w when the token reads w*len + seq, and
 // leaves w*len + seq + 1.  (expected - seen) is the number of applications still ahead of a waiting contact, which is what the
 // solver's back-off sleeps on.  Body 0 (static world) is never waited for: its entries carry the key ~0.
-__global__ void __launch_bounds__(NB_BLOCK) k_chain_heads(const u64* chain_keys, u32 batchbits, u32* chain_start, u32* chain_len, const u32* counts) {
+__global__ void __launch_bounds__(NB_BLOCK) k_chain_heads(const u64* chain_keys, u32 batchbits, u32 nbodies, u32* chain_start, u32* chain_len, const u32* counts) {
 	u32 n2 = counts[CNT_ENTRIES];
 	for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += gridDim.x * blockDim.x) {
 		u64 k = chain_keys[e];
-		if (k == ~(u64)0) continue;
 		u64 body = k >> batchbits;
+		if (body >= nbodies) continue;   // dummy entry of a static-world side
 		if (e > 0 && (chain_keys[e - 1] >> batchbits) == body) continue;
 		u32 lo = e, hi = n2;  // first index with a larger body
-		while (lo < hi) { u32 mid = (lo + hi) >> 1; u64 km = chain_keys[mid]; if (km != ~(u64)0 && (km >> batchbits) <= body) lo = mid + 1; else hi = mid; }
+		while (lo < hi) { u32 mid = (lo + hi) >> 1; u64 km = chain_keys[mid]; if ((km >> batchbits) <= body) lo = mid + 1; else hi = mid; }
 		chain_start[body] = e; chain_len[body] = lo - e;
 	}
 }
-__global__ void __launch_bounds__(NB_BLOCK) k_waits(const u64* chain_keys, const u32* chain_vals, u32 batchbits, const u32* slot_idx, const u32* chain_start, const u32* chain_len,
+__global__ void __launch_bounds__(NB_BLOCK) k_waits(const u64* chain_keys, const u32* chain_vals, u32 batchbits, u32 nbodies, const u32* slot_idx, const u32* chain_start, const u32* chain_len,
 		uint2* wait /*[2][stride]: seq, len*/, u32 stride, const u32* counts) {
 	u32 n2 = counts[CNT_ENTRIES];
 	for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += gridDim.x * blockDim.x) {
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(NB_BLOCK) k_waits(const u64* chain_keys, const
 		u32 v = chain_vals[e];
 		u32 slot = slot_idx[v >> 1], side = v & 1;
 		uint2 w = make_uint2(0, 0);
-		if (k != ~(u64)0) { u32 body = (u32)(k >> batchbits); w = make_uint2(e - chain_start[body], chain_len[body]); }
+		if ((k >> batchbits) < nbodies) { u32 body = (u32)(k >> batchbits); w = make_uint2(e - chain_start[body], chain_len[body]); }
 		if (slot < stride) wait[side * stride + slot] = w;
 	}
 }
