@@ -11,6 +11,7 @@
 #include <vector>
 #include <algorithm>
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>
 
 extern "C" void nb_host_sample_luts(u32* rcp_lut, u32* rsqrt_lut);   // nb_lut_host.cpp
 extern "C" int nb_host_check_lut_model(const u32* rcp_lut, const u32* rsqrt_lut);
@@ -93,6 +94,9 @@ static int dev_alloc(nb_context* ctx, T** p, size_t n) {
 static u32 bits_for(u64 n) { u32 b = 1; while (((u64)1 << b) < n) ++b; return b; }
 static Launch mk_launch(nb_context* ctx, void* stream) { Launch L = { (cudaStream_t)stream, &ctx->launches, ctx->sms }; return L; }
 #define GRID(n) nb_grid_for((unsigned)(n), ctx->sms)
+// NVTX range per API call: visible in Nsight timelines, a no-op costing tens of nanoseconds without a tool attached
+struct NbRange { NbRange(const char* name) { nvtxRangePushA(name); } ~NbRange() { nvtxRangePop(); } };
+#define NB_RANGE(name) NbRange nb_range_(name)
 static int launch_user_rows(nb_context* ctx, int warm, cudaStream_t st);   // nb_rows_api.cuh
 
 __global__ void k_reset_collide(u32* counts, u32 K, u64* keybits) {
@@ -263,6 +267,7 @@ int nb_lut_model_exact(const nb_context* ctx) { return ctx->lut_exact; }
 #define D2H(dst, src, n, T) CK(cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyDeviceToHost, (cudaStream_t)stream))
 
 int nb_upload_bodies(nb_context* ctx, const nb_body_data* h, void* stream) {
+	NB_RANGE("nb_upload_bodies");
 	if (h->count > ctx->cfg.max_bodies) { ctx->error = "too many bodies"; return NB_ERR_CAPACITY; }
 	ctx->B = h->count;
 	H2D(ctx->xf, h->transforms, h->count, nb_transform); H2D(ctx->props, h->properties, h->count, nb_body_properties);
@@ -304,6 +309,7 @@ int nb_upload_cache(nb_context* ctx, const nb_contact_cache* h, void* stream) {
 	return NB_OK;
 }
 int nb_download_bodies(nb_context* ctx, nb_body_data* h, void* stream) {
+	NB_RANGE("nb_download_bodies");
 	u32 n = std::min(h->count, ctx->B);
 	D2H(h->transforms, ctx->xf, n, nb_transform); D2H(h->momentum, ctx->mom, n, nb_body_momentum); D2H(h->idle_counters, ctx->idle, n, uint8_t);
 	CK(cudaStreamSynchronize((cudaStream_t)stream));
@@ -380,6 +386,7 @@ int nb_download_cache(nb_context* ctx, nb_contact_cache* h, void* stream) {
 
 // ---------------- collide ----------------
 int nb_collide(nb_context* ctx, void* stream) {
+	NB_RANGE("nb_collide");
 	Launch L = mk_launch(ctx, stream);
 	cudaStream_t st = L.stream;
 	const u32 K = ctx->nboxes + ctx->nspheres, B = ctx->B, nboxes = ctx->nboxes;
@@ -473,6 +480,7 @@ int nb_collide(nb_context* ctx, void* stream) {
 }
 
 int nb_apply_gravity_damping(nb_context* ctx, float time_step, float gravity, float damping, void* stream) {
+	NB_RANGE("nb_apply_gravity_damping");
 	k_gravity_damping<<<GRID(ctx->B), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->active_idx, ctx->mom, time_step, gravity, damping, ctx->counts);
 	++ctx->launches;
 	CK(cudaGetLastError());
@@ -481,6 +489,7 @@ int nb_apply_gravity_damping(nb_context* ctx, float time_step, float gravity, fl
 
 // ---------------- contact cache ----------------
 int nb_read_cached_impulses(nb_context* ctx, void* stream) {
+	NB_RANGE("nb_read_cached_impulses");
 	Launch L = mk_launch(ctx, stream);
 	cudaStream_t st = L.stream;
 	u32* counts = ctx->counts;
@@ -510,6 +519,7 @@ int nb_read_cached_impulses(nb_context* ctx, void* stream) {
 }
 
 int nb_write_cached_impulses(nb_context* ctx, void* stream) {
+	NB_RANGE("nb_write_cached_impulses");
 	const u32 C = ctx->cfg.max_contacts;
 	k_cache_merge<<<GRID(C), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->sorted, ctx->fin.tags, ctx->fin.features, ctx->impulses,
 		ctx->culled_tags, ctx->culled_features, ctx->culled_data, ctx->cache_tags, ctx->cache_features, ctx->cache_data, ctx->counts);
@@ -573,6 +583,7 @@ static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) 
 }
 
 int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
+	NB_RANGE("nb_setup_contact_constraints");
 	Launch L = mk_launch(ctx, stream);
 	cudaStream_t st = L.stream;
 	u32* counts = ctx->counts;
@@ -617,6 +628,7 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 }
 
 int nb_apply_impulses(nb_context* ctx, uint32_t sweeps, void* stream) {
+	NB_RANGE("nb_apply_impulses");
 	if (!sweeps) return NB_OK;
 	if (ctx->urow_n && !ctx->defer_warm_start) {   // user rows run after EVERY sweep (example/main.cpp:314-317): one sweep per solver launch
 		for (uint32_t w = 0; w < sweeps; ++w) {
@@ -632,6 +644,7 @@ int nb_apply_impulses(nb_context* ctx, uint32_t sweeps, void* stream) {
 }
 
 int nb_update_cached_impulses(nb_context* ctx, void* stream) {
+	NB_RANGE("nb_update_cached_impulses");
 	k_update_impulses<<<GRID(ctx->cstride), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->rows, ctx->impulses, ctx->counts);
 	++ctx->launches;
 	CK(cudaGetLastError());
@@ -639,6 +652,7 @@ int nb_update_cached_impulses(nb_context* ctx, void* stream) {
 }
 
 int nb_advance(nb_context* ctx, float time_step, void* stream) {
+	NB_RANGE("nb_advance");
 	k_advance<<<GRID(ctx->B), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->active_idx, ctx->xf, ctx->mom, ctx->idle, time_step, ctx->counts);
 	++ctx->launches;
 	CK(cudaGetLastError());
@@ -664,6 +678,7 @@ static int step_body(nb_context* ctx, float time_step, uint32_t iterations, floa
 // replayed; every count the kernels need lives in device memory, so the graph only depends on the parameters and the scene
 // shape held in StepKey.  NB_GRAPH=0, the legacy default stream or debug mode use plain launches.
 int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity, float damping, void* stream) {
+	NB_RANGE("nb_step");
 	cudaStream_t st = (cudaStream_t)stream;
 	if (!ctx->graph_enabled || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread || ctx->debug)
 		return step_body(ctx, time_step, iterations, gravity, damping, stream);

@@ -129,6 +129,7 @@ int nb_shard_plan(nb_shard* sh, const uint32_t* export_local, uint32_t n_export,
 
 // Ghost rows <- owners' rows.  Every rank must call it the same number of times with the same transport.
 int nb_shard_exchange(nb_shard* sh, int transport, void* stream) {
+	NB_RANGE("nb_shard_exchange");
 	nb_context* ctx = sh->ctx;
 	cudaStream_t st = (cudaStream_t)stream;
 	if (sh->world == 1) return NB_OK;
@@ -174,6 +175,7 @@ static int shard_step_body(nb_shard* sh, float time_step, uint32_t iterations, f
 // On a capturable stream the whole step — kernels, NCCL all-gathers or peer pushes/pulls — is recorded once per plan into a CUDA
 // graph and replayed (NB_GRAPH=0 keeps plain launches).
 int nb_shard_step(nb_shard* sh, float time_step, uint32_t iterations, float gravity, float damping, int transport, void* stream) {
+	NB_RANGE("nb_shard_step");
 	nb_context* ctx = sh->ctx;
 	cudaStream_t st = (cudaStream_t)stream;
 	if (!sh->graph_enabled || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread || ctx->debug)
