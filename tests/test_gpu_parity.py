@@ -376,3 +376,17 @@ def test_headless_application_loop_on_the_dropin_equals_the_reference():
         assert ref.returncode == 0 and gpu.returncode == 0, gpu.stdout + gpu.stderr
         worlds = lambda out: [l for l in out.splitlines() if l.startswith("world")]
         assert worlds(ref.stdout) == worlds(gpu.stdout) and len(worlds(ref.stdout)) == (2 if len(args) == 5 else 1), ref.stdout + gpu.stdout
+
+
+@pytest.mark.parametrize("name", ["config2_mixed_256k", "config4_bricks_256k"])
+def test_full_size_configs_2_and_4_one_step_parity(name):
+    """BASELINE configs[2] (262,144 mixed boxes/spheres, 16 iterations) and configs[4] (262,144-brick wall, 20 iterations) at FULL size:
+    settle on the GPU, then one complete step bit-exact against the widened CPU oracle from identical state (every stage compared:
+    pair list, contacts, tag order, schedule, rows, momentum after all sweeps, cache, transforms)."""
+    s = scenes.mixed_stack(262144, iterations=16) if name.startswith("config2") else scenes.brick_wall(262144, iterations=20)
+    o, g = _pair(s)
+    for _ in range(40):
+        g.step()
+    assert g.counts().overflow == 0
+    sync_oracle_from_gpu(o, g)
+    _steps(o, g, 1, individually=False)
