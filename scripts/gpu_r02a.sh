@@ -1,6 +1,6 @@
 # round 2, GPU cycle A: regression tests, all five BASELINE configs on one GPU, hand-off microbenchmark, per-kernel DRAM/L2 metrics
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r02a_pytest.log; cat gpurun_out/r02a_pytest.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -40 > gpurun_out/r02a_pytest.log; tail -15 gpurun_out/r02a_pytest.log
 timeout 120 scripts/bin/handoff_latency > gpurun_out/r02a_handoff.txt 2>&1; cat gpurun_out/r02a_handoff.txt
 for c in c2 c1 c3 c5 c4; do
   timeout 600 python bench.py --config $c --steps 10 --warmup 3 $( [ $c != c2 ] && echo --no-cpu-baseline ) > gpurun_out/r02a_$c.json 2> gpurun_out/r02a_$c.err
