@@ -497,8 +497,9 @@ int nb_read_cached_impulses(nb_context* ctx, void* stream) {
 	// order contacts by tag: stable sort on the feature word, then on the pair word (nudge.cpp:4024-4044)
 	int cur;
 	if (ctx->contacts_internal && 2 * ctx->tagbits + 16 <= 64) {
-		k_tag_keys_packed<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.tags, ctx->fin.features, ctx->sb.keys[0], ctx->sb.vals[0], ctx->tagbits, counts); ++ctx->launches;
-		cur = nb_radix_sort(L, ctx->sb, counts + CNT_CONTACTS, 0, (int)(2 * ctx->tagbits + 16), true, 0);
+		const u32 spread = (ctx->tagbits >= 3 && 2 * ctx->tagbits + 17 <= 64) ? 1u : 0u;
+		k_tag_keys_packed<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.tags, ctx->fin.features, ctx->sb.keys[0], ctx->sb.vals[0], ctx->tagbits, spread, counts); ++ctx->launches;
+		cur = nb_radix_sort(L, ctx->sb, counts + CNT_CONTACTS, 0, (int)(2 * ctx->tagbits + 16 + spread), true, 0);
 	}
 	else {  // contacts supplied through nb_upload_contacts: arbitrary feature words
 		k_tag_keys_feature<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.features, ctx->sb.keys[0], ctx->sb.vals[0], counts); ++ctx->launches;
