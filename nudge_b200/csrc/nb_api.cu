@@ -44,6 +44,8 @@ struct nb_context {
 	int solver_mode; u32* jcnt; float4* jd; int jacobi_blocks;
 	// CUDA-event timing of the dominant solver kernel (nb_debug_timing): bench.py's roofline numerator is measured live
 	int timing; cudaEvent_t tev[2][64]; int tev_n; bool tev_made;
+	// nb_step overlaps independent branches of the step on a second stream (fork/join with events; also inside the captured graph)
+	bool rows_on_side, join_before_solve; int overlap; cudaStream_t side; cudaEvent_t ev_fork, ev_fork2, ev_join, ev_join2; u32* flags2; u32* offs2; u32* block_sums2;
 	// user constraint rows (nb_upload_constraint_rows, nb_rows_api.cuh)
 	nb_constraint_row* urows; u32 urow_cap, urow_n, urow_levels; unsigned long long urow_version; std::vector<u32> urow_level_off, urow_order;
 
@@ -218,6 +220,11 @@ int nb_create(const nb_config* config, nb_context** out) {
 	ALLOC(ctx->rows.a, ctx->cstride); ALLOC(ctx->rows.b, ctx->cstride); ALLOC(ctx->rows.contact, ctx->cstride); ALLOC(ctx->rows.wait, 2 * (size_t)ctx->cstride); ALLOC(ctx->chain_start, B); ALLOC(ctx->chain_len, B);
 	ctx->rows.stride = ctx->cstride;
 	ALLOC(ctx->jcnt, B); ALLOC(ctx->jd, 2 * (size_t)B);
+	ALLOC(ctx->flags2, ctx->stride); ALLOC(ctx->offs2, ctx->stride); ALLOC(ctx->block_sums2, 16 * NB_SCAN_GRID);
+	{ const char* e = getenv("NB_OVERLAP"); ctx->overlap = e ? atoi(e) != 0 : 1; }
+	CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
 	ctx->solver_mode = NB_SOLVER_PARITY;
 	CK(cudaFuncSetAttribute(k_jacobi_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem)));
 	CK(cudaFuncSetAttribute(k_jacobi_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem)));
@@ -255,6 +262,7 @@ void nb_destroy(nb_context* ctx) {
 	if (!ctx) return;
 	cudaDeviceSynchronize();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+	if (ctx->side) { cudaStreamDestroy(ctx->side); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_join2); }
 	for (size_t i = 0; i < ctx->allocs.size(); ++i) cudaFree(ctx->allocs[i]);
 	delete ctx;
 }
@@ -488,12 +496,28 @@ int nb_apply_gravity_damping(nb_context* ctx, float time_step, float gravity, fl
 }
 
 // ---------------- contact cache ----------------
-int nb_read_cached_impulses(nb_context* ctx, void* stream) {
-	NB_RANGE("nb_read_cached_impulses");
+// The two halves of read_cached_impulses are independent of each other: (a) the tag ORDER of the contacts (one sort), (b) the cache
+// LOOKUP of every contact's impulse plus the entries of sleeping pairs that survive the frame.  nb_step runs (b) on a second stream.
+static int read_lookup(nb_context* ctx, cudaStream_t st, u32* flags, u32* offs, u32* block_sums) {
+	Launch L = { st, &ctx->launches, ctx->sms };
+	u32* counts = ctx->counts;
+	const u32 C = ctx->cfg.max_contacts, S = ctx->stride;
+	k_cache_lookup<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.tags, ctx->fin.features, ctx->cache_tags, ctx->cache_features, ctx->cache_data, ctx->impulses, counts);
+	k_culled_flags<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->cache_tags, ctx->sleeping, flags, counts);
+	ctx->launches += 2;
+	nb_scan<1>(L, flags, offs, S, counts + CNT_CACHE, 0, block_sums, counts + CNT_CULLED);
+	k_culled_scatter<<<GRID(C), NB_BLOCK, 0, st>>>(flags, offs, ctx->cache_tags, ctx->cache_features, ctx->cache_data,
+		ctx->culled_tags, ctx->culled_features, ctx->culled_data, counts);
+	++ctx->launches;
+	CK(cudaGetLastError());
+	return NB_OK;
+}
+
+static int read_sort(nb_context* ctx, void* stream) {
 	Launch L = mk_launch(ctx, stream);
 	cudaStream_t st = L.stream;
 	u32* counts = ctx->counts;
-	const u32 C = ctx->cfg.max_contacts, S = ctx->stride;
+	const u32 C = ctx->cfg.max_contacts;
 	// order contacts by tag: stable sort on the feature word, then on the pair word (nudge.cpp:4024-4044)
 	int cur;
 	if (ctx->contacts_internal && 2 * ctx->tagbits + 16 <= 64) {
@@ -508,15 +532,15 @@ int nb_read_cached_impulses(nb_context* ctx, void* stream) {
 		cur = nb_radix_sort(L, ctx->sb, counts + CNT_CONTACTS, 0, (int)(2 * ctx->tagbits), true, cur);
 	}
 	k_copy_u32<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sb.vals[cur], ctx->sorted, counts + CNT_CONTACTS);
-	k_cache_lookup<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->fin.tags, ctx->fin.features, ctx->cache_tags, ctx->cache_features, ctx->cache_data, ctx->impulses, counts);
-	k_culled_flags<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->cache_tags, ctx->sleeping, ctx->flags, counts);
-	ctx->launches += 3;
-	nb_scan<1>(L, ctx->flags, ctx->offs, S, counts + CNT_CACHE, 0, ctx->block_sums, counts + CNT_CULLED);
-	k_culled_scatter<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->flags, ctx->offs, ctx->cache_tags, ctx->cache_features, ctx->cache_data,
-		ctx->culled_tags, ctx->culled_features, ctx->culled_data, counts);
 	++ctx->launches;
 	CK(cudaGetLastError());
 	return NB_OK;
+}
+
+int nb_read_cached_impulses(nb_context* ctx, void* stream) {
+	NB_RANGE("nb_read_cached_impulses");
+	int r = read_sort(ctx, stream); if (r) return r;
+	return read_lookup(ctx, (cudaStream_t)stream, ctx->flags, ctx->offs, ctx->block_sums);
 }
 
 int nb_write_cached_impulses(nb_context* ctx, void* stream) {
@@ -597,7 +621,10 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 		k_jacobi_prepare<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->jcnt, ctx->rows, ctx->cstride, counts);
 		k_build_rows<true><<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts, ctx->jcnt);
 		ctx->launches += 3;
-		if (!ctx->defer_warm_start) { int r = launch_solve(ctx, 0, 1, st); if (r) return r; if (ctx->urow_n && (r = launch_user_rows(ctx, 1, st))) return r; }
+		if (!ctx->defer_warm_start) {
+			if (ctx->join_before_solve) { ctx->join_before_solve = false; CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); }   // the warm start reads the looked-up impulses
+			int r = launch_solve(ctx, 0, 1, st); if (r) return r; if (ctx->urow_n && (r = launch_user_rows(ctx, 1, st))) return r;
+		}
 		CK(cudaGetLastError());
 		return NB_OK;
 	}
@@ -615,12 +642,19 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 	k_batch_index<<<GRID(C), NB_BLOCK, 0, st>>>(ctx->sorted, ctx->fin.bodies, ctx->slot_of, ctx->slot_done, ctx->slot_left, ctx->slots_per_bucket,
 		ctx->offs, ctx->left_count, ctx->batch_of, ctx->slot_idx, ctx->rows.contact, ctx->cstride, ctx->sb.keys[0], ctx->sb.vals[0], ctx->batchbits, B, dummy_span, counts);
 	++ctx->launches;
+	if (ctx->rows_on_side) CK(cudaEventRecord(ctx->ev_fork2, st));   // slots are final here
 	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_ENTRIES, 0, (int)(chain_bodybits + ctx->batchbits), true, 0);
 	k_chain_heads<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->batchbits, B, ctx->chain_start, ctx->chain_len, counts); ++ctx->launches;
 	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, B, ctx->slot_idx, ctx->chain_start, ctx->chain_len, ctx->rows.wait, ctx->cstride, counts);
-	k_build_rows<false><<<GRID(ctx->cstride), NB_BLOCK, 0, st>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts, nullptr);
+	// the rows only need the slot of every contact (k_batch_index), not the chains: inside nb_step they are built on the second stream
+	// while the chain sort runs (rows_stream != st; joined before the solver)
+	cudaStream_t rows_stream = ctx->rows_on_side ? ctx->side : st;
+	if (ctx->rows_on_side) CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork2, 0));
+	k_build_rows<false><<<GRID(ctx->cstride), NB_BLOCK, 0, rows_stream>>>(ctx->fin.data, ctx->fin.bodies, ctx->xf, ctx->inertia, ctx->mom, ctx->rows, counts, nullptr);
+	if (ctx->rows_on_side) { CK(cudaEventRecord(ctx->ev_join2, ctx->side)); CK(cudaStreamWaitEvent(st, ctx->ev_join2, 0)); }
 	ctx->launches += 2;
 	if (!ctx->defer_warm_start) {  // warm start (nudge.cpp:4563-4632), then the user rows' accumulated impulses
+		if (ctx->join_before_solve) { ctx->join_before_solve = false; CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); }
 		int r = launch_solve(ctx, 0, 1, st); if (r) return r;
 		if (ctx->urow_n && (r = launch_user_rows(ctx, 1, st))) return r;
 	}
@@ -664,11 +698,25 @@ static int step_body(nb_context* ctx, float time_step, uint32_t iterations, floa
 	int r;
 	if ((r = nb_collide(ctx, stream))) return r;
 	if ((r = nb_apply_gravity_damping(ctx, time_step, gravity, damping, stream))) return r;
-	if ((r = nb_read_cached_impulses(ctx, stream))) return r;
+	const bool fork = ctx->overlap && stream != nullptr && !ctx->debug;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (fork) {
+		// branch A on the second stream: cache lookup + culled entries (needs the contacts and the sorted sleeping pairs, not the tag order);
+		// it joins before the solver's warm start reads the impulses.  Own scan scratch: the scheduler uses the main one meanwhile.
+		CK(cudaEventRecord(ctx->ev_fork, st)); CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+		if ((r = read_lookup(ctx, ctx->side, ctx->flags2, ctx->offs2, ctx->block_sums2))) return r;
+		CK(cudaEventRecord(ctx->ev_join, ctx->side));
+		if ((r = read_sort(ctx, stream))) return r;
+	}
+	else if ((r = nb_read_cached_impulses(ctx, stream))) return r;
 	ctx->defer_warm_start = iterations > 0 && !ctx->urow_n;  // warm start + sweeps in one solver launch (same arithmetic, same order); not with user rows between the sweeps
+	ctx->rows_on_side = fork && ctx->solver_mode == NB_SOLVER_PARITY;   // branch B: constraint rows while the chain sort runs
+	ctx->join_before_solve = fork;
 	r = nb_setup_contact_constraints(ctx, stream);
+	ctx->rows_on_side = false;
+	if (!r && ctx->join_before_solve) { ctx->join_before_solve = false; CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); }   // (setup joins itself when it runs the warm start)
 	if (!r) r = nb_apply_impulses(ctx, iterations, stream);
-	ctx->defer_warm_start = false;
+	ctx->defer_warm_start = false; ctx->join_before_solve = false;
 	if (r) return r;
 	if ((r = nb_update_cached_impulses(ctx, stream))) return r;
 	if ((r = nb_write_cached_impulses(ctx, stream))) return r;
