@@ -156,7 +156,11 @@ def run_sharded(args, rank, world, local):
         if k and k % 25 == 0:
             sim.reshard()
         sim.step()
-    sim.reshard()
+    torch.cuda.synchronize(); dist.barrier()
+    t_rs = time.perf_counter()
+    sim.reshard()                                   # host side (gather, nb_shard_partition, re-upload, new plan): reported, outside the timed region
+    torch.cuda.synchronize(); dist.barrier()
+    reshard_ms = (time.perf_counter() - t_rs) * 1e3
     for _ in range(2):
         sim.step()
 
@@ -253,7 +257,7 @@ def run_sharded(args, rank, world, local):
                        "presim_steps": args.presim, "parallelism": "one scene of %d bodies in %d x %d cells (x, z), one cell per GPU; halo = body radius + max radius + %.2f" % (g.n_bodies - 1, gx, gz, args.margin),
                        "value_definition": ("scene steps/s of the fixed-size scene" if strong else "scene steps/s x (total bodies / 65,536): 65,536-box-equivalent steps per second of the whole job"),
                        "scene_steps_per_s": rate, "l2": "flushed between timed steps (256 MiB write), flush excluded", "timing": "CUDA events per step, summed; max over ranks",
-                       "overflow_flags": int(ssum[6]),
+                       "overflow_flags": int(ssum[6]), "reshard_ms_host_side_untimed": reshard_ms,
                        "solver_mode": ("throughput (mass-splitting Jacobi) inside a rank" if args.solver == "throughput" else "exact reference Gauss-Seidel order inside a rank") + ", block-Jacobi across ranks"},
             "parity_check": parity,
             "e2e": {"value": ((g.n_bodies - 1) / unit_bodies) * K / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(ssum[4]), "d2h_bytes_per_step": int(ssum[5]),
