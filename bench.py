@@ -38,7 +38,7 @@ from nudge_b200 import scenes  # noqa: E402
 CONFIGS = {
     "c1": dict(workload="reference example scene: 1024 boxes + 1024 spheres falling onto ground, 8 solver iters (BASELINE.json configs[0]), settled",
                scene=lambda a, w: scenes.demo_scene(1024, 1024, iterations=a.iterations or 8), small=lambda a, seed: scenes.demo_scene(1024, 1024, iterations=a.iterations or 8, seed=seed),
-               presim=700, scaling="weak"),
+               presim=1700, scaling="weak"),   # the bodies fall from up to 300 units: ~940 steps until the last one lands
     "c2": dict(workload="64k boxes random drop onto ground plane, 8 solver iters (BASELINE.json configs[1]), settled pile",
                scene=lambda a, w: scenes.box_drop(a.boxes * w, iterations=a.iterations or 8, seed=2), small=lambda a, seed: scenes.box_drop(8191, iterations=a.iterations or 8, seed=seed),
                presim=900, scaling="weak"),
