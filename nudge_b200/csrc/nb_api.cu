@@ -588,22 +588,29 @@ static int launch_solve_jacobi(nb_context* ctx, int mode, u32 sweeps, cudaStream
 	return NB_OK;
 }
 
-static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) {
-	if (ctx->solver_mode == NB_SOLVER_THROUGHPUT) return launch_solve_jacobi(ctx, mode, sweeps, st);
+// the exact-order solver kernel alone, on a working copy `mw` that the caller has filled (k_mw_in or the sharded step's fused pull)
+static int launch_solve_core(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) {
 	Rows R = ctx->rows;
 	const float4* impulses = ctx->impulses;
 	float4* mw = ctx->mw;
 	u32* counts = ctx->counts;
-	const u32 B = ctx->B;
-	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw);
 	u32 backoff = ctx->solve_backoff_ns;
 	void* args[] = { &R, &impulses, &mw, &mode, &sweeps, &backoff, &counts };
 	if (mode) timing_begin(ctx, st);
 	if (ctx->coop_launch && (!ctx->capturing || ctx->graph_coop)) CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_blocks_solve), dim3(NB_BLOCK), args, 0, st));
 	else k_solve<<<ctx->coop_blocks_solve, NB_BLOCK, 0, st>>>(R, impulses, mw, mode, sweeps, backoff, counts);
 	if (mode) timing_end(ctx, st);
-	k_mw_out<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, mw, mode ? 1 : 0);
-	ctx->launches += 3;
+	++ctx->launches;
+	return NB_OK;
+}
+
+static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) {
+	if (ctx->solver_mode == NB_SOLVER_THROUGHPUT) return launch_solve_jacobi(ctx, mode, sweeps, st);
+	const u32 B = ctx->B;
+	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw);
+	int r = launch_solve_core(ctx, mode, sweeps, st); if (r) return r;
+	k_mw_out<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw, mode ? 1 : 0);
+	ctx->launches += 2;
 	return NB_OK;
 }
 

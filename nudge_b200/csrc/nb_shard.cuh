@@ -91,6 +91,92 @@ __global__ void __launch_bounds__(NB_BLOCK) k_shard_pull(float4* mom, ShardPlanD
 		mom[2 * P.ghost_local[i >> 1] + (i & 1)] = ld_volatile_f4(rows + i);
 }
 
+// ---- the same exchange fused into the solver's working-copy kernels (peer transport, exact-order solver) ----
+// Unfused, a sweep of the sharded step is  k_mw_in, k_solve, k_mw_out, k_shard_push, k_shard_pull;  fused it is
+// k_pull_mw_in, k_solve, k_mw_out_push: the push reads the rows it sends from the working copy the solver just left, the pull
+// writes the ghosts' rows into both the momentum array and the next working copy.  Same values, two launches less per sweep.
+
+// k_mw_out (nb_solver.cuh) + k_shard_push.  A pushed row is the BodyMomentum row k_mw_out writes: (velocity, unused0 kept,
+// angular velocity, unused1 = 0 if a contact touched the body in a sweep); computed from mw and the OLD row, so it does not matter
+// whether the block that copies the body back has run yet.
+__global__ void __launch_bounds__(NB_BLOCK) k_mw_out_push(u32 B, nb_body_momentum* momentum, const float4* mw, int mode, ShardPlanDev P, unsigned char* const* peers,
+														  u32 ghost_cap, u32 rank, u32 world, u32* epoch, u32* done) {
+	const u32 ep = *epoch + 1;
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+		float4* p = reinterpret_cast<float4*>(momentum + i);
+		float4 l = mw[2*i], w = mw[2*i + 1];
+		float4 ol = p[0], ow = p[1];
+		bool touched = asu(l.w) != 0;
+		p[0] = make_float4(l.x, l.y, l.z, ol.w);
+		p[1] = make_float4(w.x, w.y, w.z, (mode && touched) ? 0.0f : ow.w);
+	}
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_export; i += gridDim.x * blockDim.x) {
+		const u32 body = P.export_local[i];
+		const float4* p = reinterpret_cast<const float4*>(momentum + body);
+		float4 l = mw[2*body], w = mw[2*body + 1];
+		const bool touched = asu(l.w) != 0;
+		const float u0 = p[0].w, u1 = p[1].w;      // unused0 never changes here; unused1 only ever changes to what the rule below gives
+		l.w = u0; w.w = (mode && touched) ? 0.0f : u1;
+		for (u32 t = P.sub_off[i]; t < P.sub_off[i + 1]; ++t) {
+			const uint2 tg = P.sub_tgt[t];
+			float4* dst = reinterpret_cast<float4*>(peers[tg.x] + NB_SHARD_FLAG_WORDS * 4) + 2 * ((size_t)(ep & 1u) * ghost_cap + tg.y);
+			dst[0] = l; dst[1] = w;
+		}
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const u32 old = atomicAdd(done, 1u);
+		if (old == gridDim.x - 1) {
+			__threadfence_system();
+			for (u32 r = 0; r < world; ++r)
+				if (r != rank) st_release_sys(reinterpret_cast<u32*>(peers[r]) + rank, ep);
+			*done = 0;
+			*epoch = ep;
+		}
+	}
+}
+
+// k_shard_pull + k_mw_in: ghosts take their owner's row (into the momentum array AND the new working copy), everybody else's working
+// copy comes from the momentum array.  is_ghost[body] != 0 marks the ghost rows (they are skipped by the plain copy, so no two
+// blocks write the same working-copy row).
+__global__ void __launch_bounds__(NB_BLOCK) k_pull_mw_in(u32 B, nb_body_momentum* momentum, float4* mw, ShardPlanDev P, const unsigned char* is_ghost, unsigned char* inbox,
+														 u32 ghost_cap, u32 rank, u32 world, const u32* epoch, u32* counts, long long timeout_cycles) {
+	const u32 ep = *epoch;
+	__shared__ int ok;
+	if (threadIdx.x == 0) {
+		const u32* flags = reinterpret_cast<const u32*>(inbox);
+		const long long t0 = clock64();
+		int good = 1;
+		for (u32 r = 0; r < world && good; ++r) {
+			if (r == rank) continue;
+			while ((int)(ld_acquire_sys(flags + r) - ep) < 0) {
+				if (clock64() - t0 > timeout_cycles) { good = 0; atomicOr(&counts[CNT_OVERFLOW], OVF_EXCHANGE); break; }
+				__nanosleep(200);
+			}
+		}
+		ok = good;
+	}
+	__syncthreads();
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+		if (is_ghost[i] && ok) continue;
+		const float4* p = reinterpret_cast<const float4*>(momentum + i);
+		float4 l = p[0], w = p[1];
+		l.w = 0.0f; w.w = 0.0f;
+		mw[2*i] = l; mw[2*i + 1] = w;
+	}
+	if (!ok) return;
+	const float4* rows = reinterpret_cast<const float4*>(inbox + NB_SHARD_FLAG_WORDS * 4) + 2 * (size_t)(ep & 1u) * ghost_cap;
+	for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < P.n_ghost; j += gridDim.x * blockDim.x) {
+		const u32 body = P.ghost_local[j];
+		float4 l = ld_volatile_f4(rows + 2 * j), w = ld_volatile_f4(rows + 2 * j + 1);
+		float4* p = reinterpret_cast<float4*>(momentum + body);
+		p[0] = l; p[1] = w;
+		l.w = 0.0f; w.w = 0.0f;
+		mw[2*body] = l; mw[2*body + 1] = w;
+	}
+}
+
 // ---- NCCL bound at run time ----
 struct NcclApi {
 	void* lib;

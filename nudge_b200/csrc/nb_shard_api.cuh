@@ -10,7 +10,7 @@ struct nb_shard {
 	unsigned char* inbox; u32 ghost_cap; std::vector<unsigned char*> peers; unsigned char** peers_dev; std::vector<void*> opened; bool peers_ready;
 	u32* epoch; u32* done;
 	// plan (device copies)
-	u32* d_export_local; u32* d_sub_off; uint2* d_sub_tgt; u32* d_ghost_local; u32* d_ghost_src;
+	u32* d_export_local; u32* d_sub_off; uint2* d_sub_tgt; u32* d_ghost_local; u32* d_ghost_src; unsigned char* d_is_ghost; int fuse;
 	u32 cap_export, cap_ghost, cap_sub;
 	ShardPlanDev plan; u32 max_export; unsigned long long plan_version;
 	// NCCL transport buffers
@@ -48,7 +48,8 @@ int nb_shard_create(nb_context* ctx, uint32_t rank, uint32_t world, const void* 
 	ALLOC(sh->inbox, inbox_bytes);
 	ALLOC(sh->peers_dev, world); ALLOC(sh->epoch, 1); ALLOC(sh->done, 1);
 	ALLOC(sh->d_export_local, sh->cap_export); ALLOC(sh->d_sub_off, (size_t)sh->cap_export + 1); ALLOC(sh->d_sub_tgt, sh->cap_sub);
-	ALLOC(sh->d_ghost_local, sh->cap_ghost); ALLOC(sh->d_ghost_src, sh->cap_ghost);
+	ALLOC(sh->d_ghost_local, sh->cap_ghost); ALLOC(sh->d_ghost_src, sh->cap_ghost); ALLOC(sh->d_is_ghost, ctx->cfg.max_bodies);
+	{ const char* e = getenv("NB_SHARD_FUSE"); sh->fuse = e ? atoi(e) != 0 : 1; }
 	ALLOC(sh->d_export, 2 * (size_t)export_capacity); ALLOC(sh->d_gather, 2 * (size_t)export_capacity * world);
 	sh->peers.assign(world, nullptr); sh->peers[rank] = sh->inbox;
 	sh->graph_enabled = ctx->graph_enabled;
@@ -120,6 +121,11 @@ int nb_shard_plan(nb_shard* sh, const uint32_t* export_local, uint32_t n_export,
 	SCK(cudaMemcpy(sh->d_sub_off, n_export ? sub_off : &zero, sizeof(u32) * ((size_t)n_export + 1), cudaMemcpyHostToDevice));
 	if (n_sub) SCK(cudaMemcpy(sh->d_sub_tgt, tg.data(), sizeof(uint2) * n_sub, cudaMemcpyHostToDevice));
 	if (n_ghost) { SCK(cudaMemcpy(sh->d_ghost_local, ghost_local, sizeof(u32) * n_ghost, cudaMemcpyHostToDevice)); SCK(cudaMemcpy(sh->d_ghost_src, ghost_src, sizeof(u32) * n_ghost, cudaMemcpyHostToDevice)); }
+	{
+		std::vector<unsigned char> flag(ctx->cfg.max_bodies, 0);
+		for (u32 i = 0; i < n_ghost; ++i) flag[ghost_local[i]] = 1;
+		SCK(cudaMemcpy(sh->d_is_ghost, flag.data(), flag.size(), cudaMemcpyHostToDevice));
+	}
 	sh->plan.export_local = sh->d_export_local; sh->plan.sub_off = sh->d_sub_off; sh->plan.sub_tgt = sh->d_sub_tgt;
 	sh->plan.ghost_local = sh->d_ghost_local; sh->plan.ghost_src = sh->d_ghost_src; sh->plan.n_export = n_export; sh->plan.n_ghost = n_ghost;
 	sh->max_export = max_export;
@@ -154,12 +160,43 @@ int nb_shard_exchange(nb_shard* sh, int transport, void* stream) {
 	return NB_OK;
 }
 
+// peer transport + exact-order solver: the exchanges ride on the solver's working-copy kernels (k_mw_out_push / k_pull_mw_in)
+static int shard_solve_fused(nb_shard* sh, uint32_t iterations, cudaStream_t st) {
+	nb_context* ctx = sh->ctx;
+	const u32 B = ctx->B;
+	const ShardPlanDev P = sh->plan;
+	const unsigned gout = GRID(B), gin = GRID(B);
+	int r;
+	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw); ++ctx->launches;
+	if ((r = launch_solve_core(ctx, 0, 1, st))) return r;                                    // warm start (nudge.cpp:4563-4632)
+	k_mw_out_push<<<gout, NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw, 0, P, sh->peers_dev, sh->ghost_cap, sh->rank, sh->world, sh->epoch, sh->done); ++ctx->launches;
+	for (uint32_t i = 0; i < iterations; ++i) {
+		k_pull_mw_in<<<gin, NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw, P, sh->d_is_ghost, sh->inbox, sh->ghost_cap, sh->rank, sh->world, sh->epoch, ctx->counts, sh->pull_timeout_cycles); ++ctx->launches;
+		if ((r = launch_solve_core(ctx, 1, 1, st))) return r;
+		k_mw_out_push<<<gout, NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw, 1, P, sh->peers_dev, sh->ghost_cap, sh->rank, sh->world, sh->epoch, sh->done); ++ctx->launches;
+	}
+	k_shard_pull<<<std::max(1u, std::min(GRID(2 * std::max(P.n_ghost, 1u)), 64u)), NB_BLOCK, 0, st>>>((float4*)ctx->mom, P, sh->inbox, sh->ghost_cap, sh->rank, sh->world, sh->epoch, ctx->counts, sh->pull_timeout_cycles);
+	++ctx->launches;
+	SCK(cudaGetLastError());
+	return NB_OK;
+}
+
 static int shard_step_body(nb_shard* sh, float time_step, uint32_t iterations, float gravity, float damping, int transport, void* stream) {
 	nb_context* ctx = sh->ctx;
 	int r;
 	if ((r = nb_collide(ctx, stream))) return r;
 	if ((r = nb_apply_gravity_damping(ctx, time_step, gravity, damping, stream))) return r;
 	if ((r = nb_read_cached_impulses(ctx, stream))) return r;
+	if (sh->world > 1 && transport == NB_SHARD_PEER && sh->fuse && sh->peers_ready && ctx->solver_mode == NB_SOLVER_PARITY && !ctx->urow_n) {
+		ctx->defer_warm_start = true;                          // setup without its warm-start launch: it runs inside shard_solve_fused
+		r = nb_setup_contact_constraints(ctx, stream);
+		ctx->defer_warm_start = false;
+		if (r) return r;
+		if ((r = shard_solve_fused(sh, iterations, (cudaStream_t)stream))) return r;
+		if ((r = nb_update_cached_impulses(ctx, stream))) return r;
+		if ((r = nb_write_cached_impulses(ctx, stream))) return r;
+		return nb_advance(ctx, time_step, stream);
+	}
 	if ((r = nb_setup_contact_constraints(ctx, stream))) return r;        // includes the warm start
 	if ((r = nb_shard_exchange(sh, transport, stream))) return r;
 	for (uint32_t i = 0; i < iterations; ++i) {
