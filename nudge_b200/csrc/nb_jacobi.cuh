@@ -71,13 +71,15 @@ __global__ void __launch_bounds__(NB_BLOCK) k_jacobi_prepare(const u32* sorted, 
 	}
 }
 
-// sums v[0..5] over runs of equal `key` among neighbouring lanes; the first lane of each run ends up with the run's total
-NB_DEV void seg_reduce6(u32 key, float (&v)[6]) {
+// sums v[0..5] over RUNS of equal `key` among neighbouring lanes (a run = maximal stretch of adjacent lanes with the same key; the same
+// key may come back later in the warp as a separate run); the first lane of each run ends up with the run's total.  `heads` has a bit
+// for every lane that starts a run: lane i may take lane i+d's partial sum iff no run starts in (i, i+d].
+NB_DEV void seg_reduce6(u32 heads, float (&v)[6]) {
 	const u32 lane = threadIdx.x & 31;
+	const u32 later = lane < 31 ? heads >> (lane + 1) : 0u;   // bit k: a run starts at lane + 1 + k
 	#pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
-		const u32 k2 = __shfl_down_sync(0xffffffffu, key, d);
-		const bool take = lane + d < 32 && k2 == key;
+		const bool take = lane + d < 32 && (later & ((1u << d) - 1u)) == 0;
 		#pragma unroll
 		for (int i = 0; i < 6; ++i) { float t = __shfl_down_sync(0xffffffffu, v[i], d); if (take) v[i] += t; }
 	}
@@ -116,41 +118,45 @@ __global__ void __launch_bounds__(NJ_TILE, 2) k_jacobi_sweep(Rows R, const float
 		}
 	};
 
+	// Two-stage ring, both stages in flight: a thread copies its 46 values of the current tile into registers as soon as the tile
+	// has landed, the CTA synchronises once, and the producer immediately refills that stage with the tile after next — so the
+	// gathers, the arithmetic, the state stores and the reductions of tile k overlap the loads of tiles k+1 AND k+2, and no warp
+	// waits at an end-of-tile barrier for the slowest warp (ncu, first version: 5.3 of 11 stall cycles per issue were that barrier).
 	u32 it = 0;
 	u32 tile = blockIdx.x;
 	if (tile < tiles) issue(tile, 0);
+	if (tile + gridDim.x < tiles) issue(tile + gridDim.x, 1);
 	for (; tile < tiles; tile += gridDim.x, ++it) {
 		const u32 stage = it & 1;
-		if (tile + gridDim.x < tiles) issue(tile + gridDim.x, stage ^ 1);   // that stage was drained before the barrier ending the previous iteration
 		while (!mbar_try_wait(&sm.bar[stage], (it >> 1) & 1)) { }
 		const u32 slot = tile * NJ_TILE + threadIdx.x;
 		const bool valid = slot < n;
 		const float* T = &sm.tile[stage][0][threadIdx.x];
 		const u32 a = valid ? asu(T[NJ_PLANE_A * NJ_TILE]) : 0u, b = valid ? asu(T[NJ_PLANE_B * NJ_TILE]) : 0u;
+		float rv[ROW_PLANES_TOTAL], st[3];
+		#pragma unroll
+		for (int k = 0; k < ROW_PLANES_TOTAL; ++k) rv[k] = T[k * NJ_TILE];
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) st[k] = T[(ROW_PLANES_TOTAL + k) * NJ_TILE];
+		__syncthreads();                                               // the stage is drained
+		if (tile + 2 * gridDim.x < tiles) issue(tile + 2 * gridDim.x, stage);
 		float da[6] = { 0, 0, 0, 0, 0, 0 }, db[6] = { 0, 0, 0, 0, 0, 0 };
 		if (valid) {
 			float4 al = V[2*a], aw = V[2*a + 1], bl = V[2*b], bw = V[2*b + 1];
 			const float4 al0 = al, aw0 = aw, bl0 = bl, bw0 = bw;
-			if (WARM) warm_start_contact_p(T, NJ_TILE, impulses[R.contact[slot]], R.state + slot, S, al, aw, bl, bw, FastMath());
-			else {
-				float rv[ROW_PLANES_TOTAL], st[3];
-				#pragma unroll
-				for (int k = 0; k < ROW_PLANES_TOTAL; ++k) rv[k] = T[k * NJ_TILE];
-				#pragma unroll
-				for (int k = 0; k < 3; ++k) st[k] = T[(ROW_PLANES_TOTAL + k) * NJ_TILE];
-				solve_contact(R, slot, rv, st, al, aw, bl, bw, FastMath());
-			}
+			if (WARM) warm_start_contact_p(rv, 1, impulses[R.contact[slot]], R.state + slot, S, al, aw, bl, bw, FastMath());
+			else solve_contact(R, slot, rv, st, al, aw, bl, bw, FastMath());
 			da[0] = al.x - al0.x; da[1] = al.y - al0.y; da[2] = al.z - al0.z; da[3] = aw.x - aw0.x; da[4] = aw.y - aw0.y; da[5] = aw.z - aw0.z;
 			db[0] = bl.x - bl0.x; db[1] = bl.y - bl0.y; db[2] = bl.z - bl0.z; db[3] = bw.x - bw0.x; db[4] = bw.y - bw0.y; db[5] = bw.z - bw0.z;
 		}
 		// per-body accumulation across the warp, then one vector reduction per half row from the head lane of each run
 		const u32 lane = threadIdx.x & 31;
-		seg_reduce6(a, da);
-		seg_reduce6(b, db);
 		const u32 pa = __shfl_up_sync(0xffffffffu, a, 1), pb = __shfl_up_sync(0xffffffffu, b, 1);
-		if (a && (lane == 0 || pa != a)) { red_add_v4(D + 2*a, da[0], da[1], da[2]); red_add_v4(D + 2*a + 1, da[3], da[4], da[5]); }
-		if (b && (lane == 0 || pb != b)) { red_add_v4(D + 2*b, db[0], db[1], db[2]); red_add_v4(D + 2*b + 1, db[3], db[4], db[5]); }
-		__syncthreads();   // everybody is done with this stage: the producer may refill it in the next iteration
+		const bool head_a = lane == 0 || pa != a, head_b = lane == 0 || pb != b;
+		seg_reduce6(__ballot_sync(0xffffffffu, head_a), da);
+		seg_reduce6(__ballot_sync(0xffffffffu, head_b), db);
+		if (a && head_a) { red_add_v4(D + 2*a, da[0], da[1], da[2]); red_add_v4(D + 2*a + 1, da[3], da[4], da[5]); }
+		if (b && head_b) { red_add_v4(D + 2*b, db[0], db[1], db[2]); red_add_v4(D + 2*b + 1, db[3], db[4], db[5]); }
 	}
 }
 

@@ -13,6 +13,6 @@ for _ in range(4): g.step_staged()
 c = g.counts(); print("contacts", c.contacts, "overflow", c.overflow)
 PY
 for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/nb_sanitize_case.py > gpurun_out/sanitize_$tool.log 2>&1
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 env PYTHONPATH=$PWD python /tmp/nb_sanitize_case.py > gpurun_out/sanitize_$tool.log 2>&1
   echo "$tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_$tool.log | tail -1)"
 done

@@ -28,10 +28,10 @@ def _vel(g):
     return g.momentum["velocity"].astype(np.float64), g.momentum["angular_velocity"].astype(np.float64)
 
 
-@pytest.mark.parametrize("scene", [scenes.demo_scene(400, 400, iterations=8, spread=4.0, height=40.0), scenes.box_drop(3000, iterations=8)], ids=["mixed", "boxes"])
+@pytest.mark.parametrize("scene", [scenes.demo_scene(400, 400, iterations=8, spread=4.0, height=10.0), scenes.box_drop(3000, iterations=8, density_L=30.0)], ids=["mixed", "boxes"])
 def test_split_rows_warm_start_and_sweeps_equal_the_cpu_restatement(scene):
     g = nudge_b200.Sim(scene, debug=True)
-    for _ in range(150):
+    for _ in range(260):
         g.step_staged()
     g.collide(); g.apply_gravity_damping(); g.read_cached_impulses()
     g.download_bodies(); m0 = g.momentum.copy()
