@@ -19,8 +19,8 @@
 // Jacobi-style body-velocity updates"):
 //   * slots are in TAG order (slot i = i-th contact of the contact-cache order), so a tile of 256 slots is 46 contiguous 1 KB
 //     segments (41 row planes + 3 state planes + body indices a, b).  Warp 0 of the CTA issues them as 1-D bulk async copies
-//     (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes -> UBLKCP) into a two-stage shared-memory ring, tracked by one
-//     mbarrier per stage; rows stream with an L2 evict-first policy so that the body arrays (velocities + accumulators, 64 B/body)
+//     (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes -> UBLKCP) into a shared-memory stage tracked by an mbarrier (the registers of the
+//     CTA are the second stage of the ring); rows stream with an L2 evict-first policy so that the body arrays (velocities + accumulators, 64 B/body)
 //     stay L2 resident while hundreds of MB of rows pass through.
 //   * tag order sorts by (body B, body A, feature): lanes of a warp that share a body are neighbours, so the per-body velocity
 //     changes are first summed across the warp with a segmented shuffle reduction and only the head lane of each run issues the
@@ -35,9 +35,11 @@
 #define NJ_PLANE_A (ROW_PLANES_TOTAL + 3)
 #define NJ_PLANE_B (ROW_PLANES_TOTAL + 4)
 
+// ONE shared-memory stage per CTA: a thread moves its 46 values into registers as soon as the tile has landed, so the registers are
+// the second stage of the ring and the shared stage can be refilled at once.  47 KB per CTA -> three CTAs (24 warps) per SM.
 struct JacobiSmem {
-	float tile[2][NJ_PLANES][NJ_TILE];
-	unsigned long long bar[2];
+	float tile[NJ_PLANES][NJ_TILE];
+	unsigned long long bar;
 };
 
 NB_DEV u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -73,12 +75,16 @@ __global__ void __launch_bounds__(NB_BLOCK) k_jacobi_prepare(const u32* sorted, 
 
 // sums v[0..5] over RUNS of equal `key` among neighbouring lanes (a run = maximal stretch of adjacent lanes with the same key; the same
 // key may come back later in the warp as a separate run); the first lane of each run ends up with the run's total.  `heads` has a bit
-// for every lane that starts a run: lane i may take lane i+d's partial sum iff no run starts in (i, i+d].
+// for every lane that starts a run: lane i may take lane i+d's partial sum iff no run starts in (i, i+d].  The number of doubling
+// steps follows the longest run of THIS warp (warp-uniform): runs are short (a body has a handful of contacts), so two or three
+// steps instead of five, and none at all when every lane is its own run.
 NB_DEV void seg_reduce6(u32 heads, float (&v)[6]) {
 	const u32 lane = threadIdx.x & 31;
 	const u32 later = lane < 31 ? heads >> (lane + 1) : 0u;   // bit k: a run starts at lane + 1 + k
-	#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
+	// length of the run this lane starts or sits in, measured to its end: distance to the next head (or to lane 32)
+	const u32 to_end = later ? (u32)__ffs((int)later) : 32u - lane;
+	const u32 longest = __reduce_max_sync(0xffffffffu, (heads >> lane) & 1u ? to_end : 0u);
+	for (u32 d = 1; d < longest; d <<= 1) {
 		const bool take = lane + d < 32 && (later & ((1u << d) - 1u)) == 0;
 		#pragma unroll
 		for (int i = 0; i < 6; ++i) { float t = __shfl_down_sync(0xffffffffu, v[i], d); if (take) v[i] += t; }
@@ -88,7 +94,7 @@ NB_DEV void seg_reduce6(u32 heads, float (&v)[6]) {
 // One Jacobi pass over all contacts.  WARM: the warm start (nudge.cpp:4563-4632) instead of a PGS sweep.
 // V[2*body], V[2*body+1] = (velocity, -), (angular velocity, -) at the start of the pass (read only); D = accumulators.
 template<bool WARM>
-__global__ void __launch_bounds__(NJ_TILE, 2) k_jacobi_sweep(Rows R, const float4* impulses, const float4* __restrict__ V, float4* D, const u32* counts) {
+__global__ void __launch_bounds__(NJ_TILE, 3) k_jacobi_sweep(Rows R, const float4* impulses, const float4* __restrict__ V, float4* D, const u32* counts) {
 	extern __shared__ __align__(128) unsigned char nj_smem_raw[];
 	JacobiSmem& sm = *reinterpret_cast<JacobiSmem*>(nj_smem_raw);
 	const u32 n = min(counts[CNT_CONTACTS], 8u * counts[CNT_BATCHES]);
@@ -97,15 +103,15 @@ __global__ void __launch_bounds__(NJ_TILE, 2) k_jacobi_sweep(Rows R, const float
 	unsigned long long policy;
 	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 	if (threadIdx.x == 0) {
-		mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1);
+		mbar_init(&sm.bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
 	// warp 0 is the producer: one expect_tx for the whole tile, then 46 bulk copies of 1 KB spread over its lanes
-	auto issue = [&](u32 tile, u32 stage) {
+	auto issue = [&](u32 tile) {
 		if (threadIdx.x < 32) {
-			if (threadIdx.x == 0) mbar_expect_tx(&sm.bar[stage], NJ_PLANES * NJ_TILE * 4);
+			if (threadIdx.x == 0) mbar_expect_tx(&sm.bar, NJ_PLANES * NJ_TILE * 4);
 			__syncwarp();
 			const size_t t0 = (size_t)tile * NJ_TILE;
 			for (u32 k = threadIdx.x; k < NJ_PLANES; k += 32) {
@@ -113,38 +119,38 @@ __global__ void __launch_bounds__(NJ_TILE, 2) k_jacobi_sweep(Rows R, const float
 				if (k < ROW_PLANES_TOTAL) src = R.plane + (size_t)k * S + t0;
 				else if (k < ROW_PLANES_TOTAL + 3) src = R.state + (size_t)(k - ROW_PLANES_TOTAL) * S + t0;
 				else src = (k == NJ_PLANE_A ? R.a : R.b) + t0;
-				bulk_g2s(&sm.tile[stage][k][0], src, NJ_TILE * 4, &sm.bar[stage], policy);
+				bulk_g2s(&sm.tile[k][0], src, NJ_TILE * 4, &sm.bar, policy);
 			}
 		}
 	};
 
-	// Two-stage ring, both stages in flight: a thread copies its 46 values of the current tile into registers as soon as the tile
-	// has landed, the CTA synchronises once, and the producer immediately refills that stage with the tile after next — so the
-	// gathers, the arithmetic, the state stores and the reductions of tile k overlap the loads of tiles k+1 AND k+2, and no warp
-	// waits at an end-of-tile barrier for the slowest warp (ncu, first version: 5.3 of 11 stall cycles per issue were that barrier).
+	// Ring of two: shared memory holds the tile in flight, registers hold the tile being solved.  Per tile: wait for the bulk copies,
+	// read the body indices and start the velocity gathers (L2), copy the 44 row/state values into registers, ONE CTA barrier, refill
+	// the shared stage with the next tile at once, then solve, store the impulse state and accumulate - all of which overlaps the
+	// next tile's copies.
 	u32 it = 0;
 	u32 tile = blockIdx.x;
-	if (tile < tiles) issue(tile, 0);
-	if (tile + gridDim.x < tiles) issue(tile + gridDim.x, 1);
+	if (tile < tiles) issue(tile);
 	for (; tile < tiles; tile += gridDim.x, ++it) {
-		const u32 stage = it & 1;
-		while (!mbar_try_wait(&sm.bar[stage], (it >> 1) & 1)) { }
+		while (!mbar_try_wait(&sm.bar, it & 1)) { }
 		const u32 slot = tile * NJ_TILE + threadIdx.x;
 		const bool valid = slot < n;
-		const float* T = &sm.tile[stage][0][threadIdx.x];
+		const float* T = &sm.tile[0][threadIdx.x];
 		const u32 a = valid ? asu(T[NJ_PLANE_A * NJ_TILE]) : 0u, b = valid ? asu(T[NJ_PLANE_B * NJ_TILE]) : 0u;
+		float4 al = V[2*a], aw = V[2*a + 1], bl = V[2*b], bw = V[2*b + 1];      // body 0 for invalid lanes: zeros, harmless
+		float4 ci = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		if (WARM && valid) ci = impulses[R.contact[slot]];
 		float rv[ROW_PLANES_TOTAL], st[3];
 		#pragma unroll
 		for (int k = 0; k < ROW_PLANES_TOTAL; ++k) rv[k] = T[k * NJ_TILE];
 		#pragma unroll
 		for (int k = 0; k < 3; ++k) st[k] = T[(ROW_PLANES_TOTAL + k) * NJ_TILE];
 		__syncthreads();                                               // the stage is drained
-		if (tile + 2 * gridDim.x < tiles) issue(tile + 2 * gridDim.x, stage);
+		if (tile + gridDim.x < tiles) issue(tile + gridDim.x);
 		float da[6] = { 0, 0, 0, 0, 0, 0 }, db[6] = { 0, 0, 0, 0, 0, 0 };
 		if (valid) {
-			float4 al = V[2*a], aw = V[2*a + 1], bl = V[2*b], bw = V[2*b + 1];
 			const float4 al0 = al, aw0 = aw, bl0 = bl, bw0 = bw;
-			if (WARM) warm_start_contact_p(rv, 1, impulses[R.contact[slot]], R.state + slot, S, al, aw, bl, bw, FastMath());
+			if (WARM) warm_start_contact_p(rv, 1, ci, R.state + slot, S, al, aw, bl, bw, FastMath());
 			else solve_contact(R, slot, rv, st, al, aw, bl, bw, FastMath());
 			da[0] = al.x - al0.x; da[1] = al.y - al0.y; da[2] = al.z - al0.z; da[3] = aw.x - aw0.x; da[4] = aw.y - aw0.y; da[5] = aw.z - aw0.z;
 			db[0] = bl.x - bl0.x; db[1] = bl.y - bl0.y; db[2] = bl.z - bl0.z; db[3] = bw.x - bw0.x; db[4] = bw.y - bw0.y; db[5] = bw.z - bw0.z;

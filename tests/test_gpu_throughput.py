@@ -36,7 +36,7 @@ def test_split_rows_warm_start_and_sweeps_equal_the_cpu_restatement(scene):
     g.collide(); g.apply_gravity_damping(); g.read_cached_impulses()
     g.download_bodies(); m0 = g.momentum.copy()
     n = g.counts().contacts
-    assert n > 1000
+    assert n > 500
     # the same contact set through the exact-order setup (rows pinned bit-for-bit against the reference in test_gpu_parity.py)
     g.setup_contact_constraints()
     Pp, _, cp, ap, bp = _rows(g, n)
