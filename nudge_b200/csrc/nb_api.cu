@@ -41,7 +41,7 @@ struct nb_context {
 	bool contacts_internal;  // the current contact set came from nb_collide (not nb_upload_contacts)
 	u32 solve_backoff_ns;
 	// throughput mode (nb_set_solver_mode): mass-splitting Jacobi, nb_jacobi.cuh
-	int solver_mode; u32* jcnt; float4* jd; int jacobi_blocks;
+	int solver_mode; u32* jcnt; float4* jd; int jacobi_blocks1, jacobi_blocks2, jacobi_stages;
 	// CUDA-event timing of the dominant solver kernel (nb_debug_timing): bench.py's roofline numerator is measured live
 	int timing; cudaEvent_t tev[2][64]; int tev_n; bool tev_made;
 	// nb_step overlaps independent branches of the step on a second stream (fork/join with events; also inside the captured graph)
@@ -228,13 +228,18 @@ int nb_create(const nb_config* config, nb_context** out) {
 	CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
 	ctx->solver_mode = NB_SOLVER_PARITY;
-	CK(cudaFuncSetAttribute(k_jacobi_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem)));
-	CK(cudaFuncSetAttribute(k_jacobi_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem)));
+	CK(cudaFuncSetAttribute(k_jacobi_sweep<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem<1>)));
+	CK(cudaFuncSetAttribute(k_jacobi_sweep<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem<1>)));
+	CK(cudaFuncSetAttribute(k_jacobi_sweep<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem<2>)));
+	CK(cudaFuncSetAttribute(k_jacobi_sweep<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem<2>)));
 	{
-		int per = 0;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_jacobi_sweep<false>, NJ_TILE, sizeof(JacobiSmem)));
-		if (per < 1) { ctx->error = "k_jacobi_sweep does not fit on an SM"; return NB_ERR_CUDA; }
-		ctx->jacobi_blocks = ctx->sms * per;   // persistent: every CTA walks tiles blockIdx.x, + gridDim.x, ...
+		int per1 = 0, per2 = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per1, k_jacobi_sweep<false, 1>, NJ_TILE, sizeof(JacobiSmem<1>)));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_jacobi_sweep<false, 2>, NJ_TILE, sizeof(JacobiSmem<2>)));
+		if (per1 < 1 || per2 < 1) { ctx->error = "k_jacobi_sweep does not fit on an SM"; return NB_ERR_CUDA; }
+		ctx->jacobi_blocks1 = ctx->sms * per1; ctx->jacobi_blocks2 = ctx->sms * per2;   // persistent: every CTA walks tiles blockIdx.x, + gridDim.x, ...
+		ctx->jacobi_stages = 0;   // 0 = by body count at launch
+		if (const char* e = getenv("NB_JACOBI_STAGES")) ctx->jacobi_stages = atoi(e);
 		if (const char* e = getenv("NB_SOLVER")) ctx->solver_mode = !strcmp(e, "throughput") ? NB_SOLVER_THROUGHPUT : NB_SOLVER_PARITY;
 	}
 	ctx->pair_keys = ctx->sb.keys[0];
@@ -572,15 +577,19 @@ static int launch_solve_jacobi(nb_context* ctx, int mode, u32 sweeps, cudaStream
 	const u32 B = ctx->B;
 	k_mw_in<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw);
 	++ctx->launches;
+	// two tiles per CTA in flight once the body arrays (64 B per body: velocities + accumulators) take a large share of L2, else more CTAs
+	const int stages = ctx->jacobi_stages == 1 || ctx->jacobi_stages == 2 ? ctx->jacobi_stages : (B > 600000u ? 2 : 1);
 	if (mode == 0 || mode == 2) {
-		k_jacobi_sweep<true><<<ctx->jacobi_blocks, NJ_TILE, sizeof(JacobiSmem), st>>>(R, ctx->impulses, ctx->mw, ctx->jd, ctx->counts);
+		if (stages == 1) k_jacobi_sweep<true, 1><<<ctx->jacobi_blocks1, NJ_TILE, sizeof(JacobiSmem<1>), st>>>(R, ctx->impulses, ctx->mw, ctx->jd, ctx->counts);
+		else k_jacobi_sweep<true, 2><<<ctx->jacobi_blocks2, NJ_TILE, sizeof(JacobiSmem<2>), st>>>(R, ctx->impulses, ctx->mw, ctx->jd, ctx->counts);
 		k_jacobi_apply<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mw, ctx->jd, ctx->jcnt);
 		ctx->launches += 2;
 	}
 	if (mode != 0)
 		for (u32 w = 0; w < sweeps; ++w) {
 			timing_begin(ctx, st);
-			k_jacobi_sweep<false><<<ctx->jacobi_blocks, NJ_TILE, sizeof(JacobiSmem), st>>>(R, ctx->impulses, ctx->mw, ctx->jd, ctx->counts);
+			if (stages == 1) k_jacobi_sweep<false, 1><<<ctx->jacobi_blocks1, NJ_TILE, sizeof(JacobiSmem<1>), st>>>(R, ctx->impulses, ctx->mw, ctx->jd, ctx->counts);
+			else k_jacobi_sweep<false, 2><<<ctx->jacobi_blocks2, NJ_TILE, sizeof(JacobiSmem<2>), st>>>(R, ctx->impulses, ctx->mw, ctx->jd, ctx->counts);
 			timing_end(ctx, st);
 			k_jacobi_apply<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mw, ctx->jd, ctx->jcnt);
 			ctx->launches += 2;

@@ -35,11 +35,15 @@
 #define NJ_PLANE_A (ROW_PLANES_TOTAL + 3)
 #define NJ_PLANE_B (ROW_PLANES_TOTAL + 4)
 
-// ONE shared-memory stage per CTA: a thread moves its 46 values into registers as soon as the tile has landed, so the registers are
-// the second stage of the ring and the shared stage can be refilled at once.  47 KB per CTA -> three CTAs (24 warps) per SM.
+// STAGES shared-memory stages per CTA.  A thread moves its 46 values into registers as soon as a tile has landed, so the registers are
+// one more stage of the ring and a shared stage can be refilled at once.  STAGES = 1: 47 KB per CTA, three CTAs (24 warps) per SM —
+// best when the body arrays are small next to L2 (measured: 256 k-body scenes 0.70-0.78 of the HBM peak);  STAGES = 2: 94 KB, two
+// CTAs per SM but two tiles per CTA in flight — best on the 1 M-body scene (0.71 vs 0.65).  nb_api.cu picks by body count
+// (NB_JACOBI_STAGES overrides).
+template<int STAGES>
 struct JacobiSmem {
-	float tile[NJ_PLANES][NJ_TILE];
-	unsigned long long bar;
+	float tile[STAGES][NJ_PLANES][NJ_TILE];
+	unsigned long long bar[STAGES];
 };
 
 NB_DEV u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -93,25 +97,25 @@ NB_DEV void seg_reduce6(u32 heads, float (&v)[6]) {
 
 // One Jacobi pass over all contacts.  WARM: the warm start (nudge.cpp:4563-4632) instead of a PGS sweep.
 // V[2*body], V[2*body+1] = (velocity, -), (angular velocity, -) at the start of the pass (read only); D = accumulators.
-template<bool WARM>
-__global__ void __launch_bounds__(NJ_TILE, 3) k_jacobi_sweep(Rows R, const float4* impulses, const float4* __restrict__ V, float4* D, const u32* counts) {
+template<bool WARM, int STAGES>
+__global__ void __launch_bounds__(NJ_TILE, 4 - STAGES) k_jacobi_sweep(Rows R, const float4* impulses, const float4* __restrict__ V, float4* D, const u32* counts) {
 	extern __shared__ __align__(128) unsigned char nj_smem_raw[];
-	JacobiSmem& sm = *reinterpret_cast<JacobiSmem*>(nj_smem_raw);
+	JacobiSmem<STAGES>& sm = *reinterpret_cast<JacobiSmem<STAGES>*>(nj_smem_raw);
 	const u32 n = min(counts[CNT_CONTACTS], 8u * counts[CNT_BATCHES]);
 	const u32 tiles = (n + NJ_TILE - 1) / NJ_TILE;
 	const u32 S = R.stride;
 	unsigned long long policy;
 	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 	if (threadIdx.x == 0) {
-		mbar_init(&sm.bar, 1);
+		for (int k = 0; k < STAGES; ++k) mbar_init(&sm.bar[k], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
 	// warp 0 is the producer: one expect_tx for the whole tile, then 46 bulk copies of 1 KB spread over its lanes
-	auto issue = [&](u32 tile) {
+	auto issue = [&](u32 tile, u32 stage) {
 		if (threadIdx.x < 32) {
-			if (threadIdx.x == 0) mbar_expect_tx(&sm.bar, NJ_PLANES * NJ_TILE * 4);
+			if (threadIdx.x == 0) mbar_expect_tx(&sm.bar[stage], NJ_PLANES * NJ_TILE * 4);
 			__syncwarp();
 			const size_t t0 = (size_t)tile * NJ_TILE;
 			for (u32 k = threadIdx.x; k < NJ_PLANES; k += 32) {
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(NJ_TILE, 3) k_jacobi_sweep(Rows R, const float
 				if (k < ROW_PLANES_TOTAL) src = R.plane + (size_t)k * S + t0;
 				else if (k < ROW_PLANES_TOTAL + 3) src = R.state + (size_t)(k - ROW_PLANES_TOTAL) * S + t0;
 				else src = (k == NJ_PLANE_A ? R.a : R.b) + t0;
-				bulk_g2s(&sm.tile[k][0], src, NJ_TILE * 4, &sm.bar, policy);
+				bulk_g2s(&sm.tile[stage][k][0], src, NJ_TILE * 4, &sm.bar[stage], policy);
 			}
 		}
 	};
@@ -130,12 +134,14 @@ __global__ void __launch_bounds__(NJ_TILE, 3) k_jacobi_sweep(Rows R, const float
 	// next tile's copies.
 	u32 it = 0;
 	u32 tile = blockIdx.x;
-	if (tile < tiles) issue(tile);
+	#pragma unroll
+	for (int k = 0; k < STAGES; ++k) if (tile + k * gridDim.x < tiles) issue(tile + k * gridDim.x, k);
 	for (; tile < tiles; tile += gridDim.x, ++it) {
-		while (!mbar_try_wait(&sm.bar, it & 1)) { }
+		const u32 stage = STAGES == 1 ? 0u : (it & 1u);
+		while (!mbar_try_wait(&sm.bar[stage], (STAGES == 1 ? it : (it >> 1)) & 1u)) { }
 		const u32 slot = tile * NJ_TILE + threadIdx.x;
 		const bool valid = slot < n;
-		const float* T = &sm.tile[0][threadIdx.x];
+		const float* T = &sm.tile[stage][0][threadIdx.x];
 		const u32 a = valid ? asu(T[NJ_PLANE_A * NJ_TILE]) : 0u, b = valid ? asu(T[NJ_PLANE_B * NJ_TILE]) : 0u;
 		float4 al = V[2*a], aw = V[2*a + 1], bl = V[2*b], bw = V[2*b + 1];      // body 0 for invalid lanes: zeros, harmless
 		float4 ci = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(NJ_TILE, 3) k_jacobi_sweep(Rows R, const float
 		#pragma unroll
 		for (int k = 0; k < 3; ++k) st[k] = T[(ROW_PLANES_TOTAL + k) * NJ_TILE];
 		__syncthreads();                                               // the stage is drained
-		if (tile + gridDim.x < tiles) issue(tile + gridDim.x);
+		if (tile + STAGES * gridDim.x < tiles) issue(tile + STAGES * gridDim.x, stage);
 		float da[6] = { 0, 0, 0, 0, 0, 0 }, db[6] = { 0, 0, 0, 0, 0, 0 };
 		if (valid) {
 			const float4 al0 = al, aw0 = aw, bl0 = bl, bw0 = bw;
