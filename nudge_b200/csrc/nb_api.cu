@@ -45,7 +45,7 @@ struct nb_context {
 	// CUDA-event timing of the dominant solver kernel (nb_debug_timing): bench.py's roofline numerator is measured live
 	int timing; cudaEvent_t tev[2][64]; int tev_n; bool tev_made;
 	// nb_step overlaps independent branches of the step on a second stream (fork/join with events; also inside the captured graph)
-	bool rows_on_side, join_before_solve; int overlap; cudaStream_t side; cudaEvent_t ev_fork, ev_fork2, ev_join, ev_join2; u32* flags2; u32* offs2; u32* block_sums2;
+	bool rows_on_side, join_before_solve, zero_chain_len; int overlap; cudaStream_t side; cudaEvent_t ev_fork, ev_fork2, ev_join, ev_join2; u32* flags2; u32* offs2; u32* block_sums2;
 	// user constraint rows (nb_upload_constraint_rows, nb_rows_api.cuh)
 	nb_constraint_row* urows; u32 urow_cap, urow_n, urow_levels; unsigned long long urow_version; std::vector<u32> urow_level_off, urow_order;
 
@@ -662,6 +662,7 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 	++ctx->launches;
 	if (ctx->rows_on_side) CK(cudaEventRecord(ctx->ev_fork2, st));   // slots are final here
 	int cur = nb_radix_sort(L, ctx->sb, counts + CNT_ENTRIES, 0, (int)(chain_bodybits + ctx->batchbits), true, 0);
+	if (ctx->zero_chain_len) CK(cudaMemsetAsync(ctx->chain_len, 0, sizeof(u32) * B, st));
 	k_chain_heads<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->batchbits, B, ctx->chain_start, ctx->chain_len, counts); ++ctx->launches;
 	k_waits<<<GRID(2 * C), NB_BLOCK, 0, st>>>(ctx->sb.keys[cur], ctx->sb.vals[cur], ctx->batchbits, B, ctx->slot_idx, ctx->chain_start, ctx->chain_len, ctx->rows.wait, ctx->cstride, counts);
 	// the rows only need the slot of every contact (k_batch_index), not the chains: inside nb_step they are built on the second stream

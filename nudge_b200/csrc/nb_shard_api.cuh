@@ -10,7 +10,10 @@ struct nb_shard {
 	unsigned char* inbox; u32 ghost_cap; std::vector<unsigned char*> peers; unsigned char** peers_dev; std::vector<void*> opened; bool peers_ready;
 	u32* epoch; u32* done;
 	// plan (device copies)
-	u32* d_export_local; u32* d_sub_off; uint2* d_sub_tgt; u32* d_ghost_local; u32* d_ghost_src; unsigned char* d_is_ghost; int fuse;
+	u32* d_export_local; u32* d_sub_off; uint2* d_sub_tgt; u32* d_ghost_local; u32* d_ghost_src; unsigned char* d_is_ghost;
+	int fuse;   // 0: exchange kernels between the solver launches; 1: exchange fused into the working-copy kernels; 2: hand-over inside ONE solver launch (k_solve_flow)
+	// dataflow hand-over (fuse == 2): pass-indexed inbox behind the per-sweep one in the same IPC allocation
+	u32 passes_cap; size_t inbox2_offset; float4** peer_inbox2_dev; u32* d_export_row; u32* d_ghost_slot; int flow_blocks;
 	u32 cap_export, cap_ghost, cap_sub;
 	ShardPlanDev plan; u32 max_export; unsigned long long plan_version;
 	// NCCL transport buffers
@@ -44,12 +47,20 @@ int nb_shard_create(nb_context* ctx, uint32_t rank, uint32_t world, const void* 
 	sh->ctx = ctx; sh->rank = rank; sh->world = world; sh->ghost_cap = ghost_capacity;
 	sh->cap_export = export_capacity; sh->cap_ghost = ghost_capacity; sh->cap_sub = 4 * export_capacity + 64;
 	CK(cudaSetDevice(ctx->cfg.device));
-	size_t inbox_bytes = NB_SHARD_FLAG_WORDS * 4 + sizeof(float4) * 2 * 2 * (size_t)ghost_capacity;
+	sh->passes_cap = 24;
+	sh->inbox2_offset = NB_SHARD_FLAG_WORDS * 4 + sizeof(float4) * 2 * 2 * (size_t)ghost_capacity;
+	size_t inbox_bytes = sh->inbox2_offset + sizeof(float4) * 2 * 2 * (size_t)sh->passes_cap * ghost_capacity;
 	ALLOC(sh->inbox, inbox_bytes);
+	ALLOC(sh->peer_inbox2_dev, world); ALLOC(sh->d_export_row, ctx->cfg.max_bodies); ALLOC(sh->d_ghost_slot, ctx->cfg.max_bodies);
+	{
+		int per_sm = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_flow, NB_BLOCK, 0));
+		sh->flow_blocks = per_sm > 0 ? ctx->sms * per_sm : 0;
+	}
 	ALLOC(sh->peers_dev, world); ALLOC(sh->epoch, 1); ALLOC(sh->done, 1);
 	ALLOC(sh->d_export_local, sh->cap_export); ALLOC(sh->d_sub_off, (size_t)sh->cap_export + 1); ALLOC(sh->d_sub_tgt, sh->cap_sub);
 	ALLOC(sh->d_ghost_local, sh->cap_ghost); ALLOC(sh->d_ghost_src, sh->cap_ghost); ALLOC(sh->d_is_ghost, ctx->cfg.max_bodies);
-	{ const char* e = getenv("NB_SHARD_FUSE"); sh->fuse = e ? atoi(e) != 0 : 1; }
+	{ const char* e = getenv("NB_SHARD_FUSE"); sh->fuse = e ? atoi(e) : 1; }
 	ALLOC(sh->d_export, 2 * (size_t)export_capacity); ALLOC(sh->d_gather, 2 * (size_t)export_capacity * world);
 	sh->peers.assign(world, nullptr); sh->peers[rank] = sh->inbox;
 	sh->graph_enabled = ctx->graph_enabled;
@@ -94,7 +105,13 @@ int nb_shard_open_peer(nb_shard* sh, uint32_t peer, const void* handle) {
 	}
 	bool all = true;
 	for (u32 r = 0; r < sh->world; ++r) all = all && sh->peers[r];
-	if (all) { SCK(cudaMemcpy(sh->peers_dev, sh->peers.data(), sizeof(unsigned char*) * sh->world, cudaMemcpyHostToDevice)); sh->peers_ready = true; }
+	if (all) {
+		SCK(cudaMemcpy(sh->peers_dev, sh->peers.data(), sizeof(unsigned char*) * sh->world, cudaMemcpyHostToDevice));
+		std::vector<float4*> p2(sh->world);
+		for (u32 r = 0; r < sh->world; ++r) p2[r] = reinterpret_cast<float4*>(sh->peers[r] + sh->inbox2_offset);
+		SCK(cudaMemcpy(sh->peer_inbox2_dev, p2.data(), sizeof(float4*) * sh->world, cudaMemcpyHostToDevice));
+		sh->peers_ready = true;
+	}
 	return NB_OK;
 }
 
@@ -123,8 +140,12 @@ int nb_shard_plan(nb_shard* sh, const uint32_t* export_local, uint32_t n_export,
 	if (n_ghost) { SCK(cudaMemcpy(sh->d_ghost_local, ghost_local, sizeof(u32) * n_ghost, cudaMemcpyHostToDevice)); SCK(cudaMemcpy(sh->d_ghost_src, ghost_src, sizeof(u32) * n_ghost, cudaMemcpyHostToDevice)); }
 	{
 		std::vector<unsigned char> flag(ctx->cfg.max_bodies, 0);
-		for (u32 i = 0; i < n_ghost; ++i) flag[ghost_local[i]] = 1;
+		std::vector<u32> erow(ctx->cfg.max_bodies, NB_NONE), gslot(ctx->cfg.max_bodies, NB_NONE);
+		for (u32 i = 0; i < n_ghost; ++i) { flag[ghost_local[i]] = 1; gslot[ghost_local[i]] = i; }
+		for (u32 i = 0; i < n_export; ++i) if (sub_off[i + 1] > sub_off[i]) erow[export_local[i]] = i;
 		SCK(cudaMemcpy(sh->d_is_ghost, flag.data(), flag.size(), cudaMemcpyHostToDevice));
+		SCK(cudaMemcpy(sh->d_export_row, erow.data(), sizeof(u32) * erow.size(), cudaMemcpyHostToDevice));
+		SCK(cudaMemcpy(sh->d_ghost_slot, gslot.data(), sizeof(u32) * gslot.size(), cudaMemcpyHostToDevice));
 	}
 	sh->plan.export_local = sh->d_export_local; sh->plan.sub_off = sh->d_sub_off; sh->plan.sub_tgt = sh->d_sub_tgt;
 	sh->plan.ghost_local = sh->d_ghost_local; sh->plan.ghost_src = sh->d_ghost_src; sh->plan.n_export = n_export; sh->plan.n_ghost = n_ghost;
@@ -181,6 +202,32 @@ static int shard_solve_fused(nb_shard* sh, uint32_t iterations, cudaStream_t st)
 	return NB_OK;
 }
 
+// peer transport + exact-order solver, fuse == 2: warm start and all sweeps in ONE solver launch, ghosts handed over by the dataflow
+// (k_solve_flow); the step ends with one regular push/pull of the final rows, which is also the handshake between the ranks
+static int shard_solve_flow(nb_shard* sh, uint32_t iterations, cudaStream_t st) {
+	nb_context* ctx = sh->ctx;
+	const u32 B = ctx->B;
+	const ShardPlanDev P = sh->plan;
+	ShardFlow X;
+	X.inbox2 = reinterpret_cast<float4*>(sh->inbox + sh->inbox2_offset); X.peer_inbox2 = sh->peer_inbox2_dev;
+	X.export_row = sh->d_export_row; X.ghost_slot = sh->d_ghost_slot; X.ghost_cap = sh->ghost_cap; X.passes_cap = sh->passes_cap;
+	const u32 passes = iterations + 1;
+	k_mw_in_flow<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw, ctx->chain_len, X, P, sh->epoch, passes); ++ctx->launches;
+	Rows R = ctx->rows; const float4* impulses = ctx->impulses; float4* mw = ctx->mw; u32* counts = ctx->counts; u32 hop = ctx->solve_backoff_ns; u32 sweeps = iterations;
+	const u32* epoch = sh->epoch; long long timeout = sh->pull_timeout_cycles;
+	void* args[] = { &R, &impulses, &mw, &sweeps, &hop, &counts, &X, (void*)&P, &epoch, &timeout };
+	timing_begin(ctx, st);
+	if (ctx->coop_launch && (!ctx->capturing || ctx->graph_coop)) SCK(cudaLaunchCooperativeKernel((void*)k_solve_flow, dim3(sh->flow_blocks), dim3(NB_BLOCK), args, 0, st));
+	else k_solve_flow<<<sh->flow_blocks, NB_BLOCK, 0, st>>>(R, impulses, mw, sweeps, hop, counts, X, P, epoch, timeout);
+	timing_end(ctx, st);
+	++ctx->launches;
+	k_mw_out_push<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw, 1, P, sh->peers_dev, sh->ghost_cap, sh->rank, sh->world, sh->epoch, sh->done);
+	k_shard_pull<<<std::max(1u, std::min(GRID(2 * std::max(P.n_ghost, 1u)), 64u)), NB_BLOCK, 0, st>>>((float4*)ctx->mom, P, sh->inbox, sh->ghost_cap, sh->rank, sh->world, sh->epoch, ctx->counts, sh->pull_timeout_cycles);
+	ctx->launches += 2;
+	SCK(cudaGetLastError());
+	return NB_OK;
+}
+
 static int shard_step_body(nb_shard* sh, float time_step, uint32_t iterations, float gravity, float damping, int transport, void* stream) {
 	nb_context* ctx = sh->ctx;
 	int r;
@@ -188,11 +235,13 @@ static int shard_step_body(nb_shard* sh, float time_step, uint32_t iterations, f
 	if ((r = nb_apply_gravity_damping(ctx, time_step, gravity, damping, stream))) return r;
 	if ((r = nb_read_cached_impulses(ctx, stream))) return r;
 	if (sh->world > 1 && transport == NB_SHARD_PEER && sh->fuse && sh->peers_ready && ctx->solver_mode == NB_SOLVER_PARITY && !ctx->urow_n) {
-		ctx->defer_warm_start = true;                          // setup without its warm-start launch: it runs inside shard_solve_fused
+		const bool flow = sh->fuse == 2 && sh->flow_blocks > 0 && iterations > 0 && iterations + 1 <= sh->passes_cap;
+		ctx->defer_warm_start = true;                          // setup without its warm-start launch: it runs inside the fused solve
+		ctx->zero_chain_len = flow;                            // "no contacts on this rank" must read as chain length 0
 		r = nb_setup_contact_constraints(ctx, stream);
-		ctx->defer_warm_start = false;
+		ctx->defer_warm_start = false; ctx->zero_chain_len = false;
 		if (r) return r;
-		if ((r = shard_solve_fused(sh, iterations, (cudaStream_t)stream))) return r;
+		if ((r = flow ? shard_solve_flow(sh, iterations, (cudaStream_t)stream) : shard_solve_fused(sh, iterations, (cudaStream_t)stream))) return r;
 		if ((r = nb_update_cached_impulses(ctx, stream))) return r;
 		if ((r = nb_write_cached_impulses(ctx, stream))) return r;
 		return nb_advance(ctx, time_step, stream);
