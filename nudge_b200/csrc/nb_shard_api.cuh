@@ -60,7 +60,7 @@ int nb_shard_create(nb_context* ctx, uint32_t rank, uint32_t world, const void* 
 	ALLOC(sh->peers_dev, world); ALLOC(sh->epoch, 1); ALLOC(sh->done, 1);
 	ALLOC(sh->d_export_local, sh->cap_export); ALLOC(sh->d_sub_off, (size_t)sh->cap_export + 1); ALLOC(sh->d_sub_tgt, sh->cap_sub);
 	ALLOC(sh->d_ghost_local, sh->cap_ghost); ALLOC(sh->d_ghost_src, sh->cap_ghost); ALLOC(sh->d_is_ghost, ctx->cfg.max_bodies);
-	{ const char* e = getenv("NB_SHARD_FUSE"); sh->fuse = e ? atoi(e) : 1; }
+	{ const char* e = getenv("NB_SHARD_FUSE"); sh->fuse = e ? atoi(e) : 2; }
 	ALLOC(sh->d_export, 2 * (size_t)export_capacity); ALLOC(sh->d_gather, 2 * (size_t)export_capacity * world);
 	sh->peers.assign(world, nullptr); sh->peers[rank] = sh->inbox;
 	sh->graph_enabled = ctx->graph_enabled;
