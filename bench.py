@@ -121,6 +121,22 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def pin_body_arrays(sim):
+    """Moves the caller-side body arrays of a Sim into pinned host memory (what an application that streams state in and out every
+    step would use) and re-points the BodyData struct at them.  Returns the owning tensors (keep them alive)."""
+    import torch
+    from nudge_b200 import abi
+    keep = {}
+    for name in ("transforms", "properties", "momentum", "idle"):
+        a = getattr(sim, name)
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        v = t.numpy()[:a.nbytes].view(a.dtype)
+        v[:] = a
+        keep[name] = t; setattr(sim, name, v)
+    sim.bodies = abi.BodyData(abi.ptr(sim.transforms), abi.ptr(sim.properties), abi.ptr(sim.momentum), abi.ptr(sim.idle), len(sim.transforms))
+    return keep
+
+
 def settle_gpu(sim, steps):
     for _ in range(steps):
         sim.step()
@@ -228,6 +244,8 @@ def run_sharded(args, rank, world, local):
     # end to end: host state of the local bodies in and out every step
     h2d = sum(getattr(sim.sim, n).nbytes for n in ("transforms", "properties", "momentum", "idle"))
     d2h = sum(getattr(sim.sim, n).nbytes for n in ("transforms", "momentum", "idle"))
+    pinned = pin_body_arrays(sim.sim)
+    sim.sim.download_bodies()
     for _ in range(2):
         sim.sim.upload_bodies(); sim.step(); sim.sim.download_bodies()
     dist.barrier(); torch.cuda.synchronize()
@@ -367,16 +385,7 @@ def run_ours(args):
     cnt = sim.counts()
 
     # ---- end to end through the public API with HOST buffers (pinned): upload state, step, read state back ----
-    nb = scene.n_bodies
-    pinned = {}
-    for name in ("transforms", "properties", "momentum", "idle"):
-        a = getattr(sim, name)
-        t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
-        v = t.numpy().view(a.dtype)[:len(a)]
-        v[:] = a
-        pinned[name] = (t, v); setattr(sim, name, v)
-    from nudge_b200 import abi
-    sim.bodies = abi.BodyData(abi.ptr(sim.transforms), abi.ptr(sim.properties), abi.ptr(sim.momentum), abi.ptr(sim.idle), nb)
+    pinned = pin_body_arrays(sim)
     sim.download_bodies()
     h2d = sum(getattr(sim, n).nbytes for n in ("transforms", "properties", "momentum", "idle"))
     d2h = sum(getattr(sim, n).nbytes for n in ("transforms", "momentum", "idle"))
