@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(NB_BLOCK) k_inertia(u32 B, const nb_transform*
 #define NB_SCHED_REGSETS 4
 #define NB_SCHED_REGPOS (2 * NB_SCHED_REGSETS)
 #define NB_SCHED_SHARED 504
-#define NB_SCHED_MAXV (NB_SCHED_REGPOS + NB_SCHED_SHARED - 1)
+#define NB_SCHED_MAXV (NB_SCHED_REGPOS + NB_SCHED_SHARED - 1)   // positions held on chip; beyond that the list spills to global memory
 
 // Parallel pre-pass for the replay: the body pair of every contact in tag order with the body-0 substitution of
 // nudge.cpp:4238-4240 applied, and `back` = distance (in contacts of the same bucket, 1..7) to the nearest earlier contact of
@@ -176,14 +176,24 @@ __global__ void __launch_bounds__(NB_BLOCK) k_sched_prep(const u32* sorted, cons
 // conflict are accepted in parallel (they are exactly the ones the sequential first-fit would put there), and only the
 // conflicting contact runs the general search.  A lone warp pays ~8 cycles per instruction, so instructions per contact
 // are what matters here.
+// A list longer than the on-chip positions (a body with thousands of contacts: all of them conflict with each other, each opens its
+// own slot) SPILLS to global memory: positions >= NB_SCHED_REGPOS + NB_SCHED_SHARED live in spill_ent / spill_uid (per bucket,
+// `spill_cap` positions, all entries NB_NONE between launches: the kernel clears what it used).  The reference has no limit here.
 __global__ void __launch_bounds__(32) k_schedule(const uint2* cab, const uint8_t* back, u32* slot_of, u32* slot_done, u32* slot_left, u32 slots_per_bucket,
-												 u32* complete_flag, u32* left_count /*[16]*/, u32* counts) {
+												 u32* complete_flag, u32* left_count /*[16]*/, u32* spill_ent, u32* spill_uid, u32 spill_cap, u32* counts) {
 	__shared__ u32 S_ent[NB_SCHED_SHARED][16];
 	__shared__ u32 S_uid[NB_SCHED_REGPOS + NB_SCHED_SHARED];
 	const u32 bucket = blockIdx.x, lane = threadIdx.x, half = lane >> 4, ent = lane & 15, cidx = lane & 7;
 	const u32 n = counts[CNT_CONTACTS];
 	for (u32 k = lane; k < NB_SCHED_SHARED * 16; k += 32) (&S_ent[0][0])[k] = NB_NONE;
 	__syncwarp();
+	u32* const G_ent = spill_ent + (size_t)bucket * spill_cap * 16;
+	u32* const G_uid = spill_uid + (size_t)bucket * spill_cap;
+	u32 spill_high = 0;   // positions of the spill area this launch has touched (warp uniform)
+	const u32 ONCHIP = NB_SCHED_REGPOS + NB_SCHED_SHARED;
+	// entries / uid of a list position that is not in registers (pos >= NB_SCHED_REGPOS)
+	auto ent_of = [&](u32 pos) -> u32* { return pos < ONCHIP ? &S_ent[pos - NB_SCHED_REGPOS][0] : G_ent + (size_t)(pos - ONCHIP) * 16; };
+	auto uid_of = [&](u32 pos) -> u32* { return pos < ONCHIP ? &S_uid[pos] : G_uid + (pos - ONCHIP); };
 	u32 vcount = 0, next_uid = 0;
 	u32 f0 = 0, uid0 = 0;  // fill count and uid of list position 0 (warp uniform)
 	u32 reg[NB_SCHED_REGSETS];
@@ -208,23 +218,23 @@ __global__ void __launch_bounds__(32) k_schedule(const uint2* cab, const uint8_t
 			for (u32 k = 0; k < NB_SCHED_REGSETS; ++k) if (k == (last >> 1)) src = reg[k];
 			v = __shfl_sync(0xffffffffu, src, 16 * (last & 1) + ent);
 		}
-		else v = S_ent[last - NB_SCHED_REGPOS][ent];
-		u32 last_uid = S_uid[last];
+		else v = ent_of(last)[ent];
+		u32 last_uid = *uid_of(last);
 		__syncwarp();
 		if (j != last) {
 			if (j < NB_SCHED_REGPOS) {
 				#pragma unroll
 				for (u32 k = 0; k < NB_SCHED_REGSETS; ++k) if (k == (j >> 1) && half == jh) reg[k] = v;
 			}
-			else if (lane < 16) S_ent[j - NB_SCHED_REGPOS][lane] = v;
-			if (lane == 0) S_uid[j] = last_uid;
+			else if (lane < 16) ent_of(j)[lane] = v;
+			if (lane == 0) *uid_of(j) = last_uid;
 			if (j == 0) uid0 = last_uid;
 		}
 		if (last < NB_SCHED_REGPOS) {  // the vacated last position becomes empty again
 			#pragma unroll
 			for (u32 k = 0; k < NB_SCHED_REGSETS; ++k) if (k == (last >> 1) && half == (last & 1)) reg[k] = NB_NONE;
 		}
-		else if (lane < 16) S_ent[last - NB_SCHED_REGPOS][lane] = NB_NONE;
+		else if (lane < 16) ent_of(last)[lane] = NB_NONE;
 		--vcount;
 		if (j == 0) f0 = __popc(__ballot_sync(0xffffffffu, reg[0] != NB_NONE) & 0xffu);
 		__syncwarp();
@@ -243,17 +253,18 @@ __global__ void __launch_bounds__(32) k_schedule(const uint2* cab, const uint8_t
 			}
 		}
 		if (j == NB_NONE) {  // all eight register positions conflict: continue in shared memory, two positions per round
-			for (u32 pb = 0; ; pb += 2) {
+			for (u32 pb = 0; ; pb += 2) {   // shared positions, then the spill area; the position right after the list is all empty: the search ends there at the latest
 				u32 pos = pb + half;
-				if (pb >= NB_SCHED_SHARED) return false;
-				u32 v = pos < NB_SCHED_SHARED ? S_ent[pos][ent] : ca;
+				if (pb >= NB_SCHED_SHARED + spill_cap) return false;
+				u32 v = pos < NB_SCHED_SHARED ? S_ent[pos][ent] : (pos < NB_SCHED_SHARED + spill_cap ? G_ent[(size_t)(pos - NB_SCHED_SHARED) * 16 + ent] : ca);
 				u32 hit = __ballot_sync(0xffffffffu, v == ca || v == cb);
 				u32 occ = __ballot_sync(0xffffffffu, v != NB_NONE);
 				if (!(hit & 0xffffu)) { j = NB_SCHED_REGPOS + pb; f = __popc(occ & 0xffu); break; }
 				if (!(hit >> 16)) { j = NB_SCHED_REGPOS + pb + 1; f = __popc((occ >> 16) & 0xffu); break; }
 			}
 		}
-		if (j >= NB_SCHED_MAXV) return false;
+		if (j >= ONCHIP + spill_cap - 1) return false;   // keeps one always-empty position behind the list (the reference's sentinel, nudge.cpp:4225-4227)
+		if (j >= ONCHIP) spill_high = max(spill_high, j - ONCHIP + 1);
 		if (j < NB_SCHED_REGPOS) {
 			u32 jh = j & 1;
 			#pragma unroll
@@ -265,18 +276,18 @@ __global__ void __launch_bounds__(32) k_schedule(const uint2* cab, const uint8_t
 			if (j == 0) f0 = f + 1;
 		}
 		else {
-			if (lane == 0) { S_ent[j - NB_SCHED_REGPOS][f] = ca; S_ent[j - NB_SCHED_REGPOS][8 + f] = cb; }
+			if (lane == 0) { u32* e = ent_of(j); e[f] = ca; e[8 + f] = cb; }
 			__syncwarp();
 		}
 		u32 uid;
 		if (j == vcount) {  // the sentinel was taken: a new slot (f is 0)
 			uid = next_uid++;
-			if (lane == 0) { S_uid[j] = uid; done[uid] = NB_NONE; }
+			if (lane == 0) { *uid_of(j) = uid; done[uid] = NB_NONE; }
 			if (j == 0) uid0 = uid;
 			++vcount;
 			__syncwarp();
 		}
-		else uid = j ? S_uid[j] : uid0;
+		else uid = j ? *uid_of(j) : uid0;
 		if (lane == 0) slot_of[i] = (uid << 3) | f;
 		if (f == 7) {
 			if (lane == 0) { done[uid] = i; complete_flag[i] = 1; }
@@ -371,8 +382,10 @@ __global__ void __launch_bounds__(32) k_schedule(const uint2* cab, const uint8_t
 	}
 	// leftovers are flushed bucket-major in list order (nudge.cpp:4316-4338)
 	__syncwarp();
-	for (u32 jj = lane; jj < vcount; jj += 32) left[S_uid[jj]] = jj;
+	for (u32 jj = lane; jj < vcount; jj += 32) left[*uid_of(jj)] = jj;
 	if (lane == 0) left_count[bucket] = vcount;
+	__syncwarp();
+	for (u32 k = lane; k < spill_high * 16; k += 32) G_ent[k] = NB_NONE;   // leave the spill area empty for the next launch
 }
 
 // batch index and slot (batch*8 + lane) of every contact + the (body, batch) chain entries
