@@ -375,7 +375,12 @@ __global__ void __launch_bounds__(32) k_schedule(const uint2* cab, const uint8_t
 			}
 			if (cm && s < steps) {  // the contact at s conflicts with position 0: general first-fit
 				u32 ca = __shfl_sync(0xffffffffu, my_ca, s), cb = __shfl_sync(0xffffffffu, my_cb, s);
-				if (!place_general(base + 16 * s, ca, cb)) { if (lane == 0) atomicOr(&counts[CNT_OVERFLOW], OVF_SCHED); return; }
+				if (!place_general(base + 16 * s, ca, cb)) {   // the list outgrew even the spill area: report, leave the spill area clean
+					if (lane == 0) atomicOr(&counts[CNT_OVERFLOW], OVF_SCHED);
+					__syncwarp();
+					for (u32 k = lane; k < spill_high * 16; k += 32) G_ent[k] = NB_NONE;
+					return;
+				}
 				++s;
 			}
 		}

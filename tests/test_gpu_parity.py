@@ -325,21 +325,26 @@ def test_nb_step_graph_replay_equals_staged_calls_and_oracle():
     assert b.counts().overflow == 0 and a.counts().contacts == b.counts().contacts > 0
 
 
-def test_hub_body_beyond_scheduler_capacity_reports_overflow_instead_of_hanging():
-    """one dynamic body with more contacts than the batch scheduler's open-slot list holds (16 buckets x 511 slots) used to
-    leave a partial schedule behind and the dataflow solver waited forever.  Now the schedule is published empty, the step finishes,
-    and the overflow is reported (nb_counts.overflow & 4, NB_ERR_OVERFLOW from nb_download_contacts)."""
-    s = scenes.hub_platform(55, iterations=4)      # 3025 boxes x 4 contacts on the platform's body
-    g = nudge_b200.Sim(s)
-    g.step_staged()
-    c = g.counts()
-    assert c.contacts > 8176 + 16, c.contacts
-    assert c.overflow & 4 and c.batches == 0
+def test_hub_body_spills_the_scheduler_list_and_overflow_is_reported_not_hung():
+    """one dynamic body with more contacts than the batch scheduler's on-chip slot list holds (16 buckets x 511 slots) used to
+    leave a partial schedule behind and the dataflow solver waited forever.  Now (a) the list spills to global memory - the reference
+    has no limit there - and the scene runs bit-identically to the oracle, and (b) when the constraint rows cannot hold the resulting
+    batches the schedule is published EMPTY, the step finishes and the overflow is reported (nb_counts.overflow & 4)."""
+    s = scenes.hub_platform(55, iterations=4)      # 3025 boxes x 4 contacts on the platform's body: 756 mutually conflicting contacts per bucket
+    o, g = _pair(s)
+    _steps(o, g, 3)
+    assert g.counts().contacts > 8176 + 16 and g.counts().overflow == 0
+    # the same scene with room for the contacts but not for one batch per platform contact
+    small = nudge_b200.Sim(s, contact_capacity=16000)
+    small.step_staged()
+    c = small.counts()
+    assert c.contacts > 8176 + 16 and (c.overflow & 4) and c.batches == 0
     with pytest.raises(nudge_b200.NudgeError):
-        g.download_contacts()
-    # a hub below the limit runs normally and matches the oracle
-    o, g2 = _pair(scenes.hub_platform(30, iterations=4))     # 900 boxes, 3600 contacts on one body
-    _steps(o, g2, 3)
+        small.download_contacts()
+    small.step_staged()                            # and the next step runs (no stale spill state, no hang)
+    assert small.counts().overflow & 4
+    o2, g2 = _pair(scenes.hub_platform(30, iterations=4))     # a hub inside the on-chip list
+    _steps(o2, g2, 3)
 
 
 def test_two_simulations_on_two_streams_step_concurrently():
