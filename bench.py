@@ -199,12 +199,15 @@ def run_sharded(args, rank, world, local):
         s0 = snapshot()
         res = {}
         for t in ("nccl", "peer", "host"):
+            if t == "peer" and not getattr(sim, "peer_ok", True):
+                res[t] = None
+                continue
             restore(s0)
             for _ in range(3):
                 sim.step(t)
             r_ = snapshot()
             res[t] = (r_["transforms"].tobytes(), r_["momentum"].tobytes(), r_["idle"].tobytes())
-        same = torch.tensor([float(res["nccl"] == res["host"]), float(res["peer"] == res["host"])], device="cuda")
+        same = torch.tensor([float(res["nccl"] == res["host"]), float(res["peer"] is None or res["peer"] == res["host"])], device="cuda")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         parity = {"steps": 3, "nccl_equals_host_exchange": bool(same[0] > 0), "peer_equals_host_exchange": bool(same[1] > 0),
                   "what": "3 steps from the same state through each transport; transforms, momentum and idle counters of every rank compared bit for bit"}
@@ -233,10 +236,14 @@ def run_sharded(args, rank, world, local):
         dist.barrier()
         return float(sum(a.elapsed_time(b) for a, b in ev)), n_launch
 
-    other = "nccl" if args.transport == "peer" else "peer"
-    other_ms, _ = timed(other)
+    main_transport = sim.transport                      # "nccl" if the peer inboxes could not be opened on this box
+    peer_ok = getattr(sim, "peer_ok", True)
+    other = "nccl" if main_transport == "peer" else "peer"
+    other_ms = float("nan")
+    if peer_ok or other == "nccl":
+        other_ms, _ = timed(other)
     sampler = ClockSampler(local); sampler.start()
-    total_ms, launches = timed(args.transport)
+    total_ms, launches = timed(main_transport)
     sampler.stop_flag = True
     graphed = sim.sim.shard_graph_active()
     cnt = sim.sim.counts()
@@ -270,7 +277,8 @@ def run_sharded(args, rank, world, local):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "config": args.config, "bodies_total": int(g.n_bodies), "bodies_per_gpu_owned": int(ssum[1] / world), "ghost_bodies_per_gpu": int(ssum[2] / world),
                        "exchanged_rows_per_gpu_per_sweep": int(ssum[3] / world), "solver_iterations": int(g.iterations), "contacts_incl_ghost_copies": int(ssum[0]),
-                       "transport": args.transport, "exchange": exch[args.transport], "other_transport": other, "other_transport_scene_steps_per_s": K / (other_ms * 1e-3),
+                       "transport": main_transport, "exchange": exch[main_transport], "other_transport": other, "other_transport_scene_steps_per_s": (K / (other_ms * 1e-3) if other_ms == other_ms else None),
+                       "peer_memory_available": bool(peer_ok),
                        "step_call": ("nb_shard_step: one CUDA-graph replay per step (kernels + exchanges)" if graphed else "nb_shard_step: plain launches"),
                        "presim_steps": args.presim, "parallelism": "one scene of %d bodies in %d x %d cells (x, z), one cell per GPU; halo = body radius + max radius + %.2f" % (g.n_bodies - 1, gx, gz, args.margin),
                        "value_definition": ("scene steps/s of the fixed-size scene" if strong else "scene steps/s x (total bodies / 65,536): 65,536-box-equivalent steps per second of the whole job"),

@@ -163,9 +163,20 @@ class ShardedSim:
             sim.shard_create(self.rank, self.world, ids[0], self.cap_bodies, self.cap_bodies)
             handles = [None] * self.world
             dist.all_gather_object(handles, sim.shard_ipc_handle(), group=self.group)
-            for p in range(self.world):
-                if p != self.rank:
-                    sim.shard_open_peer(p, handles[p])
+            ok = True
+            try:
+                for p in range(self.world):
+                    if p != self.rank:
+                        sim.shard_open_peer(p, handles[p])
+            except Exception as e:  # noqa: BLE001 - CUDA IPC can be unavailable (container settings, no peer access): use the collective
+                ok = False; self.peer_error = repr(e)
+            oks = [None] * self.world
+            dist.all_gather_object(oks, ok, group=self.group)
+            self.peer_ok = all(oks)
+            if not self.peer_ok and self.transport == "peer":
+                if not self.nccl:
+                    raise RuntimeError("peer-memory inboxes could not be opened and the shard has no NCCL communicator: %s" % getattr(self, "peer_error", "a peer failed"))
+                self.transport = "nccl"          # every rank takes the same decision: the flags were all-gathered
             self.shard_ready = True
         p = self.plan
         sim.shard_plan(p["export_local"], p["sub_off"], p["sub_rank"], p["sub_slot"], p["ghost_local"], p["ghost_src"], p["max_export"])
