@@ -144,7 +144,6 @@ __global__ void __launch_bounds__(NB_BLOCK) k_inertia(u32 B, const nb_transform*
 #define NB_SCHED_REGSETS 4
 #define NB_SCHED_REGPOS (2 * NB_SCHED_REGSETS)
 #define NB_SCHED_SHARED 504
-#define NB_SCHED_AHEAD 8   // chunks of 32 contacts per bucket whose inputs are fetched ahead of the replay
 #define NB_SCHED_MAXV (NB_SCHED_REGPOS + NB_SCHED_SHARED - 1)   // positions held on chip; beyond that the list spills to global memory
 
 // Parallel pre-pass for the replay: the body pair of every contact in tag order with the body-0 substitution of
@@ -297,32 +296,18 @@ __global__ void __launch_bounds__(32) k_schedule(const uint2* cab, const uint8_t
 		return true;
 	};
 
-	// Software pipeline.  Placing a chunk of 32 contacts takes ~30 warp instructions, far less than a trip to memory, and a lone warp
-	// has nothing else to run: with the next chunk alone in flight 64 % of the kernel's cycles waited for it (ncu source page,
-	// profiles/r02g: 112 us for ~0.5 M warp instructions).  So the warp keeps NB_SCHED_AHEAD chunks in flight: the (ca, cb, back) of
-	// the current group of chunks sit in shared memory, the loads of the next group are in registers, issued before the group is placed.
-	__shared__ u32 S_pf[3][NB_SCHED_AHEAD][32];
-	u32 nx_ca[NB_SCHED_AHEAD], nx_cb[NB_SCHED_AHEAD], nx_back[NB_SCHED_AHEAD];
-	#pragma unroll
-	for (int q = 0; q < NB_SCHED_AHEAD; ++q) {
-		nx_ca[q] = 0; nx_cb[q] = 0; nx_back[q] = 0;
-		u32 i0 = bucket + 16 * 32 * q + 16 * lane;
-		if (i0 < n) { uint2 ab = cab[i0]; nx_ca[q] = ab.x; nx_cb[q] = ab.y; nx_back[q] = back[i0]; complete_flag[i0] = 0; }
+	// software pipeline: the (ca, cb) of the next 32 contacts of this bucket are fetched while the current 32 are placed
+	u32 nx_ca = 0, nx_cb = 0, nx_back = 0;
+	{
+		u32 i0 = bucket + 16 * lane;
+		if (i0 < n) { uint2 ab = cab[i0]; nx_ca = ab.x; nx_cb = ab.y; nx_back = back[i0]; complete_flag[i0] = 0; }
 	}
-	for (u32 gbase = bucket; gbase < n; gbase += 16 * 32 * NB_SCHED_AHEAD) {
-	__syncwarp();
-	#pragma unroll
-	for (int q = 0; q < NB_SCHED_AHEAD; ++q) { S_pf[0][q][lane] = nx_ca[q]; S_pf[1][q][lane] = nx_cb[q]; S_pf[2][q][lane] = nx_back[q]; }
-	__syncwarp();
-	#pragma unroll
-	for (int q = 0; q < NB_SCHED_AHEAD; ++q) {
-		u32 i1 = gbase + 16 * 32 * (NB_SCHED_AHEAD + q) + 16 * lane;
-		if (i1 < n) { uint2 ab = cab[i1]; nx_ca[q] = ab.x; nx_cb[q] = ab.y; nx_back[q] = back[i1]; complete_flag[i1] = 0; }
-	}
-	for (u32 q = 0; q < NB_SCHED_AHEAD; ++q) {
-		const u32 base = gbase + 16 * 32 * q;
-		if (base >= n) break;
-		const u32 my_ca = S_pf[0][q][lane], my_cb = S_pf[1][q][lane], my_back = S_pf[2][q][lane];
+	for (u32 base = bucket; base < n; base += 16 * 32) {
+		const u32 my_ca = nx_ca, my_cb = nx_cb, my_back = nx_back;
+		{
+			u32 i1 = base + 16 * 32 + 16 * lane;
+			if (i1 < n) { uint2 ab = cab[i1]; nx_ca = ab.x; nx_cb = ab.y; nx_back = back[i1]; complete_flag[i1] = 0; }
+		}
 		const u32 steps = min(32u, (n - base + 15) / 16);
 		u32 s = 0;
 		while (s < steps) {
@@ -399,7 +384,6 @@ __global__ void __launch_bounds__(32) k_schedule(const uint2* cab, const uint8_t
 				++s;
 			}
 		}
-	}
 	}
 	// leftovers are flushed bucket-major in list order (nudge.cpp:4316-4338)
 	__syncwarp();
