@@ -246,6 +246,16 @@ def run_sharded(args, rank, world, local):
     total_ms, launches = timed(main_transport)
     sampler.stop_flag = True
     graphed = sim.sim.shard_graph_active()
+    # diagnostic: the same ranks stepping their local problems WITHOUT the ghost hand-over (not a simulation of the global scene any more:
+    # timed after everything that is reported, state restored from a snapshot afterwards is not needed - the run ends here)
+    local_only_ms = None
+    if os.environ.get("NB_BENCH_LOCAL_ONLY", "0") == "1":
+        keep = snapshot() if 'snapshot' in dir() else None
+        sim.sim.shard_no_exchange(True)
+        local_only_ms, _ = timed(main_transport)
+        sim.sim.shard_no_exchange(False)
+        if keep is not None:
+            restore(keep)
     cnt = sim.sim.counts()
     lc = sim.local_counts()
     # end to end: host state of the local bodies in and out every step
@@ -265,7 +275,7 @@ def run_sharded(args, rank, world, local):
     t = torch.tensor([total_ms, e2e_ms, other_ms], dtype=torch.float64, device="cuda")
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     per_rank = torch.zeros((world, 3), dtype=torch.float64, device="cuda")        # ms per step, contacts, ghosts of every rank: shows imbalance
-    per_rank[rank] = torch.tensor([total_ms / K, float(cnt.contacts), float(lc["ghosts"])], dtype=torch.float64, device="cuda")
+    per_rank[rank] = torch.tensor([(local_only_ms if local_only_ms is not None else total_ms) / K, float(cnt.contacts), float(lc["ghosts"])], dtype=torch.float64, device="cuda")
     dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
     ssum = torch.tensor([float(cnt.contacts), float(lc["owned"]), float(lc["ghosts"]), float(lc["export"]), float(h2d), float(d2h), float(cnt.overflow)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ssum, op=dist.ReduceOp.SUM)
@@ -287,7 +297,7 @@ def run_sharded(args, rank, world, local):
                        "value_definition": ("scene steps/s of the fixed-size scene" if strong else "scene steps/s x (total bodies / 65,536): 65,536-box-equivalent steps per second of the whole job"),
                        "scene_steps_per_s": rate, "l2": "flushed between timed steps (256 MiB write), flush excluded", "timing": "CUDA events per step, summed; max over ranks",
                        "overflow_flags": int(ssum[6]), "reshard_ms_host_side_untimed": reshard_ms,
-                       "per_rank_ms_per_step": [round(float(x), 4) for x in per_rank[:, 0]], "per_rank_contacts": [int(x) for x in per_rank[:, 1]], "per_rank_ghosts": [int(x) for x in per_rank[:, 2]],
+                       ("per_rank_local_only_ms_per_step" if local_only_ms is not None else "per_rank_ms_per_step"): [round(float(x), 4) for x in per_rank[:, 0]], "per_rank_contacts": [int(x) for x in per_rank[:, 1]], "per_rank_ghosts": [int(x) for x in per_rank[:, 2]],
                        "solver_mode": ("throughput (mass-splitting Jacobi) inside a rank" if args.solver == "throughput" else "exact reference Gauss-Seidel order inside a rank") + ", block-Jacobi across ranks"},
             "parity_check": parity,
             "e2e": {"value": ((g.n_bodies - 1) / unit_bodies) * K / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(ssum[4]), "d2h_bytes_per_step": int(ssum[5]),

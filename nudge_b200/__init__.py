@@ -18,7 +18,7 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_setup_contact_constraints", "nb_apply_impulses", "nb_update_cached_impulses", "nb_write_cached_impulses", "nb_advance", "nb_step",
            "nb_launch_count", "nb_debug_read", "nb_debug_rcp", "nb_lut_model_exact", "nb_debug_sort", "nb_debug_scan", "nb_debug_enable", "nb_pack_momentum", "nb_unpack_momentum",
            "nb_shard_unique_id", "nb_shard_create", "nb_shard_destroy", "nb_shard_ipc_handle", "nb_shard_open_peer", "nb_shard_plan", "nb_shard_exchange",
-           "nb_shard_step", "nb_shard_graph_active", "nb_shard_partition",
+           "nb_shard_step", "nb_shard_graph_active", "nb_shard_partition", "nb_shard_debug_no_exchange",
            "nb_set_solver_mode", "nb_get_solver_mode", "nb_debug_timing_enable", "nb_debug_timing",
            "nb_stream_create", "nb_stream_destroy", "nb_stream_synchronize", "nb_save_state", "nb_load_state", "nb_state_info",
            "nb_upload_constraint_rows", "nb_download_constraint_rows"]
@@ -77,6 +77,7 @@ def load_library():
         lib.nb_shard_exchange.argtypes = [V, C.c_int, V]
         lib.nb_shard_step.argtypes = [V, C.c_float, C.c_uint32, C.c_float, C.c_float, C.c_int, V]
         lib.nb_shard_graph_active.argtypes = [V]
+        lib.nb_shard_debug_no_exchange.argtypes = [V, C.c_int]
         lib.nb_shard_partition.argtypes = [V, V, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, V, V, V, C.c_uint32]
         lib.nb_set_solver_mode.argtypes = [V, C.c_int]
         lib.nb_get_solver_mode.argtypes = [V]
@@ -213,6 +214,9 @@ class Sim(abi.HostState):
     def shard_step(self, transport):
         s = self.scene
         self._ck(self.lib.nb_shard_step(self.shard, float(s.time_step), int(s.iterations), float(s.gravity), float(s.damping), self.TRANSPORT[transport], self.stream), "nb_shard_step")
+
+    def shard_no_exchange(self, on):
+        self._ck(self.lib.nb_shard_debug_no_exchange(self.shard, 1 if on else 0), "nb_shard_debug_no_exchange")
 
     def shard_graph_active(self):
         return bool(self.lib.nb_shard_graph_active(self.shard))

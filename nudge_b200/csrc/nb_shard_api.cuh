@@ -22,6 +22,7 @@ struct nb_shard {
 	struct Key { cudaStream_t stream; float ts, gravity, damping; u32 iterations; int transport, solver_mode; unsigned long long plan_version, urow_version; u32 B, nboxes, nspheres; } key;
 	cudaGraphExec_t graph; unsigned long long graph_launches; int graph_enabled;
 	long long pull_timeout_cycles;
+	int no_exchange;   // nb_shard_debug_no_exchange: time the rank's local problem without the ghost hand-over (results are then not a simulation of the global scene)
 };
 
 #define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { sh->ctx->error = std::string(#call) + ": " + cudaGetErrorString(e_); return NB_ERR_CUDA; } } while (0)
@@ -263,6 +264,7 @@ static int shard_step_body(nb_shard* sh, float time_step, uint32_t iterations, f
 int nb_shard_step(nb_shard* sh, float time_step, uint32_t iterations, float gravity, float damping, int transport, void* stream) {
 	NB_RANGE("nb_shard_step");
 	nb_context* ctx = sh->ctx;
+	if (sh->no_exchange) return nb_step(ctx, time_step, iterations, gravity, damping, stream);   // diagnostic: this rank's local problem alone
 	cudaStream_t st = (cudaStream_t)stream;
 	if (!sh->graph_enabled || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread || ctx->debug)
 		return shard_step_body(sh, time_step, iterations, gravity, damping, transport, stream);
@@ -298,6 +300,7 @@ int nb_shard_step(nb_shard* sh, float time_step, uint32_t iterations, float grav
 }
 
 int nb_shard_graph_active(const nb_shard* sh) { return sh->graph != nullptr; }
+int nb_shard_debug_no_exchange(nb_shard* sh, int on) { sh->no_exchange = on; return NB_OK; }
 
 // Partition of a scene for `gx * gz` ranks (rank = ix * gz + iz): equal-count columns along x, each cut into equal-count cells
 // along z.  A body is OWNED by the cell its centre lies in; it is a GHOST of every other cell whose box, grown by
