@@ -78,7 +78,7 @@ def load_library():
         lib.nb_shard_step.argtypes = [V, C.c_float, C.c_uint32, C.c_float, C.c_float, C.c_int, V]
         lib.nb_shard_graph_active.argtypes = [V]
         lib.nb_shard_debug_no_exchange.argtypes = [V, C.c_int]
-        lib.nb_shard_partition.argtypes = [V, V, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, V, V, V, C.c_uint32]
+        lib.nb_shard_partition.argtypes = [V, V, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32, V, V, V, C.c_uint32]
         lib.nb_set_solver_mode.argtypes = [V, C.c_int]
         lib.nb_get_solver_mode.argtypes = [V]
         lib.nb_debug_timing_enable.argtypes = [V, C.c_int]
@@ -114,7 +114,7 @@ def nccl_unique_id():
     return bytes(buf)
 
 
-def shard_partition(pos, radius, gx, gz, margin):
+def shard_partition(pos, radius, gx, gz, margin, balance=0):
     """nb_shard_partition (C++ host code, runs without a GPU): owner[n] and the ghost list of every rank."""
     lib = load_library()
     pos = np.ascontiguousarray(pos, np.float32); radius = np.ascontiguousarray(radius, np.float32)
@@ -123,7 +123,7 @@ def shard_partition(pos, radius, gx, gz, margin):
     cap = max(1024, n)
     while True:
         ids = np.zeros(cap, np.uint32)
-        r = lib.nb_shard_partition(abi.ptr(pos), abi.ptr(radius), n, int(gx), int(gz), C.c_float(margin), abi.ptr(owner), abi.ptr(off), abi.ptr(ids), cap)
+        r = lib.nb_shard_partition(abi.ptr(pos), abi.ptr(radius), n, int(gx), int(gz), C.c_float(margin), int(balance), abi.ptr(owner), abi.ptr(off), abi.ptr(ids), cap)
         if r == 0:
             break
         if r != -2:

@@ -306,9 +306,10 @@ int nb_shard_debug_no_exchange(nb_shard* sh, int on) { sh->no_exchange = on; ret
 // along z.  A body is OWNED by the cell its centre lies in; it is a GHOST of every other cell whose box, grown by
 // radius[i] + max_radius + margin, contains its centre (two bodies can only touch if their centres are closer than the sum of their
 // bounding radii).  pos: n x 3 floats (x, y, z), radius: n bounding radii.  owner_out[n]; ghost lists as CSR over ranks
-// (ghost_off[world + 1], ghost_ids up to ghost_cap entries, ascending per rank).  Returns NB_ERR_CAPACITY if ghost_cap is too small
+// (ghost_off[world + 1], ghost_ids up to ghost_cap entries, ascending per rank).  balance_iterations > 0 re-cuts the cells that many
+// times so that owned + ghost bodies, not owned bodies, are even across ranks.  Returns NB_ERR_CAPACITY if ghost_cap is too small
 // (ghost_off[world] then holds the required size).  Pure host code, deterministic: every rank computes the same partition.
-int nb_shard_partition(const float* pos, const float* radius, uint32_t n, uint32_t gx, uint32_t gz, float margin,
+int nb_shard_partition(const float* pos, const float* radius, uint32_t n, uint32_t gx, uint32_t gz, float margin, uint32_t balance_iterations,
 					   uint32_t* owner_out, uint32_t* ghost_off, uint32_t* ghost_ids, uint32_t ghost_cap) {
 	if (!gx || !gz || !pos || !radius || !owner_out || !ghost_off) return NB_ERR_ARGUMENT;
 	const u32 world = gx * gz;
@@ -319,35 +320,70 @@ int nb_shard_partition(const float* pos, const float* radius, uint32_t n, uint32
 	float rmax = 0.0f;
 	for (u32 i = 0; i < n; ++i) rmax = std::max(rmax, radius[i]);
 	const float inf = INFINITY;
-	for (u32 cx = 0; cx < gx; ++cx) {
-		const size_t b0 = (size_t)n * cx / gx, b1 = (size_t)n * (cx + 1) / gx;
-		xlo[cx] = cx == 0 ? -inf : 0.5f * (pos[3 * idx[b0 - 1]] + pos[3 * idx[b0]]);
-		if (cx) xhi[cx - 1] = xlo[cx];
-		std::vector<u32> col(idx.begin() + b0, idx.begin() + b1);
-		std::stable_sort(col.begin(), col.end(), [&](u32 a, u32 b) { return pos[3 * a + 2] < pos[3 * b + 2]; });
-		const size_t m = col.size();
-		for (u32 cz = 0; cz < gz; ++cz) {
-			const size_t c0 = m * cz / gz, c1 = m * (cz + 1) / gz;
-			const u32 r = cx * gz + cz;
-			zlo[r] = cz == 0 ? -inf : 0.5f * (pos[3 * col[c0 - 1] + 2] + pos[3 * col[c0] + 2]);
-			if (cz) zhi[r - 1] = zlo[r];
-			if (cz == gz - 1) zhi[r] = inf;
-			for (size_t k = c0; k < c1; ++k) owner_out[col[k]] = r;
+	// share of the bodies every column / every cell of a column OWNS: equal to start with; the balance iterations shrink the cells
+	// that carry many ghosts (interior cells have more neighbours) until owned + ghosts is even - a rank's step time follows its
+	// LOCAL body count, and every step ends with a handshake that waits for the slowest rank
+	std::vector<double> colw(gx, 1.0 / gx), cellw(world, 1.0 / gz);
+	std::vector<size_t> owned(world), ghosts(world);
+	bool uniform = true;   // equal shares: exact integer cuts (k * m / parts), the rule the tests restate
+	auto cut = [](size_t m, double lo) { double v = lo * (double)m + 0.5; size_t k = v <= 0.0 ? 0 : (size_t)v; return k > m ? m : k; };
+	auto assign = [&]() {
+		double cx0 = 0.0;
+		for (u32 cx = 0; cx < gx; ++cx) {
+			const double cx1 = cx + 1 == gx ? 1.0 : cx0 + colw[cx];
+			const size_t b0 = uniform ? (size_t)n * cx / gx : cut(n, cx0), b1 = cx + 1 == gx ? n : (uniform ? (size_t)n * (cx + 1) / gx : cut(n, cx1));
+			cx0 = cx1;
+			xlo[cx] = (cx == 0 || b0 == 0 || b0 >= n) ? (cx == 0 ? -inf : xlo[cx - 1]) : 0.5f * (pos[3 * idx[b0 - 1]] + pos[3 * idx[b0]]);
+			if (cx) xhi[cx - 1] = xlo[cx];
+			std::vector<u32> col(idx.begin() + b0, idx.begin() + std::max(b0, b1));
+			std::stable_sort(col.begin(), col.end(), [&](u32 a, u32 b) { return pos[3 * a + 2] < pos[3 * b + 2]; });
+			const size_t m = col.size();
+			double cz0 = 0.0;
+			for (u32 cz = 0; cz < gz; ++cz) {
+				const u32 r = cx * gz + cz;
+				const double cz1 = cz + 1 == gz ? 1.0 : cz0 + cellw[r];
+				const size_t c0 = uniform ? m * cz / gz : cut(m, cz0), c1 = cz + 1 == gz ? m : (uniform ? m * (cz + 1) / gz : cut(m, cz1));
+				cz0 = cz1;
+				zlo[r] = (cz == 0 || c0 == 0 || c0 >= m) ? (cz == 0 ? -inf : zlo[r - 1]) : 0.5f * (pos[3 * col[c0 - 1] + 2] + pos[3 * col[c0] + 2]);
+				if (cz) zhi[r - 1] = zlo[r];
+				if (cz == gz - 1) zhi[r] = inf;
+				owned[r] = c1 > c0 ? c1 - c0 : 0;
+				for (size_t k = c0; k < c1; ++k) owner_out[col[k]] = r;
+			}
 		}
+		xhi[gx - 1] = inf;
+	};
+	auto is_ghost = [&](u32 r, u32 i) {
+		if (owner_out[i] == r) return false;
+		const u32 cx = r / gz;
+		const float h = radius[i] + rmax + margin, x = pos[3 * i], z = pos[3 * i + 2];
+		return x >= xlo[cx] - h && x < xhi[cx] + h && z >= zlo[r] - h && z < zhi[r] + h;
+	};
+	assign();
+	for (u32 it = 0; it < balance_iterations && world > 1; ++it) {
+		for (u32 r = 0; r < world; ++r) { size_t c = 0; for (u32 i = 0; i < n; ++i) c += is_ghost(r, i); ghosts[r] = c; }
+		std::vector<double> coltot(gx, 0.0);
+		for (u32 r = 0; r < world; ++r) coltot[r / gz] += (double)(owned[r] + ghosts[r]);
+		double mean_col = 0.0; for (u32 c = 0; c < gx; ++c) mean_col += coltot[c] / gx;
+		double sw = 0.0;
+		for (u32 c = 0; c < gx; ++c) { colw[c] *= coltot[c] > 0 ? mean_col / coltot[c] : 1.0; sw += colw[c]; }
+		for (u32 c = 0; c < gx; ++c) colw[c] /= sw;
+		for (u32 c = 0; c < gx; ++c) {
+			double mean_cell = coltot[c] / gz, s2 = 0.0;
+			for (u32 z = 0; z < gz; ++z) { const u32 r = c * gz + z; const double t = (double)(owned[r] + ghosts[r]); cellw[r] *= t > 0 ? mean_cell / t : 1.0; s2 += cellw[r]; }
+			for (u32 z = 0; z < gz; ++z) cellw[c * gz + z] /= s2;
+		}
+		uniform = false;
+		assign();
 	}
-	xhi[gx - 1] = inf;
 	size_t total = 0;
 	for (u32 r = 0; r < world; ++r) {
 		ghost_off[r] = (u32)total;
-		const u32 cx = r / gz;
-		for (u32 i = 0; i < n; ++i) {
-			if (owner_out[i] == r) continue;
-			const float h = radius[i] + rmax + margin, x = pos[3 * i], z = pos[3 * i + 2];
-			if (x >= xlo[cx] - h && x < xhi[cx] + h && z >= zlo[r] - h && z < zhi[r] + h) {
+		for (u32 i = 0; i < n; ++i)
+			if (is_ghost(r, i)) {
 				if (ghost_ids && total < ghost_cap) ghost_ids[total] = i;
 				++total;
 			}
-		}
 	}
 	ghost_off[world] = (u32)total;
 	return (ghost_ids && total <= ghost_cap) ? NB_OK : NB_ERR_CAPACITY;

@@ -43,14 +43,14 @@ def choose_grid(pos, world):
     return best[1], best[2]
 
 
-def partition(g, world, margin=0.5, grid=None):
+def partition(g, world, margin=0.5, grid=None, balance=3):
     """Owned / ghost / export lists (global body ids, ascending) of every rank for scene `g` (body 0 = static world, on every rank)."""
     from . import shard_partition
     pos = g.transforms["position"][1:].astype(np.float32)
     rad = body_radius(g)[1:]
     gx, gz = grid if grid is not None else choose_grid(pos, world)
     assert gx * gz == world
-    owner, ghost_idx = shard_partition(pos, rad, gx, gz, margin)
+    owner, ghost_idx = shard_partition(pos, rad, gx, gz, margin, balance)
     ids = np.arange(1, g.n_bodies, dtype=np.int64)
     owned = [ids[owner == r] for r in range(world)]
     ghosts = [ghost_idx[r].astype(np.int64) + 1 for r in range(world)]
@@ -117,13 +117,14 @@ class ShardedSim:
     CPU oracle in the gloo tests).  transport: "nccl" | "peer" (the C++ host, device resident) or "host" (numpy exchange through
     torch.distributed `group`, any simulator)."""
 
-    def __init__(self, global_scene, rank, world, make_sim, margin=0.5, transport="host", group=None, grid=None, capacity_factor=1.6, nccl=True):
+    def __init__(self, global_scene, rank, world, make_sim, margin=0.5, transport="host", group=None, grid=None, capacity_factor=1.6, nccl=True, balance=3):
         self.g = global_scene.copy()
         self.rank, self.world, self.margin, self.grid = rank, world, float(margin), grid
         self.make_sim = make_sim
         self.transport = transport
         self.group = group
         self.capacity_factor = capacity_factor
+        self.balance = balance                 # re-cuts of the cells towards even owned + ghost counts (nb_shard_partition)
         self.nccl = nccl                       # False: create the C++ shard without an NCCL communicator (peer transport only)
         self.sim = None
         self.shard_ready = False
@@ -133,7 +134,7 @@ class ShardedSim:
     # ---- partition bookkeeping ----
     def _partition(self):
         g = self.g
-        self.part = partition(g, self.world, self.margin, self.grid)
+        self.part = partition(g, self.world, self.margin, self.grid, self.balance)
         owned, ghosts = self.part["owned"][self.rank], self.part["ghosts"][self.rank]
         scene, self.gids = local_scene(g, owned, ghosts)
         self.n_owned = len(owned)

@@ -43,7 +43,7 @@ def test_partition_covers_every_body_once_and_plans_the_exchange():
     pos = g.transforms["position"][1:].astype(np.float32); rad = shard.body_radius(g)[1:]
     n = len(rad)
     for world, grid in ((1, None), (2, None), (4, None), (8, None), (8, (8, 1)), (6, (2, 3))):
-        p = shard.partition(g, world, margin=0.5, grid=grid)
+        p = shard.partition(g, world, margin=0.5, grid=grid, balance=0)
         gx, gz = p["grid"]
         assert gx * gz == world
         owned = np.concatenate(p["owned"])
@@ -86,6 +86,17 @@ def test_partition_covers_every_body_once_and_plans_the_exchange():
                 assert np.array_equal(pl["ghost_src"] // pl["max_export"], p["owner"][p["ghosts"][r] - 1])
             for r in range(world):
                 assert np.all(fed[r] == 1)
+    # balance iterations: every body still owned exactly once, and owned + ghosts more even than with equal owned counts
+    gs = g.copy()                                   # a settled pile has continuous positions (the start lattice has thousands of bodies per z row)
+    rs = np.random.default_rng(7)
+    gs.transforms["position"][1:, 0] = rs.uniform(-60, 60, n); gs.transforms["position"][1:, 2] = rs.uniform(-60, 60, n)
+    for world in (4, 8):
+        p0 = shard.partition(gs, world, margin=0.5, balance=0); p3 = shard.partition(gs, world, margin=0.5, balance=3)
+        assert np.array_equal(np.sort(np.concatenate(p3["owned"])), np.arange(1, n + 1))
+        tot = lambda p: np.array([len(p["owned"][r]) + len(p["ghosts"][r]) for r in range(world)])
+        assert tot(p3).max() - tot(p3).min() < 0.6 * (tot(p0).max() - tot(p0).min()) + 8, (tot(p0), tot(p3))
+        for r in range(world):
+            assert not np.intersect1d(p3["ghosts"][r], p3["owned"][r]).size
     # a thin wall is cut along x only, a square pile in both directions
     w = scenes.brick_wall(4000, iterations=4)
     assert shard.choose_grid(w.transforms["position"][1:], 8) == (8, 1)
