@@ -47,3 +47,19 @@ def test_host_lut_calibration_model_is_exact_here():
     lib.nb_host_sample_luts(rcp.ctypes.data_as(ctypes.c_void_p), rsq.ctypes.data_as(ctypes.c_void_p))
     assert lib.nb_host_check_lut_model(rcp.ctypes.data_as(ctypes.c_void_p), rsq.ctypes.data_as(ctypes.c_void_p)) == 1
     assert (rcp & 0x7ff).max() == 0 and (rsq & 0x7ff).max() == 0  # 12 significant mantissa bits
+
+
+def test_state_file_header_is_read_without_a_gpu(tmp_path):
+    """nb_state_info parses the header of a state file (layout: nudge_b200/csrc/nb_state_api.cuh) — pure host code, so tools can size an
+    nb_config before any context exists; a file that is not a state file is refused."""
+    import struct
+    lib = nudge_b200.load_library()
+    good = tmp_path / "s.bin"
+    good.write_bytes(b"NBSTATE1" + struct.pack("<15I", 1, 1000, 600, 400, 7, 12345, 0, *([0] * 8)))
+    counts = (ctypes.c_uint32 * 5)()
+    assert lib.nb_state_info(os.fsencode(str(good)), counts) == 0
+    assert list(counts) == [1000, 600, 400, 7, 12345]
+    bad = tmp_path / "t.bin"
+    bad.write_bytes(b"not a state file at all" + bytes(64))
+    assert lib.nb_state_info(os.fsencode(str(bad)), counts) != 0
+    assert lib.nb_state_info(os.fsencode(str(tmp_path / "missing.bin")), counts) != 0
