@@ -273,6 +273,7 @@ void nb_destroy(nb_context* ctx) {
 	if (!ctx) return;
 	cudaDeviceSynchronize();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+	if (ctx->tev_made) for (int i = 0; i < 64; ++i) { cudaEventDestroy(ctx->tev[0][i]); cudaEventDestroy(ctx->tev[1][i]); }
 	if (ctx->side) { cudaStreamDestroy(ctx->side); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_join2); }
 	for (size_t i = 0; i < ctx->allocs.size(); ++i) cudaFree(ctx->allocs[i]);
 	delete ctx;

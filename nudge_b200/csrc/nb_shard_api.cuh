@@ -73,7 +73,7 @@ int nb_shard_create(nb_context* ctx, uint32_t rank, uint32_t world, const void* 
 		if (!api) { ctx->error = err; return NB_ERR_CUDA; }
 		ncclUniqueId id; memcpy(&id, nccl_id, sizeof(id));
 		ncclResult_t r = api->CommInitRank(&sh->comm, (int)world, id, (int)rank);
-		if (r != ncclSuccess) { ctx->error = std::string("ncclCommInitRank: ") + api->GetErrorString(r); return NB_ERR_CUDA; }
+		if (r != ncclSuccess) { ctx->error = std::string("ncclCommInitRank: ") + api->GetErrorString(r); delete sh; *out = nullptr; return NB_ERR_CUDA; }
 		sh->has_nccl = true;
 	}
 	return NB_OK;
