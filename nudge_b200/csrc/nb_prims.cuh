@@ -665,6 +665,20 @@ __global__ void __launch_bounds__(NB_CS_THREADS) k_sort_coop(u64* k0, u64* k1, u
 		cs_scan_digits(S, S.below[0], 0);
 		if (tid < 256) S.below[1][tid] = S.running[tid];
 		grid_barrier(bar, G);
+		// Bucket phase.  256 buckets on G = 148 blocks means two rounds for most blocks and an idle tail for the rest (a quarter of
+		// this kernel's stall samples, profiles/r02g).  When the buckets are small the block instead takes every bucket that STARTS in
+		// its slice [b n/G, (b+1) n/G) of the key range and sorts them together, once, on ALL digits (the top digit included: the group
+		// spans several of its values) - one local sort of ~n/G keys per block, even across blocks, instead of two of n/256.
+		const u32 slice = n / G + 1;
+		const bool small = slice < NB_CS_CAP && !__syncthreads_or(tid < 256 && S.below[0][tid] > NB_CS_CAP - slice);
+		if (small) {
+			const u32 lo = (u32)((u64)b * n / G), hi = (u32)((u64)(b + 1) * n / G);
+			const u32 d0 = (u32)__syncthreads_count(tid < 256 && S.below[1][tid] < lo);
+			const u32 d1 = (u32)__syncthreads_count(tid < 256 && S.below[1][tid] < hi);
+			const u32 s = d0 < 256 ? S.below[1][d0] : n, e = d1 < 256 ? S.below[1][d1] : n;
+			if (e > s) cs_local_sort<HAS_VALS>(S, k1 + s, v1 + s, k1 + s, v1 + s, e - s, P, P.n);
+			return;
+		}
 		for (u32 d = b; d < 256; d += G) {
 			const u32 m = S.below[0][d], s = S.below[1][d];
 			if (m > NB_CS_CAP) cs_bucket_split<HAS_VALS>(S, k1 + s, v1 + s, k0 + s, v0 + s, m, P, nlocal - 1);
