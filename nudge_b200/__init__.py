@@ -21,7 +21,7 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_shard_step", "nb_shard_graph_active", "nb_shard_partition", "nb_shard_debug_no_exchange",
            "nb_set_solver_mode", "nb_get_solver_mode", "nb_debug_timing_enable", "nb_debug_timing",
            "nb_stream_create", "nb_stream_destroy", "nb_stream_synchronize", "nb_save_state", "nb_load_state", "nb_state_info",
-           "nb_upload_constraint_rows", "nb_download_constraint_rows"]
+           "nb_upload_constraint_rows", "nb_download_constraint_rows", "nb_instance_matrices"]
 
 
 class Config(C.Structure):
@@ -91,6 +91,7 @@ def load_library():
         lib.nb_state_info.argtypes = [C.c_char_p, V]
         lib.nb_upload_constraint_rows.argtypes = [V, V, C.c_uint32, V]
         lib.nb_download_constraint_rows.argtypes = [V, V, C.c_uint32, V]
+        lib.nb_instance_matrices.argtypes = [V, V, C.c_uint32, C.c_int, V, V]
         _lib = lib
     return _lib
 
@@ -300,6 +301,20 @@ class Sim(abi.HostState):
         rows = np.zeros(n, ROW)
         self._ck(self.lib.nb_download_constraint_rows(self.ctx, abi.ptr(rows) if n else None, n, self.stream), "nb_download_constraint_rows")
         return rows
+
+    # ---- renderer read-back (example/main.cpp:224-268): one column-major 4x4 model matrix per collider, boxes first, then spheres ----
+    def instance_matrices(self, out=None, device_ptr=None, capacity=0):
+        """Host destination (default): returns an (n, 16) float32 array.  device_ptr: writes into that device buffer (e.g. a mapped
+        graphics resource) asynchronously on the Sim's stream and returns the collider count."""
+        n = C.c_uint32(0)
+        if device_ptr is not None:
+            self._ck(self.lib.nb_instance_matrices(self.ctx, C.c_void_p(device_ptr), capacity, 1, C.byref(n), self.stream), "nb_instance_matrices")
+            return int(n.value)
+        k = self.scene.n_colliders
+        if out is None:
+            out = np.zeros((k, 16), np.float32)
+        self._ck(self.lib.nb_instance_matrices(self.ctx, abi.ptr(out), len(out), 0, C.byref(n), self.stream), "nb_instance_matrices")
+        return out[:n.value]
 
     # ---- state files (nb_save_state / nb_load_state; tools/nb_replay steps them headless) ----
     def save_state(self, path):

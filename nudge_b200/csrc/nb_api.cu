@@ -47,6 +47,7 @@ struct nb_context {
 	// nb_step overlaps independent branches of the step on a second stream (fork/join with events; also inside the captured graph)
 	bool rows_on_side, join_before_solve, zero_chain_len; int overlap; cudaStream_t side; cudaEvent_t ev_fork, ev_fork2, ev_join, ev_join2; u32* flags2; u32* offs2; u32* block_sums2;
 	// user constraint rows (nb_upload_constraint_rows, nb_rows_api.cuh)
+	float4* instances;   // nb_instance_matrices with a host destination (allocated on first use)
 	nb_constraint_row* urows; u32 urow_cap, urow_n, urow_levels; unsigned long long urow_version; std::vector<u32> urow_level_off, urow_order;
 
 	// scene
@@ -916,3 +917,4 @@ int nb_debug_rcp(nb_context* ctx, const float* x, float* y, uint32_t n, int rsq)
 #include "nb_shard_api.cuh"
 #include "nb_state_api.cuh"
 #include "nb_rows_api.cuh"
+#include "nb_render_api.cuh"
