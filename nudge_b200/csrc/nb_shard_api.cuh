@@ -313,9 +313,18 @@ int nb_shard_partition(const float* pos, const float* radius, uint32_t n, uint32
 					   uint32_t* owner_out, uint32_t* ghost_off, uint32_t* ghost_ids, uint32_t ghost_cap) {
 	if (!gx || !gz || !pos || !radius || !owner_out || !ghost_off) return NB_ERR_ARGUMENT;
 	const u32 world = gx * gz;
-	std::vector<u32> idx(n);
-	for (u32 i = 0; i < n; ++i) idx[i] = i;
-	std::stable_sort(idx.begin(), idx.end(), [&](u32 a, u32 b) { return pos[3 * a] < pos[3 * b]; });
+	// x order (ties by body index) and, once for all the re-cuts, the z order with ties by x rank: walking it and dealing every body
+	// to its column yields each column sorted by z exactly as a stable sort of the column's x-ordered slice would
+	std::vector<std::pair<float, u32>> keyed(n);
+	for (u32 i = 0; i < n; ++i) keyed[i] = std::make_pair(pos[3 * i], i);
+	std::sort(keyed.begin(), keyed.end());
+	std::vector<u32> idx(n), xrank(n), zorder(n);
+	for (u32 k = 0; k < n; ++k) { idx[k] = keyed[k].second; xrank[keyed[k].second] = k; }
+	for (u32 i = 0; i < n; ++i) keyed[i] = std::make_pair(pos[3 * i + 2], xrank[i]);
+	std::sort(keyed.begin(), keyed.end());
+	for (u32 k = 0; k < n; ++k) zorder[k] = idx[keyed[k].second];
+	std::vector<std::pair<float, u32>>().swap(keyed);
+	std::vector<u32> col_begin(gx + 1), col_fill(gx), cols(n);
 	std::vector<float> xlo(gx), xhi(gx), zlo(world), zhi(world);
 	float rmax = 0.0f;
 	for (u32 i = 0; i < n; ++i) rmax = std::max(rmax, radius[i]);
@@ -329,15 +338,24 @@ int nb_shard_partition(const float* pos, const float* radius, uint32_t n, uint32
 	auto cut = [](size_t m, double lo) { double v = lo * (double)m + 0.5; size_t k = v <= 0.0 ? 0 : (size_t)v; return k > m ? m : k; };
 	auto assign = [&]() {
 		double cx0 = 0.0;
-		for (u32 cx = 0; cx < gx; ++cx) {
+		for (u32 cx = 0; cx < gx; ++cx) {   // column cuts in the x order
 			const double cx1 = cx + 1 == gx ? 1.0 : cx0 + colw[cx];
 			const size_t b0 = uniform ? (size_t)n * cx / gx : cut(n, cx0), b1 = cx + 1 == gx ? n : (uniform ? (size_t)n * (cx + 1) / gx : cut(n, cx1));
 			cx0 = cx1;
 			xlo[cx] = (cx == 0 || b0 == 0 || b0 >= n) ? (cx == 0 ? -inf : xlo[cx - 1]) : 0.5f * (pos[3 * idx[b0 - 1]] + pos[3 * idx[b0]]);
 			if (cx) xhi[cx - 1] = xlo[cx];
-			std::vector<u32> col(idx.begin() + b0, idx.begin() + std::max(b0, b1));
-			std::stable_sort(col.begin(), col.end(), [&](u32 a, u32 b) { return pos[3 * a + 2] < pos[3 * b + 2]; });
-			const size_t m = col.size();
+			col_begin[cx] = (u32)b0; col_begin[cx + 1] = (u32)std::max(b0, b1);
+		}
+		for (u32 cx = 0; cx < gx; ++cx) col_fill[cx] = col_begin[cx];
+		for (u32 k = 0; k < n; ++k) {       // deal the z order to the columns
+			const u32 i = zorder[k], xr = xrank[i];
+			u32 cx = 0;
+			while (cx + 1 < gx && xr >= col_begin[cx + 1]) ++cx;
+			cols[col_fill[cx]++] = i;
+		}
+		for (u32 cx = 0; cx < gx; ++cx) {
+			const u32* col = cols.data() + col_begin[cx];
+			const size_t m = col_begin[cx + 1] - col_begin[cx];
 			double cz0 = 0.0;
 			for (u32 cz = 0; cz < gz; ++cz) {
 				const u32 r = cx * gz + cz;
@@ -361,7 +379,8 @@ int nb_shard_partition(const float* pos, const float* radius, uint32_t n, uint32
 	};
 	assign();
 	for (u32 it = 0; it < balance_iterations && world > 1; ++it) {
-		for (u32 r = 0; r < world; ++r) { size_t c = 0; for (u32 i = 0; i < n; ++i) c += is_ghost(r, i); ghosts[r] = c; }
+		std::fill(ghosts.begin(), ghosts.end(), (size_t)0);
+		for (u32 i = 0; i < n; ++i) for (u32 r = 0; r < world; ++r) ghosts[r] += is_ghost(r, i);
 		std::vector<double> coltot(gx, 0.0);
 		for (u32 r = 0; r < world; ++r) coltot[r / gz] += (double)(owned[r] + ghosts[r]);
 		double mean_col = 0.0; for (u32 c = 0; c < gx; ++c) mean_col += coltot[c] / gx;
@@ -376,17 +395,15 @@ int nb_shard_partition(const float* pos, const float* radius, uint32_t n, uint32
 		uniform = false;
 		assign();
 	}
+	std::fill(ghosts.begin(), ghosts.end(), (size_t)0);
+	for (u32 i = 0; i < n; ++i) for (u32 r = 0; r < world; ++r) ghosts[r] += is_ghost(r, i);
 	size_t total = 0;
-	for (u32 r = 0; r < world; ++r) {
-		ghost_off[r] = (u32)total;
-		for (u32 i = 0; i < n; ++i)
-			if (is_ghost(r, i)) {
-				if (ghost_ids && total < ghost_cap) ghost_ids[total] = i;
-				++total;
-			}
-	}
+	for (u32 r = 0; r < world; ++r) { ghost_off[r] = (u32)total; total += ghosts[r]; }
 	ghost_off[world] = (u32)total;
-	return (ghost_ids && total <= ghost_cap) ? NB_OK : NB_ERR_CAPACITY;
+	if (!ghost_ids || total > ghost_cap) return NB_ERR_CAPACITY;
+	std::vector<u32> fill(ghost_off, ghost_off + world);
+	for (u32 i = 0; i < n; ++i) for (u32 r = 0; r < world; ++r) if (is_ghost(r, i)) ghost_ids[fill[r]++] = i;   // ascending per rank
+	return NB_OK;
 }
 
 }  // extern "C"
