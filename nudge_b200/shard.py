@@ -230,12 +230,24 @@ class ShardedSim:
         if self.world == 1:
             g.transforms[ids] = sim.transforms[own]; g.momentum[ids] = sim.momentum[own]; g.idle[ids] = sim.idle[own]
             return g
-        import torch.distributed as dist
-        payload = (ids.copy(), sim.transforms[own].copy(), sim.momentum[own].copy(), sim.idle[own].copy())
-        out = [None] * self.world
-        dist.all_gather_object(out, payload, group=self.group)
-        for (i, t, m, c) in out:
-            g.transforms[i] = t; g.momentum[i] = m; g.idle[i] = c
+        import torch, torch.distributed as dist
+        # every rank knows every rank's owned list (the partition is a deterministic function of the gathered state), so only the rows
+        # travel: 32 B transform + 32 B momentum + 1 B idle counter per owned body, padded to the largest rank, one all_gather
+        owned = self.part["owned"]
+        cap = max(1, max(len(o) for o in owned))
+        n = self.n_owned
+        rec = np.zeros((cap, 65), np.uint8)
+        rec[:n, 0:32] = sim.transforms[own].view(np.uint8).reshape(n, 32)
+        rec[:n, 32:64] = sim.momentum[own].view(np.uint8).reshape(n, 32)
+        rec[:n, 64] = sim.idle[own]
+        out = torch.empty((self.world, cap, 65), dtype=torch.uint8)
+        dist.all_gather([out[r] for r in range(self.world)], torch.from_numpy(rec), group=self.group)
+        got = out.numpy()
+        for r in range(self.world):
+            i, k = owned[r], len(owned[r])
+            g.transforms[i] = np.ascontiguousarray(got[r, :k, 0:32]).view(S.TRANSFORM).reshape(k)
+            g.momentum[i] = np.ascontiguousarray(got[r, :k, 32:64]).view(S.MOMENTUM).reshape(k)
+            g.idle[i] = got[r, :k, 64]
         return g
 
     def reshard(self):
