@@ -81,6 +81,9 @@ void nb_destroy(nb_context* ctx);
 const char* nb_last_error(const nb_context* ctx);
 
 /* Host <-> HBM.  Counts in the structs say how many rows to move; pointers are HOST pointers. */
+/* nb_upload_bodies is asynchronous (keep the host arrays unchanged until the next synchronising call; pin them to get real overlap): on a created
+ * stream the momentum and property rows travel on the library's own copy stream while `stream` goes on with the collision stage, and whatever
+ * reads them first on `stream` is ordered after the copy by the library (NB_COPY_OVERLAP=0 disables it).  Use ONE stream per context. */
 int nb_upload_bodies(nb_context*, const nb_body_data* host, void* stream);
 int nb_upload_colliders(nb_context*, const nb_collider_data* host, void* stream);
 int nb_upload_connections(nb_context*, const nb_body_connections* host, void* stream);

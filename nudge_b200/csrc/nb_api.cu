@@ -48,6 +48,9 @@ struct nb_context {
 	bool rows_on_side, join_before_solve, zero_chain_len; int overlap; cudaStream_t side; cudaEvent_t ev_fork, ev_fork2, ev_join, ev_join2; u32* flags2; u32* offs2; u32* block_sums2;
 	// user constraint rows (nb_upload_constraint_rows, nb_rows_api.cuh)
 	float4* instances;   // nb_instance_matrices with a host destination (allocated on first use)
+	// nb_upload_bodies sends what the collision stage does not read (momentum, properties) on a second stream, so that copy runs under
+	// `collide`; the first consumer waits for ev_up_done (inside a captured step: an external event-wait node, re-armed by every upload)
+	cudaStream_t copy_stream; cudaEvent_t ev_up_begin, ev_up_done; bool upload_pending, capture_joined; int copy_overlap;
 	nb_constraint_row* urows; u32 urow_cap, urow_n, urow_levels; unsigned long long urow_version; std::vector<u32> urow_level_off, urow_order;
 
 	// scene
@@ -132,10 +135,22 @@ __global__ void __launch_bounds__(NB_BLOCK) k_unpack_rows(float4* rows, const u3
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += gridDim.x * blockDim.x) rows[2 * idx[i >> 1] + (i & 1)] = in[2 * src[i >> 1] + (i & 1)];
 }
 
+// Called by everything that touches momentum or properties on `st`: orders it after a pending nb_upload_bodies side copy.
+static int join_uploads(nb_context* ctx, cudaStream_t st) {
+	if (ctx->capturing) {   // in a captured step: one event-wait node that, at every replay, waits for the most recent upload's copy
+		if (ctx->copy_stream && !ctx->capture_joined) { CK(cudaStreamWaitEvent(st, ctx->ev_up_done, cudaEventWaitExternal)); ctx->capture_joined = true; }
+		return NB_OK;
+	}
+	if (ctx->upload_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_up_done, 0)); ctx->upload_pending = false; }
+	return NB_OK;
+}
+#define JOIN_UPLOADS() do { int r_ = join_uploads(ctx, (cudaStream_t)stream); if (r_) return r_; } while (0)
+
 extern "C" {
 
 int nb_pack_momentum(nb_context* ctx, const uint32_t* dev_indices, uint32_t n, void* dev_out, void* stream) {
 	if (!n) return NB_OK;
+	JOIN_UPLOADS();
 	k_pack_rows<<<GRID(2 * n), NB_BLOCK, 0, (cudaStream_t)stream>>>((const float4*)ctx->mom, dev_indices, n, (float4*)dev_out);
 	++ctx->launches;
 	CK(cudaGetLastError());
@@ -143,6 +158,7 @@ int nb_pack_momentum(nb_context* ctx, const uint32_t* dev_indices, uint32_t n, v
 }
 int nb_unpack_momentum(nb_context* ctx, const uint32_t* dev_indices, const uint32_t* dev_sources, uint32_t n, const void* dev_in, void* stream) {
 	if (!n) return NB_OK;
+	JOIN_UPLOADS();
 	k_unpack_rows<<<GRID(2 * n), NB_BLOCK, 0, (cudaStream_t)stream>>>((float4*)ctx->mom, dev_indices, dev_sources, n, (const float4*)dev_in);
 	++ctx->launches;
 	CK(cudaGetLastError());
@@ -232,6 +248,11 @@ int nb_create(const nb_config* config, nb_context** out) {
 	CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
 	CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
+	// upload of the rows `collide` does not read, on a copy stream of its own (NB_COPY_OVERLAP=0: everything on the caller's stream)
+	{ const char* e = getenv("NB_COPY_OVERLAP"); ctx->copy_overlap = e ? atoi(e) != 0 : 1; }
+	CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&ctx->ev_up_begin, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_up_done, cudaEventDisableTiming));
+	CK(cudaEventRecord(ctx->ev_up_done, ctx->copy_stream));   // a first, already complete record for the step graph's event-wait node
 	ctx->solver_mode = NB_SOLVER_PARITY;
 	CK(cudaFuncSetAttribute(k_jacobi_sweep<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem<1>)));
 	CK(cudaFuncSetAttribute(k_jacobi_sweep<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacobiSmem<1>)));
@@ -275,6 +296,7 @@ void nb_destroy(nb_context* ctx) {
 	cudaDeviceSynchronize();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	if (ctx->tev_made) for (int i = 0; i < 64; ++i) { cudaEventDestroy(ctx->tev[0][i]); cudaEventDestroy(ctx->tev[1][i]); }
+	if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_up_begin); cudaEventDestroy(ctx->ev_up_done); }
 	if (ctx->side) { cudaStreamDestroy(ctx->side); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_join2); }
 	for (size_t i = 0; i < ctx->allocs.size(); ++i) cudaFree(ctx->allocs[i]);
 	delete ctx;
@@ -291,14 +313,25 @@ int nb_upload_bodies(nb_context* ctx, const nb_body_data* h, void* stream) {
 	NB_RANGE("nb_upload_bodies");
 	if (h->count > ctx->cfg.max_bodies) { ctx->error = "too many bodies"; return NB_ERR_CAPACITY; }
 	ctx->B = h->count;
-	H2D(ctx->xf, h->transforms, h->count, nb_transform); H2D(ctx->props, h->properties, h->count, nb_body_properties);
-	H2D(ctx->mom, h->momentum, h->count, nb_body_momentum); H2D(ctx->idle, h->idle_counters, h->count, uint8_t);
+	cudaStream_t st = (cudaStream_t)stream;
+	H2D(ctx->xf, h->transforms, h->count, nb_transform); H2D(ctx->idle, h->idle_counters, h->count, uint8_t);   // all the collision stage reads
+	if (ctx->copy_overlap && ctx->copy_stream && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread) {
+		CK(cudaEventRecord(ctx->ev_up_begin, st));                       // after everything already queued on the caller's stream (it may still use the old rows)
+		CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_up_begin, 0));
+		CK(cudaMemcpyAsync(ctx->mom, h->momentum, (size_t)h->count * sizeof(nb_body_momentum), cudaMemcpyHostToDevice, ctx->copy_stream));
+		CK(cudaMemcpyAsync(ctx->props, h->properties, (size_t)h->count * sizeof(nb_body_properties), cudaMemcpyHostToDevice, ctx->copy_stream));
+		CK(cudaEventRecord(ctx->ev_up_done, ctx->copy_stream));
+		ctx->upload_pending = true;
+	}
+	else {
+		H2D(ctx->props, h->properties, h->count, nb_body_properties); H2D(ctx->mom, h->momentum, h->count, nb_body_momentum);
+	}
 	return NB_OK;
 }
 #define ROWS_OK(count) do { if ((count) > ctx->cfg.max_bodies) { ctx->error = "row count exceeds max_bodies"; return NB_ERR_CAPACITY; } } while (0)
-int nb_upload_momentum(nb_context* ctx, const nb_body_momentum* h, uint32_t count, void* stream) { ROWS_OK(count); H2D(ctx->mom, h, count, nb_body_momentum); return NB_OK; }
+int nb_upload_momentum(nb_context* ctx, const nb_body_momentum* h, uint32_t count, void* stream) { ROWS_OK(count); JOIN_UPLOADS(); H2D(ctx->mom, h, count, nb_body_momentum); return NB_OK; }
 int nb_upload_transforms(nb_context* ctx, const nb_transform* h, uint32_t count, void* stream) { ROWS_OK(count); H2D(ctx->xf, h, count, nb_transform); return NB_OK; }
-int nb_download_momentum(nb_context* ctx, nb_body_momentum* h, uint32_t count, void* stream) { ROWS_OK(count); D2H(h, ctx->mom, count, nb_body_momentum); return NB_OK; }
+int nb_download_momentum(nb_context* ctx, nb_body_momentum* h, uint32_t count, void* stream) { ROWS_OK(count); JOIN_UPLOADS(); D2H(h, ctx->mom, count, nb_body_momentum); return NB_OK; }
 int nb_download_transforms(nb_context* ctx, nb_transform* h, uint32_t count, void* stream) { ROWS_OK(count); D2H(h, ctx->xf, count, nb_transform); return NB_OK; }
 
 int nb_upload_colliders(nb_context* ctx, const nb_collider_data* h, void* stream) {
@@ -332,6 +365,7 @@ int nb_upload_cache(nb_context* ctx, const nb_contact_cache* h, void* stream) {
 int nb_download_bodies(nb_context* ctx, nb_body_data* h, void* stream) {
 	NB_RANGE("nb_download_bodies");
 	u32 n = std::min(h->count, ctx->B);
+	JOIN_UPLOADS();
 	D2H(h->transforms, ctx->xf, n, nb_transform); D2H(h->momentum, ctx->mom, n, nb_body_momentum); D2H(h->idle_counters, ctx->idle, n, uint8_t);
 	CK(cudaStreamSynchronize((cudaStream_t)stream));
 	return NB_OK;
@@ -502,6 +536,7 @@ int nb_collide(nb_context* ctx, void* stream) {
 
 int nb_apply_gravity_damping(nb_context* ctx, float time_step, float gravity, float damping, void* stream) {
 	NB_RANGE("nb_apply_gravity_damping");
+	JOIN_UPLOADS();   // first reader of the momentum rows in a step
 	k_gravity_damping<<<GRID(ctx->B), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->active_idx, ctx->mom, time_step, gravity, damping, ctx->counts);
 	++ctx->launches;
 	CK(cudaGetLastError());
@@ -633,6 +668,7 @@ static int launch_solve(nb_context* ctx, int mode, u32 sweeps, cudaStream_t st) 
 
 int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 	NB_RANGE("nb_setup_contact_constraints");
+	JOIN_UPLOADS();
 	Launch L = mk_launch(ctx, stream);
 	cudaStream_t st = L.stream;
 	u32* counts = ctx->counts;
@@ -689,6 +725,7 @@ int nb_setup_contact_constraints(nb_context* ctx, void* stream) {
 
 int nb_apply_impulses(nb_context* ctx, uint32_t sweeps, void* stream) {
 	NB_RANGE("nb_apply_impulses");
+	JOIN_UPLOADS();
 	if (!sweeps) return NB_OK;
 	if (ctx->urow_n && !ctx->defer_warm_start) {   // user rows run after EVERY sweep (example/main.cpp:314-317): one sweep per solver launch
 		for (uint32_t w = 0; w < sweeps; ++w) {
@@ -713,6 +750,7 @@ int nb_update_cached_impulses(nb_context* ctx, void* stream) {
 
 int nb_advance(nb_context* ctx, float time_step, void* stream) {
 	NB_RANGE("nb_advance");
+	JOIN_UPLOADS();
 	k_advance<<<GRID(ctx->B), NB_BLOCK, 0, (cudaStream_t)stream>>>(ctx->active_idx, ctx->xf, ctx->mom, ctx->idle, time_step, ctx->counts);
 	++ctx->launches;
 	CK(cudaGetLastError());
@@ -770,7 +808,7 @@ int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity
 			const unsigned long long before = ctx->launches;
 			const int coop = ctx->sb.coop_launch, gcoop = ctx->graph_coop;
 			if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); break; }
-			ctx->capturing = true;
+			ctx->capturing = true; ctx->capture_joined = false;
 			if (attempt == 1) { ctx->sb.coop_launch = 0; ctx->graph_coop = 0; }
 			int r = step_body(ctx, time_step, iterations, gravity, damping, stream);
 			ctx->capturing = false; ctx->sb.coop_launch = coop; ctx->graph_coop = gcoop;
@@ -790,6 +828,7 @@ int nb_step(nb_context* ctx, float time_step, uint32_t iterations, float gravity
 		ctx->graph_key = key;
 	}
 	CK(cudaGraphLaunch(ctx->graph_exec, st));
+	ctx->upload_pending = false;   // the graph's event-wait node has ordered this replay after the side copy
 	ctx->launches += ctx->graph_launches;
 	ctx->contacts_internal = true;
 	return NB_OK;

@@ -161,6 +161,7 @@ int nb_shard_exchange(nb_shard* sh, int transport, void* stream) {
 	nb_context* ctx = sh->ctx;
 	cudaStream_t st = (cudaStream_t)stream;
 	if (sh->world == 1) return NB_OK;
+	if (!ctx->capturing) { int jr = join_uploads(ctx, st); if (jr) return jr; }   // reads the momentum rows
 	const ShardPlanDev P = sh->plan;
 	if (transport == NB_SHARD_NCCL) {
 		if (!sh->has_nccl) { ctx->error = "this shard was created without an NCCL id"; return NB_ERR_ARGUMENT; }
@@ -266,6 +267,8 @@ int nb_shard_step(nb_shard* sh, float time_step, uint32_t iterations, float grav
 	nb_context* ctx = sh->ctx;
 	if (sh->no_exchange) return nb_step(ctx, time_step, iterations, gravity, damping, stream);   // diagnostic: this rank's local problem alone
 	cudaStream_t st = (cudaStream_t)stream;
+	{ int jr = join_uploads(ctx, st); if (jr) return jr; }   // a pending side copy of nb_upload_bodies: ordered here, on the host side (the sharded graph has no event-wait node)
+	ctx->capture_joined = true;
 	if (!sh->graph_enabled || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread || ctx->debug)
 		return shard_step_body(sh, time_step, iterations, gravity, damping, transport, stream);
 	nb_shard::Key key;

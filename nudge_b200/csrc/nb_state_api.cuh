@@ -32,6 +32,7 @@ extern "C" {
 
 int nb_save_state(nb_context* ctx, const char* path, void* stream) {
 	cudaStream_t st = (cudaStream_t)stream;
+	{ int jr = join_uploads(ctx, st); if (jr) return jr; }
 	u32 c[CNT__COUNT];
 	int r = get_counts(ctx, c, stream); if (r) return r;
 	FILE* f = fopen(path, "wb");
@@ -66,6 +67,7 @@ int nb_state_info(const char* path, uint32_t counts[5]) {
 
 int nb_load_state(nb_context* ctx, const char* path, void* stream) {
 	cudaStream_t st = (cudaStream_t)stream;
+	{ int jr = join_uploads(ctx, st); if (jr) return jr; }
 	FILE* f = fopen(path, "rb");
 	if (!f) { ctx->error = std::string("cannot open ") + path; return NB_ERR_ARGUMENT; }
 	NbStateHeader h;

@@ -395,3 +395,52 @@ def test_full_size_configs_2_and_4_one_step_parity(name):
     assert g.counts().overflow == 0
     sync_oracle_from_gpu(o, g)
     _steps(o, g, 1, individually=False)
+
+
+def _pin_bodies(sim):
+    import torch
+    from nudge_b200 import abi
+    keep = {}
+    for name in ("transforms", "properties", "momentum", "idle"):
+        a = getattr(sim, name)
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        v = t.numpy()[:a.nbytes].view(a.dtype)
+        v[:] = a
+        keep[name] = t; setattr(sim, name, v)
+    sim.bodies = abi.BodyData(abi.ptr(sim.transforms), abi.ptr(sim.properties), abi.ptr(sim.momentum), abi.ptr(sim.idle), len(sim.transforms))
+    return keep
+
+
+def test_upload_step_download_with_the_side_copy_equals_single_stream_and_oracle(monkeypatch):
+    """The end-to-end loop an application with host-side state runs (nb_upload_bodies + nb_step + nb_download_bodies every step, host
+    edits in between): nb_upload_bodies sends momentum and properties on the library's copy stream so they travel under `collide`, and
+    the captured step waits for them through an event-wait node.  Same bits as the same loop with NB_COPY_OVERLAP=0 (one stream), as
+    the stage calls, and as the oracle fed the same edits."""
+    import torch
+    from oracle import pyoracle
+    scene = scenes.demo_scene(500, 400, iterations=6, spread=4.0, height=30.0)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    a = nudge_b200.Sim(scene, stream=s1.cuda_stream)               # side copy + graph replay
+    monkeypatch.setenv("NB_COPY_OVERLAP", "0")
+    b = nudge_b200.Sim(scene, stream=s2.cuda_stream)               # everything on the caller's stream
+    monkeypatch.delenv("NB_COPY_OVERLAP")
+    c = nudge_b200.Sim(scene, stream=s1.cuda_stream)               # side copy, stage calls (host-side join)
+    o = pyoracle.OracleSim(scene, contact_capacity=a.cap)
+    keep = [_pin_bodies(x) for x in (a, b, c)]
+    rng = np.random.default_rng(3)
+    for k in range(12):
+        kick = rng.integers(1, scene.n_bodies, 40)
+        dv = rng.normal(size=(40, 3)).astype(np.float32)
+        for x in (a, b, c, o):
+            x.momentum["velocity"][kick] += dv                     # the application's own code between two steps
+            x.idle[kick] = 0
+        for x in (a, b, c):
+            x.upload_bodies()
+        a.step(); b.step(); c.step_staged(); o.step()
+        for x in (a, b, c):
+            x.download_bodies()
+        for name in ("transforms", "momentum", "idle"):
+            assert getattr(a, name).tobytes() == getattr(o, name).tobytes(), "%s differs from the oracle at step %d" % (name, k)
+            assert getattr(a, name).tobytes() == getattr(b, name).tobytes() == getattr(c, name).tobytes(), "%s differs between the upload paths at step %d" % (name, k)
+    assert a.counts().overflow == 0 and a.counts().contacts > 0
+    del keep
