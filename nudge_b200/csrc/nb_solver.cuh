@@ -577,6 +577,17 @@ NB_DEV void st128(float4* p, float4 v) {
 	asm volatile("{\n .reg .b128 q;\n mov.b128 q, {%1,%2,%3,%4};\n st.relaxed.gpu.global.b128 [%0], q;\n}" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Both halves of a body's working row (32 bytes, one L2 sector) in one access: sm_100 has 256-bit global loads / stores
+// (LDG.E.ENL2.256 / STG.E.ENL2.256).  Each half still carries its own token, so only 16-byte granularity is assumed of the access.
+NB_DEV void ld256(const float4* p, float4& lo, float4& hi) {
+	asm volatile("ld.relaxed.gpu.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p) : "memory");
+}
+NB_DEV void st256(float4* p, float4 lo, float4 hi) {
+	asm volatile("st.relaxed.gpu.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+		:: "l"(p), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+}
+
 __global__ void __launch_bounds__(NB_BLOCK) k_mw_in(u32 B, const nb_body_momentum* momentum, float4* mw) {
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
 		const float4* p = reinterpret_cast<const float4*>(momentum + i);
@@ -752,6 +763,8 @@ NB_DEV void solve_contact(const Rows& R, u32 j, const float (&rv)[ROW_PLANES_TOT
 // Waiting: the body's token says how many applications are still ahead of this contact (k_chain_heads).  While that number is
 // >= 2 on either body only the linear halves are polled, and the warp sleeps hop_ns per missing application when all of its
 // lanes are that far away; from 1 on, all four halves are fetched in one round trip so the hand-off costs a single L2 access.
+// WIDE: a body's two halves are polled and handed over with one 256-bit access each (NB_SOLVE_WIDE at nb_create).
+template<bool WIDE>
 __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve(Rows R, const float4* impulses, float4* mw, int mode, u32 sweeps, u32 hop_ns, u32* counts) {
 	__shared__ u32 s_rcp[2048];
 	__shared__ u32 s_rsqrt[2048];
@@ -779,6 +792,28 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve(Rows R, const float4* imp
 					for (int k = 0; k < ROW_PLANES_TOTAL; ++k) rv[k] = c[(size_t)k * S];
 					st[0] = R.state[0*S + slot]; st[1] = R.state[1*S + slot]; st[2] = R.state[2*S + slot];
 				}
+			}
+			if constexpr (WIDE) {
+				while (__any_sync(0xffffffffu, pending)) {
+					u32 want = 0xffffffffu;
+					if (pending) {
+						float4 al, aw, bl, bw;
+						ld256(mw + 2*a, al, aw); ld256(mw + 2*b, bl, bw);
+						u32 ra = a ? exp_a - asu(al.w) : 0, rb = b ? exp_b - asu(bl.w) : 0;
+						u32 r = max(ra, rb);
+						if (r == 0 && (!a || asu(aw.w) == exp_a) && (!b || asu(bw.w) == exp_b)) {
+							if (sweep) solve_contact(R, slot, rv, st, al, aw, bl, bw, LutMath{ s_rcp, s_rsqrt });
+							else warm_start_contact(R, slot, impulses, al, aw, bl, bw, LutMath{ s_rcp, s_rsqrt });
+							if (a) { float tk = asf(exp_a + 1); al.w = tk; aw.w = tk; st256(mw + 2*a, al, aw); }  // body 0 is static: never written
+							if (b) { float tk = asf(exp_b + 1); bl.w = tk; bw.w = tk; st256(mw + 2*b, bl, bw); }
+							pending = false;
+						}
+						else want = r >= 2 ? (r - 1) * hop_ns : 0;
+					}
+					want = __reduce_min_sync(0xffffffffu, want);
+					if (want != 0xffffffffu && want) __nanosleep(min(want, 20000u));
+				}
+				continue;
 			}
 			while (__any_sync(0xffffffffu, pending)) {
 				u32 want = 0xffffffffu;
