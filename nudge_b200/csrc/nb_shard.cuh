@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(NB_BLOCK) k_mw_in_flow(u32 B, const nb_body_mo
 }
 
 // k_solve(mode 2) with the hand-over woven in: pass 0 = warm start, passes 1..sweeps = PGS sweeps.
+// WIDE: the local working rows are polled and handed over with one 256-bit access per body, as in k_solve<true> (nb_solver.cuh).
+template<bool WIDE>
 __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve_flow(Rows R, const float4* impulses, float4* mw, u32 sweeps, u32 hop_ns, u32* counts, ShardFlow X, ShardPlanDev P, const u32* epoch, long long timeout_cycles) {
 	__shared__ u32 s_rcp[2048];
 	__shared__ u32 s_rsqrt[2048];
@@ -275,8 +277,12 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve_flow(Rows R, const float4
 			while (__any_sync(0xffffffffu, pending)) {
 				u32 want = 0xffffffffu;
 				if (pending) {
-					float4 al = ld128(mw + 2*a), bl = ld128(mw + 2*b), aw, bw;
-					if (near) { aw = ld128(mw + 2*a + 1); bw = ld128(mw + 2*b + 1); }
+					float4 al, bl, aw, bw;
+					if constexpr (WIDE) { ld256(mw + 2*a, al, aw); ld256(mw + 2*b, bl, bw); near = true; }
+					else {
+						al = ld128(mw + 2*a); bl = ld128(mw + 2*b);
+						if (near) { aw = ld128(mw + 2*a + 1); bw = ld128(mw + 2*b + 1); }
+					}
 					u32 ra = a ? exp_a - asu(al.w) : 0, rb = b ? exp_b - asu(bl.w) : 0;
 					u32 r = max(ra, rb);
 					bool ready = r == 0 && near && (!a || asu(aw.w) == exp_a) && (!b || asu(bw.w) == exp_b);
@@ -301,8 +307,8 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_solve_flow(Rows R, const float4
 					if (ready) {
 						if (sweep) solve_contact(R, slot, rv, st, al, aw, bl, bw, LutMath{ s_rcp, s_rsqrt });
 						else warm_start_contact(R, slot, impulses, al, aw, bl, bw, LutMath{ s_rcp, s_rsqrt });
-						if (a) { float tk = asf(exp_a + 1); al.w = tk; aw.w = tk; st128(mw + 2*a, al); st128(mw + 2*a + 1, aw); }
-						if (b) { float tk = asf(exp_b + 1); bl.w = tk; bw.w = tk; st128(mw + 2*b, bl); st128(mw + 2*b + 1, bw); }
+						if (a) { float tk = asf(exp_a + 1); al.w = tk; aw.w = tk; if constexpr (WIDE) st256(mw + 2*a, al, aw); else { st128(mw + 2*a, al); st128(mw + 2*a + 1, aw); } }
+						if (b) { float tk = asf(exp_b + 1); bl.w = tk; bw.w = tk; if constexpr (WIDE) st256(mw + 2*b, bl, bw); else { st128(mw + 2*b, bl); st128(mw + 2*b + 1, bw); } }
 						if (pub_a != NB_NONE) flow_publish(X, P, pub_a, ep, w, al, aw);  // this body is done for pass w: hand it to its subscribers
 						if (pub_b != NB_NONE) flow_publish(X, P, pub_b, ep, w, bl, bw);
 						pending = false;

@@ -55,7 +55,7 @@ int nb_shard_create(nb_context* ctx, uint32_t rank, uint32_t world, const void* 
 	ALLOC(sh->peer_inbox2_dev, world); ALLOC(sh->d_export_row, ctx->cfg.max_bodies); ALLOC(sh->d_ghost_slot, ctx->cfg.max_bodies);
 	{
 		int per_sm = 0;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_flow, NB_BLOCK, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_flow<false>, NB_BLOCK, 0));   // both variants: 128 registers, 16 KB shared
 		sh->flow_blocks = per_sm > 0 ? ctx->sms * per_sm : 0;
 	}
 	ALLOC(sh->peers_dev, world); ALLOC(sh->epoch, 1); ALLOC(sh->done, 1);
@@ -219,8 +219,9 @@ static int shard_solve_flow(nb_shard* sh, uint32_t iterations, cudaStream_t st) 
 	const u32* epoch = sh->epoch; long long timeout = sh->pull_timeout_cycles;
 	void* args[] = { &R, &impulses, &mw, &sweeps, &hop, &counts, &X, (void*)&P, &epoch, &timeout };
 	timing_begin(ctx, st);
-	if (ctx->coop_launch && (!ctx->capturing || ctx->graph_coop)) SCK(cudaLaunchCooperativeKernel((void*)k_solve_flow, dim3(sh->flow_blocks), dim3(NB_BLOCK), args, 0, st));
-	else k_solve_flow<<<sh->flow_blocks, NB_BLOCK, 0, st>>>(R, impulses, mw, sweeps, hop, counts, X, P, epoch, timeout);
+	if (ctx->coop_launch && (!ctx->capturing || ctx->graph_coop)) SCK(cudaLaunchCooperativeKernel(ctx->solve_wide ? (void*)k_solve_flow<true> : (void*)k_solve_flow<false>, dim3(sh->flow_blocks), dim3(NB_BLOCK), args, 0, st));
+	else if (ctx->solve_wide) k_solve_flow<true><<<sh->flow_blocks, NB_BLOCK, 0, st>>>(R, impulses, mw, sweeps, hop, counts, X, P, epoch, timeout);
+	else k_solve_flow<false><<<sh->flow_blocks, NB_BLOCK, 0, st>>>(R, impulses, mw, sweeps, hop, counts, X, P, epoch, timeout);
 	timing_end(ctx, st);
 	++ctx->launches;
 	k_mw_out_push<<<GRID(B), NB_BLOCK, 0, st>>>(B, ctx->mom, ctx->mw, 1, P, sh->peers_dev, sh->ghost_cap, sh->rank, sh->world, sh->epoch, sh->done);
