@@ -7,8 +7,13 @@
 // Both print an FNV-1a hash of all transforms after the run (must be identical: tests/test_gpu_parity.py) and the measured steps/s
 // (bench.py reports the drop-in's number as `dropin_seven_call_steps_per_s`).  `worlds` > 1 steps that many independent worlds from
 // as many threads at once — the reference is re-entrant on disjoint data and so must the drop-in be.
+//   _ref/headless_resident   -DNB_RESIDENT: the same program with step() replaced by integration/nudge_gpu.h (nudge::gpu::World::simulate =
+//                        nb_step on the resident state, the fast path of INTEGRATION.md section 2), linked with libnudge_b200.so only
 //   usage: headless_example <boxes> <spheres> <steps> <iterations> [worlds]
 #include <nudge.h>
+#ifdef NB_RESIDENT
+#include "../integration/nudge_gpu.h"   // the reference-side binding over the C ABI: state resident in HBM, nb_step per sub-step
+#endif
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -24,6 +29,9 @@ struct Lcg { uint64_t s; float next() { s = s * 6364136223846793005ull + 1442695
 struct World {
 	nudge::Arena arena; nudge::BodyData bodies; nudge::ColliderData colliders; nudge::ContactData contacts; nudge::ContactCache cache; nudge::ActiveBodies active;
 	unsigned max_bodies;
+#ifdef NB_RESIDENT
+	nudge::gpu::World gpu;
+#endif
 
 	unsigned add_body(const float pos[3], float mass, const float inertia[3]) {
 		unsigned b = bodies.count++;
@@ -80,6 +88,10 @@ struct World {
 		}
 	}
 	void step(unsigned iterations, float time_step) {   // one sub-step of example/main.cpp:280-327
+#ifdef NB_RESIDENT
+		gpu.simulate(bodies, 1, iterations, 9.82f, 0.25f, time_step);   // gravity, damping and the seven stages on the device; state comes back
+		return;
+#endif
 		nudge::Arena temporary = arena;
 		nudge::BodyConnections connections = {};
 		nudge::collide(&active, &contacts, bodies, colliders, connections, temporary);
@@ -109,14 +121,23 @@ int main(int argc, char** argv) {
 	unsigned n_boxes = atoi(argv[1]), n_spheres = atoi(argv[2]), steps = atoi(argv[3]), iterations = atoi(argv[4]), n_worlds = argc > 5 ? atoi(argv[5]) : 1;
 	std::vector<World> worlds(n_worlds);
 	for (unsigned w = 0; w < n_worlds; ++w) worlds[w].build(n_boxes, n_spheres, 12345 + 77 * w);
+#ifdef NB_RESIDENT
+	try { for (unsigned w = 0; w < n_worlds; ++w) worlds[w].gpu.create(worlds[w].bodies, worlds[w].colliders, worlds[w].max_bodies, n_boxes + 1, n_spheres + 1); }
+	catch (const std::exception& e) { fprintf(stderr, "nudge_b200: %s\n", e.what()); return 3; }
+#endif
 	const float dt = 1.0f / 120.0f;
 	auto run = [&](unsigned w) { for (unsigned s = 0; s < steps; ++s) worlds[w].step(iterations, dt); };
 	auto t0 = std::chrono::steady_clock::now();
 	if (n_worlds == 1) run(0);
 	else { std::vector<std::thread> th; for (unsigned w = 0; w < n_worlds; ++w) th.emplace_back(run, w); for (auto& t : th) t.join(); }
 	double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-	for (unsigned w = 0; w < n_worlds; ++w)
-		printf("world %u bodies %u contacts %u cache %u hash %016llx\n", w, worlds[w].bodies.count, worlds[w].contacts.count, worlds[w].cache.count, (unsigned long long)worlds[w].hash());
+	for (unsigned w = 0; w < n_worlds; ++w) {
+		unsigned n_contacts = worlds[w].contacts.count, n_cache = worlds[w].cache.count;
+#ifdef NB_RESIDENT
+		{ nb_counts c = worlds[w].gpu.counts(); n_contacts = c.contacts; n_cache = c.cache; }
+#endif
+		printf("world %u bodies %u contacts %u cache %u hash %016llx\n", w, worlds[w].bodies.count, n_contacts, n_cache, (unsigned long long)worlds[w].hash());
+	}
 	printf("steps_per_s %.3f (%u steps of %u world(s) in %.3f s)\n", steps / sec, steps, n_worlds, sec);
 	return 0;
 }
