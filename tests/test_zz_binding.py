@@ -1,6 +1,6 @@
 """integration/nudge_gpu.h — the reference-side binding of INTEGRATION.md section 2 (resident state, nb_step) — driven by the headless
 application loop of oracle/headless_example.cpp built with -DNB_RESIDENT (oracle/_ref/headless_resident, linked with libnudge_b200.so).
-Sorted last on purpose: the GPU half of this file was added after the round's GPU budget was spent."""
+The GPU half ran once on a B200 with the round's last seconds of GPU time (passed: `profiles/r02_summary.md`)."""
 import os, subprocess
 import pytest
 
