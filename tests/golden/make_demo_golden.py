@@ -13,7 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-FRAMES = (0, 40)
+FRAMES = (0, 40, 900)
 
 
 def parse(path):

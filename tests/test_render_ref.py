@@ -38,7 +38,9 @@ def test_render_oracle_is_a_rigid_transform_times_scale():
 
 
 def test_oracle_follows_the_demo_trajectory():
-    """The widened restatement, started from the demo's initial state, reaches the demo's recorded frames bit for bit."""
+    """The widened restatement, started from the demo's initial state, reaches the demo's recorded frames bit for bit: frames 0, 40 and 900
+    (1802 sub-steps of 20 iterations; by then the pile has settled and 566 of the 1536 bodies sleep, so islands, idle counters, the culled
+    part of the contact cache and waking are all on the path)."""
     from oracle import pyoracle
     g = G.load_demo_frames()
     o = pyoracle.OracleSim(G.demo_scene(g, "initial"))
