@@ -188,3 +188,49 @@ def test_two_ranks_stay_close_to_one_rank_physics():
     assert ke(two["momentum"]) < 10.0 * ke(one.momentum) + 5.0
     px = lambda m: (mass[:, None] * m["velocity"][1:]).sum(0)
     assert np.abs(px(two["momentum"]) - px(one.momentum)).max() < 0.05 * mass.sum()
+
+
+def test_partition_edge_cases_ties_tiny_inputs_and_capacity_retry():
+    """nb_shard_partition on degenerate inputs: exact ties in x and z (a lattice: the tie rule is the body index, via the x rank), fewer
+    bodies than cells, one body, equal positions, and the ghost-capacity retry of the Python wrapper (NB_ERR_CAPACITY -> required size)."""
+    import ctypes as C
+    import nudge_b200
+    from nudge_b200 import abi
+    rng = np.random.default_rng(1)
+    # lattice with many equal coordinates, shuffled body order
+    gx_, gz_ = 12, 9
+    pos = np.stack(np.meshgrid(np.arange(gx_, dtype=np.float32), np.zeros(1, np.float32), np.arange(gz_, dtype=np.float32), indexing="ij"), -1).reshape(-1, 3)
+    pos = np.repeat(pos, 3, axis=0)                      # three bodies on every lattice point
+    pos = pos[rng.permutation(len(pos))].copy()
+    rad = np.full(len(pos), 0.4, np.float32)
+    for gx, gz in ((1, 1), (2, 2), (3, 2), (4, 1), (1, 5)):
+        owner, ghosts = nudge_b200.shard_partition(pos, rad, gx, gz, 0.25, 0)
+        o2, g2 = _numpy_partition(pos, rad, gx, gz, 0.25)
+        assert np.array_equal(owner, o2), (gx, gz)
+        for r in range(gx * gz):
+            assert np.array_equal(ghosts[r], g2[r]), (gx, gz, r)
+    # fewer bodies than cells, a single body, all bodies at one point: every body owned exactly once, ghost lists consistent with the rule
+    # (cells without bodies are outside the numpy restatement above; what must hold is the contract the solver relies on)
+    for pos in (rng.normal(size=(3, 3)).astype(np.float32), np.zeros((1, 3), np.float32), np.ones((7, 3), np.float32), rng.normal(size=(40, 3)).astype(np.float32)):
+        rad = np.full(len(pos), 0.5, np.float32)
+        for balance in (0, 3):
+            owner, ghosts = nudge_b200.shard_partition(pos, rad, 2, 4, 0.5, balance)
+            assert len(owner) == len(pos) and owner.max() < 8
+            for r in range(8):
+                assert (owner[ghosts[r]] != r).all() and np.array_equal(ghosts[r], np.unique(ghosts[r]))     # ascending, no owned body among the ghosts
+            d = np.linalg.norm(pos[:, None, :] - pos[None, :, :], axis=2)
+            ii, jj = np.nonzero((d < rad[:, None] + rad[None, :]) & (owner[:, None] != owner[None, :]))
+            for a, b in zip(ii, jj):          # touching bodies of different ranks see each other
+                assert a in ghosts[owner[b]] and b in ghosts[owner[a]], (len(pos), balance, a, b)
+    # capacity protocol of the C entry point: too small a ghost buffer -> NB_ERR_CAPACITY and the required size in ghost_off[world]
+    pos = rng.uniform(-5, 5, size=(400, 3)).astype(np.float32); rad = np.full(400, 1.0, np.float32)
+    lib = nudge_b200.load_library()
+    owner = np.zeros(400, np.uint32); off = np.zeros(5, np.uint32); ids = np.zeros(8, np.uint32)
+    r = lib.nb_shard_partition(abi.ptr(pos), abi.ptr(rad), 400, 2, 2, C.c_float(0.5), 0, abi.ptr(owner), abi.ptr(off), abi.ptr(ids), 8)
+    assert r == -2 and off[4] > 8
+    need = int(off[4]); ids = np.zeros(need, np.uint32)
+    r = lib.nb_shard_partition(abi.ptr(pos), abi.ptr(rad), 400, 2, 2, C.c_float(0.5), 0, abi.ptr(owner), abi.ptr(off), abi.ptr(ids), need)
+    assert r == 0 and off[4] == need
+    _, g2 = _numpy_partition(pos, rad, 2, 2, 0.5)
+    for k in range(4):
+        assert np.array_equal(ids[off[k]:off[k + 1]], g2[k])
