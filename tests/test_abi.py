@@ -1,6 +1,7 @@
 """The C-ABI library loads without a GPU and exports every symbol include/nudge_b200.h declares; creating a context
 without a GPU fails loudly (no CPU fallback).  CPU only."""
 import ctypes, os, re
+import pytest
 import numpy as np
 import nudge_b200
 
@@ -63,3 +64,27 @@ def test_state_file_header_is_read_without_a_gpu(tmp_path):
     bad.write_bytes(b"not a state file at all" + bytes(64))
     assert lib.nb_state_info(os.fsencode(str(bad)), counts) != 0
     assert lib.nb_state_info(os.fsencode(str(tmp_path / "missing.bin")), counts) != 0
+
+
+def test_replay_tool_rejects_bad_files_and_has_no_cpu_path():
+    """tools/bin/nb_replay: not a state file -> message and exit code 1; a valid file without a CUDA device -> the library's
+    "no CPU path" error, not a silent fallback."""
+    import struct, subprocess, tempfile
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "bin", "nb_replay")
+    if not os.path.exists(exe):
+        pytest.skip("tools/bin/nb_replay not built")
+    r = subprocess.run([exe, "/nonexistent/state.bin", "--steps", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "not an nb state file" in (r.stdout + r.stderr)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "one_body.bin")
+        with open(p, "wb") as f:
+            f.write(b"NBSTATE1" + struct.pack("<15I", 1, 1, 0, 0, 0, 0, 0, *([0] * 8)) + b"\0" * 96)   # one body (the static world), no colliders
+        r = subprocess.run([exe, p, "--steps", "1"], capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0 and "hash" not in r.stdout, r.stdout + r.stderr
