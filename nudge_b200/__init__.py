@@ -21,7 +21,7 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_shard_step", "nb_shard_graph_active", "nb_shard_partition", "nb_shard_debug_no_exchange",
            "nb_set_solver_mode", "nb_get_solver_mode", "nb_debug_timing_enable", "nb_debug_timing",
            "nb_stream_create", "nb_stream_destroy", "nb_stream_synchronize", "nb_save_state", "nb_load_state", "nb_state_info",
-           "nb_upload_constraint_rows", "nb_download_constraint_rows", "nb_instance_matrices"]
+           "nb_upload_constraint_rows", "nb_download_constraint_rows", "nb_instance_matrices", "nb_shard_build_plan"]
 
 
 class Config(C.Structure):
@@ -92,6 +92,7 @@ def load_library():
         lib.nb_upload_constraint_rows.argtypes = [V, V, C.c_uint32, V]
         lib.nb_download_constraint_rows.argtypes = [V, V, C.c_uint32, V]
         lib.nb_instance_matrices.argtypes = [V, V, C.c_uint32, C.c_int, V, V]
+        lib.nb_shard_build_plan.argtypes = [V, C.c_uint32, V, V, C.c_uint32, C.c_uint32, V, V, V, V, V, V, V, V]
         _lib = lib
     return _lib
 
@@ -131,6 +132,29 @@ def shard_partition(pos, radius, gx, gz, margin, balance=0):
             raise NudgeError("nb_shard_partition failed (%d)" % r)
         cap = int(off[world]) + 16
     return owner, [ids[off[k]:off[k + 1]].copy() for k in range(world)]
+
+
+def shard_build_plan(owner, ghost_lists, rank):
+    """nb_shard_build_plan (C++ host code, runs without a GPU): the exchange plan of `rank` from a partition (owner[n], one 0-based ascending
+    ghost id list per rank).  Returns a dict with the arrays nb_shard_plan takes plus owned_ids and max_export."""
+    lib = load_library()
+    owner = np.ascontiguousarray(owner, np.uint32)
+    world = len(ghost_lists)
+    off = np.zeros(world + 1, np.uint32)
+    off[1:] = np.cumsum([len(g) for g in ghost_lists])
+    ids = np.ascontiguousarray(np.concatenate([np.asarray(g, np.uint32) for g in ghost_lists]) if off[world] else np.zeros(1, np.uint32), np.uint32)
+    sizes = (C.c_uint32 * 5)()
+    r = lib.nb_shard_build_plan(abi.ptr(owner), len(owner), abi.ptr(off), abi.ptr(ids), world, int(rank), sizes, None, None, None, None, None, None, None)
+    if r != 0:
+        raise NudgeError("nb_shard_build_plan failed (%d)" % r)
+    n_owned, n_export, n_ghost, n_sub, max_export = (int(x) for x in sizes)
+    A = lambda k: np.zeros(max(int(k), 1), np.uint32)
+    owned, exp, so, sr, ss, gl, gs = A(n_owned), A(n_export), A(n_export + 1), A(n_sub), A(n_sub), A(n_ghost), A(n_ghost)
+    r = lib.nb_shard_build_plan(abi.ptr(owner), len(owner), abi.ptr(off), abi.ptr(ids), world, int(rank), sizes, abi.ptr(owned), abi.ptr(exp), abi.ptr(so), abi.ptr(sr), abi.ptr(ss), abi.ptr(gl), abi.ptr(gs))
+    if r != 0:
+        raise NudgeError("nb_shard_build_plan failed (%d)" % r)
+    return dict(owned_ids=owned[:n_owned], export_local=exp[:n_export], sub_off=so[:n_export + 1], sub_rank=sr[:n_sub], sub_slot=ss[:n_sub],
+                ghost_local=gl[:n_ghost], ghost_src=gs[:n_ghost], max_export=max_export)
 
 
 class Sim(abi.HostState):

@@ -410,4 +410,53 @@ int nb_shard_partition(const float* pos, const float* radius, uint32_t n, uint32
 	return NB_OK;
 }
 
+// The exchange plan of one rank from a partition (nb_shard_partition's owner[] and ghost lists): the arrays nb_shard_plan takes.
+// Local body order of a rank: [world body, owned bodies ascending, ghosts ascending].  A body is EXPORTED by its owner if it is a
+// ghost anywhere; a rank's export row k is its k-th exported body (ascending), rows are padded to `max_export` per rank for the
+// all-gather (ghost_src = owner * max_export + row), and for the peer transport every export row lists its subscribers
+// (rank, inbox slot = position in that rank's ghost list), ordered by (row, rank).  Pure host code, every rank computes its own plan
+// from the same partition.  Two-pass protocol: with any output pointer null only sizes[] is filled
+// (sizes = { n_owned, n_export, n_ghost, n_subscriptions, max_export }); capacities are then exactly those sizes.
+int nb_shard_build_plan(const uint32_t* owner, uint32_t n, const uint32_t* ghost_off, const uint32_t* ghost_ids, uint32_t world, uint32_t rank,
+						uint32_t sizes[5], uint32_t* owned_ids, uint32_t* export_local, uint32_t* sub_off, uint32_t* sub_rank, uint32_t* sub_slot,
+						uint32_t* ghost_local, uint32_t* ghost_src) {
+	if (!owner || !ghost_off || !sizes || rank >= world || !world) return NB_ERR_ARGUMENT;
+	if (ghost_off[world] && !ghost_ids) return NB_ERR_ARGUMENT;
+	std::vector<uint8_t> exported(n, 0);
+	for (u32 k = 0; k < ghost_off[world]; ++k) { if (ghost_ids[k] >= n) return NB_ERR_ARGUMENT; exported[ghost_ids[k]] = 1; }
+	// position of every exported body in its owner's export list, export counts per rank, local index of this rank's owned bodies
+	std::vector<u32> n_exp(world, 0), pos_in_export(n, 0), lid(n, 0);
+	u32 n_owned = 0;
+	for (u32 i = 0; i < n; ++i) {
+		if (owner[i] >= world) return NB_ERR_ARGUMENT;
+		if (exported[i]) pos_in_export[i] = n_exp[owner[i]]++;
+		if (owner[i] == rank) lid[i] = 1 + n_owned++;
+	}
+	u32 max_export = 1;
+	for (u32 r = 0; r < world; ++r) max_export = std::max(max_export, n_exp[r]);
+	const u32 n_export = n_exp[rank], n_ghost = ghost_off[rank + 1] - ghost_off[rank];
+	u32 n_sub = 0;
+	for (u32 p = 0; p < world; ++p) if (p != rank) for (u32 k = ghost_off[p]; k < ghost_off[p + 1]; ++k) n_sub += owner[ghost_ids[k]] == rank;
+	sizes[0] = n_owned; sizes[1] = n_export; sizes[2] = n_ghost; sizes[3] = n_sub; sizes[4] = max_export;
+	if (!owned_ids || !export_local || !sub_off || !sub_rank || !sub_slot || !ghost_local || !ghost_src) return NB_OK;
+	for (u32 i = 0, k = 0, e = 0; i < n; ++i) if (owner[i] == rank) { owned_ids[k++] = i; if (exported[i]) export_local[e++] = lid[i]; }
+	for (u32 j = 0; j < n_ghost; ++j) {
+		const u32 g = ghost_ids[ghost_off[rank] + j];
+		if (owner[g] == rank) return NB_ERR_ARGUMENT;   // a rank's own body among its ghosts
+		ghost_local[j] = 1 + n_owned + j;
+		ghost_src[j] = owner[g] * max_export + pos_in_export[g];
+	}
+	// subscribers by export row: counting sort on the row; ranks ascend inside a row because p ascends in both passes
+	for (u32 k = 0; k <= n_export; ++k) sub_off[k] = 0;
+	for (u32 p = 0; p < world; ++p) if (p != rank) for (u32 k = ghost_off[p]; k < ghost_off[p + 1]; ++k) { const u32 g = ghost_ids[k]; if (owner[g] == rank) ++sub_off[pos_in_export[g] + 1]; }
+	for (u32 k = 0; k < n_export; ++k) sub_off[k + 1] += sub_off[k];
+	std::vector<u32> cursor(sub_off, sub_off + n_export);
+	for (u32 p = 0; p < world; ++p) if (p != rank) for (u32 k = ghost_off[p]; k < ghost_off[p + 1]; ++k) {
+		const u32 g = ghost_ids[k];
+		if (owner[g] == rank) { const u32 at = cursor[pos_in_export[g]]++; sub_rank[at] = p; sub_slot[at] = k - ghost_off[p]; }
+	}
+	return NB_OK;
+}
+
+
 }  // extern "C"

@@ -83,7 +83,17 @@ def local_scene(g, owned, ghosts):
 
 
 def exchange_plan(part, rank, n_bodies):
-    """The arrays nb_shard_plan takes for `rank` (local body order: [world body, owned..., ghosts...]; ghost j uses inbox slot j)."""
+    """The arrays nb_shard_plan takes for `rank` (local body order: [world body, owned..., ghosts...]; ghost j uses inbox slot j), built by
+    the C++ host (nb_shard_build_plan); exchange_plan_numpy is the same rule restated in numpy (tests compare the two)."""
+    from . import shard_build_plan
+    p = shard_build_plan(part["owner"], [g - 1 for g in part["ghosts"]], rank)
+    assert np.array_equal(p["owned_ids"].astype(np.int64) + 1, part["owned"][rank])
+    del p["owned_ids"]
+    return p
+
+
+def exchange_plan_numpy(part, rank, n_bodies):
+    """exchange_plan restated in numpy (test infrastructure for nb_shard_build_plan)."""
     world = len(part["owned"])
     exp, ghosts, owned = part["export"], part["ghosts"], part["owned"]
     max_export = max(1, max(len(e) for e in exp))

@@ -234,3 +234,28 @@ def test_partition_edge_cases_ties_tiny_inputs_and_capacity_retry():
     _, g2 = _numpy_partition(pos, rad, 2, 2, 0.5)
     for k in range(4):
         assert np.array_equal(ids[off[k]:off[k + 1]], g2[k])
+
+
+def test_cxx_exchange_plan_equals_the_numpy_restatement():
+    """nb_shard_build_plan (C++ host) against shard.exchange_plan_numpy on a real partition, for every rank of several grids, with and without
+    balance iterations; plus the degenerate cases: one rank, a rank without ghosts, a rank that exports nothing."""
+    g = scenes.box_drop(4000, iterations=4, seed=5)
+    for world, grid, balance in ((1, None, 0), (2, None, 0), (4, None, 3), (8, (4, 2), 0), (6, (2, 3), 2)):
+        p = shard.partition(g, world, margin=0.5, grid=grid, balance=balance)
+        for r in range(world):
+            a = shard.exchange_plan(p, r, g.n_bodies); b = shard.exchange_plan_numpy(p, r, g.n_bodies)
+            assert a["max_export"] == b["max_export"]
+            for k in ("export_local", "sub_off", "sub_rank", "sub_slot", "ghost_local", "ghost_src"):
+                assert np.array_equal(np.asarray(a[k], np.int64), np.asarray(b[k], np.int64)), (world, r, k)
+    # hand-made partition: 6 bodies, 3 ranks; rank 2 owns body 5 only and nobody needs it; rank 0 has no ghosts
+    part = dict(owner=np.array([0, 0, 1, 1, 1, 2]), owned=[np.array([1, 2]), np.array([3, 4, 5]), np.array([6])],
+                ghosts=[np.zeros(0, np.int64), np.array([1, 2]), np.array([2, 4])])
+    exported = np.zeros(7, bool)
+    for gl in part["ghosts"]:
+        exported[gl] = True
+    part["export"] = [o[exported[o]] for o in part["owned"]]
+    for r in range(3):
+        a = shard.exchange_plan(part, r, 7); b = shard.exchange_plan_numpy(part, r, 7)
+        assert a["max_export"] == b["max_export"] == 2
+        for k in ("export_local", "sub_off", "sub_rank", "sub_slot", "ghost_local", "ghost_src"):
+            assert np.array_equal(np.asarray(a[k], np.int64), np.asarray(b[k], np.int64)), (r, k, a[k], b[k])
