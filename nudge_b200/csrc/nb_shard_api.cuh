@@ -11,6 +11,7 @@ struct nb_shard {
 	u32* epoch; u32* done;
 	// plan (device copies)
 	u32* d_export_local; u32* d_sub_off; uint2* d_sub_tgt; u32* d_ghost_local; u32* d_ghost_src; unsigned char* d_is_ghost;
+	int flow_wide;   // k_solve_flow with the 256-bit hand-off of its local rows (NB_SOLVE_FLOW_WIDE=1; off by default: not yet run on several GPUs)
 	int fuse;   // 0: exchange kernels between the solver launches; 1: exchange fused into the working-copy kernels; 2: hand-over inside ONE solver launch (k_solve_flow)
 	// dataflow hand-over (fuse == 2): pass-indexed inbox behind the per-sweep one in the same IPC allocation
 	u32 passes_cap; size_t inbox2_offset; float4** peer_inbox2_dev; u32* d_export_row; u32* d_ghost_slot; int flow_blocks;
@@ -62,6 +63,7 @@ int nb_shard_create(nb_context* ctx, uint32_t rank, uint32_t world, const void* 
 	ALLOC(sh->d_export_local, sh->cap_export); ALLOC(sh->d_sub_off, (size_t)sh->cap_export + 1); ALLOC(sh->d_sub_tgt, sh->cap_sub);
 	ALLOC(sh->d_ghost_local, sh->cap_ghost); ALLOC(sh->d_ghost_src, sh->cap_ghost); ALLOC(sh->d_is_ghost, ctx->cfg.max_bodies);
 	{ const char* e = getenv("NB_SHARD_FUSE"); sh->fuse = e ? atoi(e) : 2; }
+	{ const char* e = getenv("NB_SOLVE_FLOW_WIDE"); sh->flow_wide = e ? atoi(e) != 0 : 0; }
 	ALLOC(sh->d_export, 2 * (size_t)export_capacity); ALLOC(sh->d_gather, 2 * (size_t)export_capacity * world);
 	sh->peers.assign(world, nullptr); sh->peers[rank] = sh->inbox;
 	sh->graph_enabled = ctx->graph_enabled;
@@ -219,8 +221,8 @@ static int shard_solve_flow(nb_shard* sh, uint32_t iterations, cudaStream_t st) 
 	const u32* epoch = sh->epoch; long long timeout = sh->pull_timeout_cycles;
 	void* args[] = { &R, &impulses, &mw, &sweeps, &hop, &counts, &X, (void*)&P, &epoch, &timeout };
 	timing_begin(ctx, st);
-	if (ctx->coop_launch && (!ctx->capturing || ctx->graph_coop)) SCK(cudaLaunchCooperativeKernel(ctx->solve_wide ? (void*)k_solve_flow<true> : (void*)k_solve_flow<false>, dim3(sh->flow_blocks), dim3(NB_BLOCK), args, 0, st));
-	else if (ctx->solve_wide) k_solve_flow<true><<<sh->flow_blocks, NB_BLOCK, 0, st>>>(R, impulses, mw, sweeps, hop, counts, X, P, epoch, timeout);
+	if (ctx->coop_launch && (!ctx->capturing || ctx->graph_coop)) SCK(cudaLaunchCooperativeKernel(sh->flow_wide ? (void*)k_solve_flow<true> : (void*)k_solve_flow<false>, dim3(sh->flow_blocks), dim3(NB_BLOCK), args, 0, st));
+	else if (sh->flow_wide) k_solve_flow<true><<<sh->flow_blocks, NB_BLOCK, 0, st>>>(R, impulses, mw, sweeps, hop, counts, X, P, epoch, timeout);
 	else k_solve_flow<false><<<sh->flow_blocks, NB_BLOCK, 0, st>>>(R, impulses, mw, sweeps, hop, counts, X, P, epoch, timeout);
 	timing_end(ctx, st);
 	++ctx->launches;
