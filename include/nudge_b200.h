@@ -132,6 +132,11 @@ int nb_shard_partition(const float* pos_xyz, const float* radius, uint32_t n, ui
 int nb_shard_build_plan(const uint32_t* owner, uint32_t n, const uint32_t* ghost_off, const uint32_t* ghost_ids, uint32_t world, uint32_t rank,
                         uint32_t sizes[5], uint32_t* owned_ids, uint32_t* export_local, uint32_t* sub_off /* n_export + 1 */, uint32_t* sub_rank, uint32_t* sub_slot,
                         uint32_t* ghost_local, uint32_t* ghost_src);
+/* The colliders of one rank's local scene ([world body, owned..., ghosts...]) in the global collider order and the local index of their
+ * bodies; host code, two passes (sizes = { kept boxes, kept spheres }). */
+int nb_shard_local_scene(const uint32_t* owned_ids, uint32_t n_owned, const uint32_t* ghost_ids, uint32_t n_ghost, uint32_t n_bodies_global,
+                         const uint32_t* box_body, uint32_t n_boxes, const uint32_t* sphere_body, uint32_t n_spheres, uint32_t sizes[2],
+                         uint32_t* box_sel, uint32_t* box_local_body, uint32_t* sphere_sel, uint32_t* sphere_local_body);
 
 /* The simulation step, device resident.  Same order of calls as example/main.cpp:274-328. */
 int nb_collide(nb_context*, void* stream);

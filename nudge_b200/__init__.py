@@ -21,7 +21,7 @@ EXPORTS = ["nb_create", "nb_destroy", "nb_last_error", "nb_upload_bodies", "nb_u
            "nb_shard_step", "nb_shard_graph_active", "nb_shard_partition", "nb_shard_debug_no_exchange",
            "nb_set_solver_mode", "nb_get_solver_mode", "nb_debug_timing_enable", "nb_debug_timing",
            "nb_stream_create", "nb_stream_destroy", "nb_stream_synchronize", "nb_save_state", "nb_load_state", "nb_state_info",
-           "nb_upload_constraint_rows", "nb_download_constraint_rows", "nb_instance_matrices", "nb_shard_build_plan"]
+           "nb_upload_constraint_rows", "nb_download_constraint_rows", "nb_instance_matrices", "nb_shard_build_plan", "nb_shard_local_scene"]
 
 
 class Config(C.Structure):
@@ -93,6 +93,7 @@ def load_library():
         lib.nb_download_constraint_rows.argtypes = [V, V, C.c_uint32, V]
         lib.nb_instance_matrices.argtypes = [V, V, C.c_uint32, C.c_int, V, V]
         lib.nb_shard_build_plan.argtypes = [V, C.c_uint32, V, V, C.c_uint32, C.c_uint32, V, V, V, V, V, V, V, V]
+        lib.nb_shard_local_scene.argtypes = [V, C.c_uint32, V, C.c_uint32, C.c_uint32, V, C.c_uint32, V, C.c_uint32, V, V, V, V, V]
         _lib = lib
     return _lib
 
@@ -155,6 +156,26 @@ def shard_build_plan(owner, ghost_lists, rank):
         raise NudgeError("nb_shard_build_plan failed (%d)" % r)
     return dict(owned_ids=owned[:n_owned], export_local=exp[:n_export], sub_off=so[:n_export + 1], sub_rank=sr[:n_sub], sub_slot=ss[:n_sub],
                 ghost_local=gl[:n_ghost], ghost_src=gs[:n_ghost], max_export=max_export)
+
+
+def shard_local_scene(owned_ids, ghost_ids, n_bodies_global, box_body, sphere_body):
+    """nb_shard_local_scene (C++ host code): (box_sel, box_local_body, sphere_sel, sphere_local_body) for the local scene
+    [world body, owned_ids + 1 ..., ghost_ids + 1 ...] (ids 0-based as in shard_partition)."""
+    lib = load_library()
+    o = np.ascontiguousarray(owned_ids, np.uint32); g = np.ascontiguousarray(ghost_ids, np.uint32)
+    bb = np.ascontiguousarray(box_body, np.uint32); sb = np.ascontiguousarray(sphere_body, np.uint32)
+    P = lambda a: abi.ptr(a) if len(a) else None
+    sizes = (C.c_uint32 * 2)()
+    r = lib.nb_shard_local_scene(P(o), len(o), P(g), len(g), int(n_bodies_global), P(bb), len(bb), P(sb), len(sb), sizes, None, None, None, None)
+    if r != 0:
+        raise NudgeError("nb_shard_local_scene failed (%d)" % r)
+    kb, ks = int(sizes[0]), int(sizes[1])
+    A = lambda k: np.zeros(max(k, 1), np.uint32)
+    bsel, bloc, ssel, sloc = A(kb), A(kb), A(ks), A(ks)
+    r = lib.nb_shard_local_scene(P(o), len(o), P(g), len(g), int(n_bodies_global), P(bb), len(bb), P(sb), len(sb), sizes, abi.ptr(bsel), abi.ptr(bloc), abi.ptr(ssel), abi.ptr(sloc))
+    if r != 0:
+        raise NudgeError("nb_shard_local_scene failed (%d)" % r)
+    return bsel[:kb], bloc[:kb], ssel[:ks], sloc[:ks]
 
 
 class Sim(abi.HostState):

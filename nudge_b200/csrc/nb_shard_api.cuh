@@ -461,4 +461,33 @@ int nb_shard_build_plan(const uint32_t* owner, uint32_t n, const uint32_t* ghost
 }
 
 
+// Which colliders a rank's local scene holds and where their bodies sit locally.  Local body order: [world body (global 0), owned bodies,
+// ghosts]; owned_ids / ghost_ids are 0-based like nb_shard_partition's (global body = id + 1).  A collider is kept if its body is one of
+// those, in the global collider order (so contact tags order contacts the way the global scene would).  box_body / sphere_body = the
+// global body of every collider (nb_transform.body).  Two passes like nb_shard_build_plan: with any output null only
+// sizes = { kept boxes, kept spheres } is filled.  box_sel / sphere_sel = kept collider indices (ascending), *_local_body = their local body.
+int nb_shard_local_scene(const uint32_t* owned_ids, uint32_t n_owned, const uint32_t* ghost_ids, uint32_t n_ghost, uint32_t n_bodies_global,
+						 const uint32_t* box_body, uint32_t n_boxes, const uint32_t* sphere_body, uint32_t n_spheres, uint32_t sizes[2],
+						 uint32_t* box_sel, uint32_t* box_local_body, uint32_t* sphere_sel, uint32_t* sphere_local_body) {
+	if (!sizes || (n_owned && !owned_ids) || (n_ghost && !ghost_ids) || (n_boxes && !box_body) || (n_spheres && !sphere_body) || !n_bodies_global) return NB_ERR_ARGUMENT;
+	std::vector<u32> lid(n_bodies_global, NB_NONE);
+	lid[0] = 0;
+	for (u32 k = 0; k < n_owned; ++k) { if (owned_ids[k] + 1 >= n_bodies_global) return NB_ERR_ARGUMENT; lid[owned_ids[k] + 1] = 1 + k; }
+	for (u32 k = 0; k < n_ghost; ++k) { if (ghost_ids[k] + 1 >= n_bodies_global || lid[ghost_ids[k] + 1] != NB_NONE) return NB_ERR_ARGUMENT; lid[ghost_ids[k] + 1] = 1 + n_owned + k; }
+	u32 kb = 0, ks = 0;
+	const bool fill = box_sel && box_local_body && sphere_sel && sphere_local_body;
+	for (u32 i = 0; i < n_boxes; ++i) {
+		if (box_body[i] >= n_bodies_global) return NB_ERR_ARGUMENT;
+		const u32 l = lid[box_body[i]];
+		if (l != NB_NONE) { if (fill) { box_sel[kb] = i; box_local_body[kb] = l; } ++kb; }
+	}
+	for (u32 i = 0; i < n_spheres; ++i) {
+		if (sphere_body[i] >= n_bodies_global) return NB_ERR_ARGUMENT;
+		const u32 l = lid[sphere_body[i]];
+		if (l != NB_NONE) { if (fill) { sphere_sel[ks] = i; sphere_local_body[ks] = l; } ++ks; }
+	}
+	sizes[0] = kb; sizes[1] = ks;
+	return NB_OK;
+}
+
 }  // extern "C"

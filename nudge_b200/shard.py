@@ -65,18 +65,18 @@ def local_scene(g, owned, ghosts):
     """Local Scene of one rank: body 0 (static world) + owned + ghosts, and every collider (box or sphere) that sits on one of them,
     in the global collider order.  Colliders keep their GLOBAL tag, so every rank orders contacts the way the global scene would
     (box tags < sphere tags as in example/main.cpp:171)."""
+    from . import shard_local_scene
     gids = np.concatenate([[0], owned, ghosts]).astype(np.int64)
     n = len(gids)
-    lid = np.full(g.n_bodies, -1, np.int64); lid[gids] = np.arange(n)
-    bb, sb = g.box_transforms["body"].astype(np.int64), g.sphere_transforms["body"].astype(np.int64)
-    kb, ks = lid[bb] >= 0, lid[sb] >= 0
-    s = S.Scene(n, int(kb.sum()), int(ks.sum()))
+    # which colliders sit on those bodies, and the local index of their bodies: the C++ host (nb_shard_local_scene)
+    kb, lb, ks, ls = shard_local_scene(np.asarray(owned, np.int64) - 1, np.asarray(ghosts, np.int64) - 1, g.n_bodies, g.box_transforms["body"], g.sphere_transforms["body"])
+    s = S.Scene(n, len(kb), len(ks))
     s.name = g.name + "_shard"
     s.transforms[:] = g.transforms[gids]; s.properties[:] = g.properties[gids]; s.momentum[:] = g.momentum[gids]; s.idle[:] = g.idle[gids]
     s.box_data[:] = g.box_data[kb]; s.box_transforms[:] = g.box_transforms[kb]; s.box_tags[:] = g.box_tags[kb]
-    s.box_transforms["body"] = lid[bb[kb]].astype(np.uint32)
+    s.box_transforms["body"] = lb
     s.sphere_data[:] = g.sphere_data[ks]; s.sphere_transforms[:] = g.sphere_transforms[ks]; s.sphere_tags[:] = g.sphere_tags[ks]
-    s.sphere_transforms["body"] = lid[sb[ks]].astype(np.uint32)
+    s.sphere_transforms["body"] = ls
     for k in ("time_step", "iterations", "gravity", "damping"):
         setattr(s, k, getattr(g, k))
     return s, gids

@@ -259,3 +259,32 @@ def test_cxx_exchange_plan_equals_the_numpy_restatement():
         assert a["max_export"] == b["max_export"] == 2
         for k in ("export_local", "sub_off", "sub_rank", "sub_slot", "ghost_local", "ghost_src"):
             assert np.array_equal(np.asarray(a[k], np.int64), np.asarray(b[k], np.int64)), (r, k, a[k], b[k])
+
+
+def test_cxx_local_scene_equals_the_numpy_rule_on_a_mixed_scene():
+    """nb_shard_local_scene (C++ host) against the rule restated in numpy: the colliders kept are those whose body is the world body, an owned
+    body or a ghost, in the global collider order, with the local index of that body — boxes and spheres, several colliders on one body."""
+    import nudge_b200
+    rng = np.random.default_rng(2)
+    g = scenes.demo_scene(300, 200, iterations=4, seed=4)
+    # put a second collider on some bodies (a sphere riding on a box body) and a second box on the world body
+    g.sphere_transforms["body"][:50] = g.box_transforms["body"][1:51]
+    g.box_transforms["body"][5] = 0
+    p = shard.partition(g, 4, margin=0.5, balance=2)
+    for r in range(4):
+        owned, ghosts = p["owned"][r], p["ghosts"][r]
+        s, gids = shard.local_scene(g, owned, ghosts)
+        lid = np.full(g.n_bodies, -1, np.int64); lid[gids] = np.arange(len(gids))
+        bb, sb = g.box_transforms["body"].astype(np.int64), g.sphere_transforms["body"].astype(np.int64)
+        kb, ks = lid[bb] >= 0, lid[sb] >= 0
+        assert s.n_boxes == kb.sum() and s.n_spheres == ks.sum() and s.n_bodies == 1 + len(owned) + len(ghosts)
+        assert np.array_equal(s.box_tags, g.box_tags[kb]) and np.array_equal(s.sphere_tags, g.sphere_tags[ks])
+        assert np.array_equal(s.box_transforms["body"], lid[bb[kb]]) and np.array_equal(s.sphere_transforms["body"], lid[sb[ks]])
+        assert s.box_data.tobytes() == g.box_data[kb].tobytes() and s.sphere_data.tobytes() == g.sphere_data[ks].tobytes()
+        assert s.transforms.tobytes() == g.transforms[gids].tobytes()
+    # argument errors are reported, not overrun: a ghost that is also owned, a collider on a body beyond the scene
+    import ctypes as C
+    with __import__("pytest").raises(nudge_b200.NudgeError):
+        nudge_b200.shard_local_scene(np.array([0, 1]), np.array([1]), 5, np.array([1, 2]), np.zeros(0, np.uint32))
+    with __import__("pytest").raises(nudge_b200.NudgeError):
+        nudge_b200.shard_local_scene(np.array([0]), np.zeros(0, np.uint32), 3, np.array([7]), np.zeros(0, np.uint32))
