@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, cycle n: scheduler inputs bucket-major (coalesced loads for the replay warp)
+# (record of a measurement: the bucket-major layout it measured was reverted)
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -4
 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-throughput-leg > gpurun_out/r02n_c2.json 2> gpurun_out/r02n_c2.err

@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, cycle p: k_solve with two polls in flight per lane (NB_SOLVE_POLL=2), parity under it and A/B on the same box
+# (record of a measurement: the NB_SOLVE_POLL variants it selects were dropped from the source afterwards, see profiles/r02pq_solver_polling_experiments.txt)
 mkdir -p gpurun_out
 NB_SOLVE_POLL=2 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 2>&1 | tail -3
 for pv in 1 2 1 2; do

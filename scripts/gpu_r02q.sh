@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, cycle q: k_solve with a per-lane poll throttle (NB_SOLVE_POLL=3): parity under it, A/B on the same box for three lane-hop settings
+# (record of a measurement: the NB_SOLVE_POLL variants it selects were dropped from the source afterwards, see profiles/r02pq_solver_polling_experiments.txt)
 mkdir -p gpurun_out
 NB_SOLVE_POLL=3 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 2>&1 | tail -3
 run() { # label, env...
