@@ -288,3 +288,29 @@ def test_cxx_local_scene_equals_the_numpy_rule_on_a_mixed_scene():
         nudge_b200.shard_local_scene(np.array([0, 1]), np.array([1]), 5, np.array([1, 2]), np.zeros(0, np.uint32))
     with __import__("pytest").raises(nudge_b200.NudgeError):
         nudge_b200.shard_local_scene(np.array([0]), np.zeros(0, np.uint32), 3, np.array([7]), np.zeros(0, np.uint32))
+
+
+def test_world4_gloo_two_by_two_cells_ghosts_follow_their_owners():
+    """Four ranks (2 x 2 cells: a body near the centre is a ghost of three ranks, corner neighbours exchange diagonally) over gloo with the CPU
+    oracle per rank, re-partitioned on the way: every rank gathers the same global state, and every ghost row equals its owner's row - the
+    subscriber lists of nb_shard_build_plan at work with more than two ranks."""
+    a = shard_util.run_ranks(4, "oracle", steps=7, reshard_every=3, n_boxes=900)
+    for r in range(1, 4):
+        assert np.array_equal(a[0]["transforms"].view(np.uint8), a[r]["transforms"].view(np.uint8))
+        assert np.array_equal(a[0]["momentum"].view(np.uint8), a[r]["momentum"].view(np.uint8))
+    assert np.isfinite(a[0]["transforms"]["position"]).all()
+    owner_row = {}
+    for r in range(4):
+        gids, n_owned = a[r]["gids"], int(a[r]["n_owned"])
+        for i in range(1, 1 + n_owned):
+            owner_row[int(gids[i])] = a[r]["last_local_mom"][i]["velocity"].copy()
+    shared = 0
+    multi = {}
+    for r in range(4):
+        gids, n_owned = a[r]["gids"], int(a[r]["n_owned"])
+        assert int(a[r]["counts"][1]) == len(gids) - 1 - n_owned > 0
+        for i in range(1 + n_owned, len(gids)):
+            assert np.array_equal(a[r]["last_local_mom"][i]["velocity"], owner_row[int(gids[i])]), (r, int(gids[i]))
+            multi[int(gids[i])] = multi.get(int(gids[i]), 0) + 1
+            shared += 1
+    assert shared > 0 and max(multi.values()) >= 2      # some body is a ghost on more than one rank
