@@ -64,3 +64,14 @@ def test_staged_calls_equal_fused_reference_step():
         a.step(); b.step_staged()
     assert np.array_equal(a.transforms.view(np.uint8), b.transforms.view(np.uint8))
     assert np.array_equal(a.momentum.view(np.uint8), b.momentum.view(np.uint8))
+
+
+@needs_ref
+def test_random_scenes_differential_fuzz_seeded():
+    """A bounded, seeded run of tests/fuzz_oracle_vs_ref.py (random scenes, iterations, connections, sleep): every stage bit for bit."""
+    from tests import fuzz_oracle_vs_ref as F
+    rng = np.random.default_rng(77)
+    for k in range(120):
+        s = F.random_scene(rng)
+        err = F.run_scene(s, rng, int(rng.integers(5, 40)))
+        assert err is None, "scene %d (%s): %s" % (k, s.name, err[:600])
