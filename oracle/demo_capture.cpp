@@ -45,8 +45,11 @@ void demo_capture_before_simulate() {
 	if (capture_file) return;
 	// the demo turns FTZ/DAZ on for speed (example/main.cpp:338-339); the parity harness runs every implementation with denormals kept
 	// (SURVEY.md section 8c), so the recorded frames are computed that way too — an MXCSR setting, not a change to the demo
-	_MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_OFF);
-	_MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_OFF);
+	// (DEMO_CAPTURE_KEEP_FTZ=1 leaves the demo's own setting in place: the second fixture, pinned by the oracle's FTZ mode)
+	if (!getenv("DEMO_CAPTURE_KEEP_FTZ")) {
+		_MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_OFF);
+		_MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_OFF);
+	}
 	const char* out = getenv("DEMO_CAPTURE_OUT");
 	if (!out) { fprintf(stderr, "set DEMO_CAPTURE_OUT and DEMO_CAPTURE_FRAMES\n"); exit(2); }
 	capture_file = fopen(out, "wb");
