@@ -32,3 +32,18 @@ def test_bench_refuses_to_run_the_gpu_arm_without_a_gpu():
         pytest.skip("a GPU is present")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and not [l for l in r.stdout.splitlines() if l.strip().startswith("{")], r.stdout[-500:]
+
+
+def test_roofline_table_tool_reproduces_the_committed_table():
+    """scripts/roofline_table.py on the committed ncu CSV and bench line regenerates profiles/r02f_roofline_c2.md (the per-kernel roofline
+    table is an output of committed inputs, not hand-written)."""
+    csv = os.path.join(ROOT, "profiles", "r02f_kernels_c2_metrics.csv"); line = os.path.join(ROOT, "profiles", "r02f_bench_c2.json")
+    want = os.path.join(ROOT, "profiles", "r02f_roofline_c2.md")
+    if not (os.path.exists(csv) and os.path.exists(line) and os.path.exists(want)):
+        pytest.skip("profiles not present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "roofline_table.py"), csv, line, "--steps", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-1000:]
+    rows = lambda text: [l for l in text.splitlines() if l.startswith("| `")]
+    got, ref = rows(r.stdout), rows(open(want).read())
+    assert len(got) == len(ref) > 40
+    assert got[0].startswith("| `k_solve`") and got == ref
