@@ -117,3 +117,25 @@ def test_shipped_library_contains_the_blackwell_instructions_the_design_claims()
     assert "LDG.E.128.STRONG.GPU" in narrow and "ENL2.256" not in narrow
     flow = body("k_solve_flowILb0E")
     assert "LDG.E.128.STRONG.SYS" in flow and "STG.E.128.STRONG.SYS" in flow
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under nudge_b200/, include/, integration/ or tools/ may import, link or execute it, and bench.py
+    only in its CPU legs (cpu_baseline_sample, dropin_sample, run_reference)."""
+    import ast
+    for d in ("nudge_b200", "include", "integration", "tools"):
+        for base, _, files in os.walk(os.path.join(ROOT, d)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".sh")):
+                    text = open(os.path.join(base, f), errors="replace").read()
+                    for bad in ("import oracle", "from oracle", "oracle/", "liboracle", "pyoracle", "pyref", "libnudge_ref"):
+                        assert bad not in text, "%s mentions %r" % (os.path.join(base, f), bad)
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    allowed = {"cpu_baseline_sample", "dropin_sample", "run_reference"}
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        uses = any((isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle")) or (isinstance(n, ast.Import) and any(a.name.startswith("oracle") for a in n.names)) or
+                   (isinstance(n, ast.Constant) and n.value == "oracle") for n in ast.walk(fn))
+        if uses:
+            assert fn.name in allowed, "bench.py:%s uses the oracle" % fn.name
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any((getattr(n, "module", None) or "").startswith("oracle") or any(a.name.startswith("oracle") for a in n.names) for n in top)
