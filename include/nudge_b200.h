@@ -11,6 +11,12 @@
  *   nb_advance                      <- nudge::advance                    nudge.h:146, nudge.cpp:4886-4926
  *   nb_apply_gravity_damping        <- the user loop of example/main.cpp:291-305
  *   nb_step                         <- simulate(), example/main.cpp:274-328 (one sub-step)
+ *   nb_upload_connections           <- BodyConnections of nudge::collide  nudge.h:108-111, example/main.cpp:285
+ *   nb_upload_contacts              <- "custom contacts can be added here" example/main.cpp:288
+ *   nb_upload_constraint_rows       <- "custom constraint impulses"        example/main.cpp:316
+ *   nb_instance_matrices            <- the draw loops of render()          example/main.cpp:224-268 (helpers :53-110)
+ *   nb_save_state / nb_load_state   <- the caller-owned PODs               nudge.h:73-129
+ *   nb_shard_*                      <- no reference counterpart (the reference is single threaded): SURVEY.md section 8e
  *
  * Data layout: the reference's caller-owned SoA structs (nudge.h:29-129) with every index-carrying field
  * widened to 32 bits (the reference caps at 8192 colliders / 65535 bodies, nudge.cpp:3010, nudge.h:68-71):
